@@ -1,0 +1,372 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> shared (128B swizzle) -> tcgen05.mma (TMEM fp32
+// accumulators, double buffered) -> tcgen05.ld epilogue -> swizzled staging -> TMA store / TMA reduce-add.
+//
+//   C[M,N] (+)= A[M,K] * B[N,K]^T (+ bias[N])
+//
+// Replaces the cuBLASLt calls behind nn.Linear / nn.Conv2d(k=s=p) on the reference hot path
+// (reference: src/diffulab/networks/denoisers/mmdit.py:70-73,260-264,539,697-699 and their autograd mirrors).
+// Operand "major" flags let one kernel serve forward (K-major x K-major), dgrad (K-major x MN-major: B is the
+// row-major weight read along its other dimension) and wgrad (MN-major x MN-major: dY^T * X straight from the
+// row-major activations), so no transposed copies are ever materialised.
+#include "common.cuh"
+#include "ptx.cuh"
+#include <cudaTypedefs.h>
+
+namespace {
+
+constexpr int BM = 128;            // UMMA M (cta_group::1)
+constexpr int BK = 64;             // one 128-byte swizzle atom of bf16 along K
+constexpr int UMMA_K = 16;
+constexpr int A_TILE_BYTES = BM * BK * 2;            // 16 KB
+constexpr int MN_BLOCK_BYTES = 64 * BK * 2;          // one 64(MN) x 64(K) TMA box of an MN-major operand: 8 KB
+constexpr int EPI_WARPS = 4;
+constexpr int EPI_BUF_BYTES = 32 * 128;              // 32 rows x 128 B per warp per buffer
+constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF_BYTES;  // 32 KB
+constexpr int SMEM_LIMIT = 232448;                   // 227 KB opt-in maximum per CTA
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int STAGES_RAW = (SMEM_LIMIT - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256;
+  static_assert(STAGES >= 3, "pipeline too shallow");
+  static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget exceeded");
+};
+
+enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_ADD = 2 };
+
+struct TileCoord {
+  int m_blk, n_blk, kb0, kb1, ks;
+};
+__device__ __forceinline__ TileCoord decode_tile(int t, int mb, int nb, int kb_total, int kb_per) {
+  TileCoord c;
+  const int per_split = mb * nb;
+  c.ks = t / per_split;
+  const int r = t - c.ks * per_split;
+  c.m_blk = r / nb;
+  c.n_blk = r - c.m_blk * nb;
+  c.kb0 = c.ks * kb_per;
+  c.kb1 = min(c.kb0 + kb_per, kb_total);
+  return c;
+}
+
+template <int BN, bool A_MN, bool B_MN, int OUT>
+__global__ void __launch_bounds__(256, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K,
+                    int split_k) {
+  using C = Cfg<BN>;
+  constexpr int NST = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + NST * A_TILE_BYTES;
+  uint8_t* sE = sB + NST * C::B_TILE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sE + EPI_BYTES);
+  uint64_t* empty = full + NST;
+  uint64_t* tfull = empty + NST;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mb = (M + BM - 1) / BM, nb = (N + BN - 1) / BN;
+  const int kb_total = (K + BK - 1) / BK;
+  const int kb_per = (kb_total + split_k - 1) / split_k;
+  const int tiles = mb * nb * split_k;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NST; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull[i], 1);
+      ptx::mbar_init(&tempty[i], EPI_WARPS);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(t, mb, nb, kb_total, kb_per);
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+          uint8_t* a = sA + stage * A_TILE_BYTES;
+          uint8_t* b = sB + stage * C::B_TILE_BYTES;
+          if constexpr (!A_MN) {
+            ptx::tma_load_2d(a, &tmA, &full[stage], kb * BK, tc.m_blk * BM);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              ptx::tma_load_2d(a + i * MN_BLOCK_BYTES, &tmA, &full[stage], tc.m_blk * BM + i * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            ptx::tma_load_2d(b, &tmB, &full[stage], kb * BK, tc.n_blk * BN);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              ptx::tma_load_2d(b + i * MN_BLOCK_BYTES, &tmB, &full[stage], tc.n_blk * BN + i * 64, kb * BK);
+          }
+          if (++stage == NST) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(t, mb, nb, kb_total, kb_per);
+        ptx::mbar_wait(&tempty[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(sA + stage * A_TILE_BYTES);
+          const uint32_t b_addr = ptx::smem_u32(sB + stage * C::B_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: step 16 elements (32 B) inside the swizzle atom. MN-major: step 16 k-rows (2 KB).
+            const uint64_t adesc = A_MN ? ptx::make_smem_desc_sw128(a_addr + k * (UMMA_K * 128), MN_BLOCK_BYTES, 1024)
+                                        : ptx::make_smem_desc_sw128(a_addr + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t bdesc = B_MN ? ptx::make_smem_desc_sw128(b_addr + k * (UMMA_K * 128), MN_BLOCK_BYTES, 1024)
+                                        : ptx::make_smem_desc_sw128(b_addr + k * (UMMA_K * 2), 16, 1024);
+            ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == NST) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> swizzled smem -> TMA store =====================
+    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
+    constexpr int CH = (OUT == OUT_BF16) ? 64 : 32;  // columns per 128-byte staging row
+    uint8_t* ebase = sE + ew * (2 * EPI_BUF_BYTES);
+    int ebuf = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(t, mb, nb, kb_total, kb_per);
+      ptx::mbar_wait(&tfull[as], aphase);
+      ptx::tc_fence_after();
+      const int row0 = tc.m_blk * BM + ew * 32;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+      const bool add_bias = (bias != nullptr) && (tc.ks == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += CH) {
+        const int col0 = tc.n_blk * BN + c;
+        if (col0 >= N) break;
+        uint32_t r[CH];
+        ptx::tmem_ld32(taddr + c, r);
+        if constexpr (CH == 64) ptx::tmem_ld32(taddr + c + 32, r + 32);
+        ptx::tmem_ld_wait();
+        if (add_bias) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const float bv = (col0 + i < N) ? __ldg(bias + col0 + i) : 0.f;
+            r[i] = __float_as_uint(__uint_as_float(r[i]) + bv);
+          }
+        }
+        uint8_t* buf = ebase + ebuf * EPI_BUF_BYTES;
+        if (lane == 0) ptx::tma_wait_group_read<1>();  // the store that last read this buffer is done
+        __syncwarp();
+        uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 v;
+          if constexpr (OUT == OUT_BF16) {
+            v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+            v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+            v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+            v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+          } else {
+            v.x = r[4 * j + 0]; v.y = r[4 * j + 1]; v.z = r[4 * j + 2]; v.w = r[4 * j + 3];
+          }
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = v;  // 128B swizzle: chunk ^= row % 8
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && row0 < M) {
+          if constexpr (OUT == OUT_F32_ADD) ptx::tma_reduce_add_2d(&tmC, buf, col0, row0);
+          else ptx::tma_store_2d(&tmC, buf, col0, row0);
+          ptx::tma_commit_group();
+        }
+        ebuf ^= 1;
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+    if (lane == 0) ptx::tma_wait_group<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major tensor [outer][inner] with `ld` elements between rows.
+int encode2d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* ptr, uint64_t inner, uint64_t outer,
+             uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+  auto enc = get_encode();
+  DLB_REQUIRE(enc != nullptr, DLB_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * elem_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DLB_REQUIRE(r == CUDA_SUCCESS, DLB_ERR_DRIVER,
+              "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%llu box=%ux%u ptr=%p", (int)r,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer, ptr);
+  return DLB_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN, int OUT>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const float* bias, int M, int N, int K,
+           int split_k, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, OUT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    DLB_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(smem=%d): %s", C::SMEM_BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int mb = (M + BM - 1) / BM, nb = (N + BN - 1) / BN;
+  const int tiles = mb * nb * split_k;
+  const int grid = tiles < dlb_num_sms() ? tiles : dlb_num_sms();
+  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(ta, tb, tc, bias, M, N, K, split_k);
+  dlb_count_launch();
+  return dlb_check_launch("gemm_tcgen05");
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int dispatch_out(int out_mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const float* bias,
+                 int M, int N, int K, int split_k, cudaStream_t s) {
+  switch (out_mode) {
+    case OUT_BF16: return launch<BN, A_MN, B_MN, OUT_BF16>(ta, tb, tc, bias, M, N, K, split_k, s);
+    case OUT_F32: return launch<BN, A_MN, B_MN, OUT_F32>(ta, tb, tc, bias, M, N, K, split_k, s);
+    default: return launch<BN, A_MN, B_MN, OUT_F32_ADD>(ta, tb, tc, bias, M, N, K, split_k, s);
+  }
+}
+template <int BN>
+int dispatch_major(int a_mn, int b_mn, int out_mode, const CUtensorMap& ta, const CUtensorMap& tb,
+                   const CUtensorMap& tc, const float* bias, int M, int N, int K, int split_k, cudaStream_t s) {
+  if (!a_mn && !b_mn) return dispatch_out<BN, false, false>(out_mode, ta, tb, tc, bias, M, N, K, split_k, s);
+  if (!a_mn && b_mn) return dispatch_out<BN, false, true>(out_mode, ta, tb, tc, bias, M, N, K, split_k, s);
+  if (a_mn && !b_mn) return dispatch_out<BN, true, false>(out_mode, ta, tb, tc, bias, M, N, K, split_k, s);
+  return dispatch_out<BN, true, true>(out_mode, ta, tb, tc, bias, M, N, K, split_k, s);
+}
+
+// Relative cost of one k-block on a 128 x BN tile: tensor pipe needs 2*BN cycles, the shared-memory
+// read port (128 B/cycle) needs 128 + BN cycles; the slower one paces the main loop.
+int pick_tile_n(int M, int N, int split_k) {
+  if (N <= 64) return 64;
+  const int sms = dlb_num_sms();
+  const int cands[3] = {256, 192, 128};
+  int best = 128;
+  double best_cost = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
+    const long tiles = (long)((M + BM - 1) / BM) * ((N + bn - 1) / bn) * split_k;
+    const long waves = (tiles + sms - 1) / sms;
+    const double per_tile = (2 * bn > 128 + bn) ? 2.0 * bn : 128.0 + bn;
+    const double cost = (double)waves * per_tile;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+}  // namespace
+
+// See include/diffulab_b200.h for the contract.
+DLB_EXPORT int dlb_gemm_bf16(const void* A, const void* B, void* Cout, const float* bias, int64_t M, int64_t N,
+                             int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major,
+                             int out_mode, int split_k, int tile_n, cudaStream_t stream) {
+  DLB_REQUIRE(M > 0 && N > 0 && K > 0, DLB_ERR_SHAPE, "gemm: empty problem M=%lld N=%lld K=%lld", (long long)M,
+              (long long)N, (long long)K);
+  DLB_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), DLB_ERR_SHAPE, "gemm: dimension overflow");
+  DLB_REQUIRE(out_mode >= 0 && out_mode <= 2, DLB_ERR_UNSUPPORTED, "gemm: bad out_mode %d", out_mode);
+  DLB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, DLB_ERR_ALIGN, "gemm: lda/ldb must be multiples of 8 elements (got %lld, %lld)",
+              (long long)lda, (long long)ldb);
+  const int c_elem = out_mode == OUT_BF16 ? 2 : 4;
+  DLB_REQUIRE((ldc * c_elem) % 16 == 0, DLB_ERR_ALIGN, "gemm: ldc*elem must be a multiple of 16 bytes (ldc=%lld)",
+              (long long)ldc);
+  DLB_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)Cout % 16) == 0, DLB_ERR_ALIGN,
+              "gemm: operand pointers must be 16-byte aligned");
+  const int kb_total = (int)((K + BK - 1) / BK);
+  if (split_k < 1) split_k = 1;
+  if (split_k > 1) {
+    DLB_REQUIRE(out_mode == OUT_F32_ADD, DLB_ERR_UNSUPPORTED, "gemm: split_k>1 needs out_mode=2 (fp32 accumulate)");
+    if (split_k > kb_total) split_k = kb_total;
+    const int kb_per = (kb_total + split_k - 1) / split_k;
+    split_k = (kb_total + kb_per - 1) / kb_per;  // no empty splits
+  }
+  int bn = tile_n > 0 ? tile_n : pick_tile_n((int)M, (int)N, split_k);
+  DLB_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, DLB_ERR_UNSUPPORTED, "gemm: tile_n %d unsupported", bn);
+
+  CUtensorMap ta, tb, tc;
+  int rc;
+  // A: K-major = row-major [M][K] (ld=lda); MN-major = row-major [K][M] (ld=lda).
+  if (!a_mn_major) rc = encode2d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, K, M, lda, BK, BM);
+  else rc = encode2d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda, 64, BK);
+  if (rc) return rc;
+  if (!b_mn_major) rc = encode2d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, K, N, ldb, BK, bn);
+  else rc = encode2d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, N, K, ldb, 64, BK);
+  if (rc) return rc;
+  if (out_mode == OUT_BF16) rc = encode2d(&tc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Cout, N, M, ldc, 64, 32);
+  else rc = encode2d(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Cout, N, M, ldc, 32, 32);
+  if (rc) return rc;
+
+  switch (bn) {
+    case 64: return dispatch_major<64>(a_mn_major, b_mn_major, out_mode, ta, tb, tc, bias, M, N, K, split_k, stream);
+    case 128: return dispatch_major<128>(a_mn_major, b_mn_major, out_mode, ta, tb, tc, bias, M, N, K, split_k, stream);
+    case 192: return dispatch_major<192>(a_mn_major, b_mn_major, out_mode, ta, tb, tc, bias, M, N, K, split_k, stream);
+    default: return dispatch_major<256>(a_mn_major, b_mn_major, out_mode, ta, tb, tc, bias, M, N, K, split_k, stream);
+  }
+}

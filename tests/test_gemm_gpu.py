@@ -1,0 +1,122 @@
+"""tcgen05 GEMM vs torch.matmul (fp32 reference of the same bf16 inputs). Tolerance: bf16 output rounding
+(rel 2^-8) on top of fp32 accumulation-order noise -> relL2 <= 4e-3 (bf16 out) / 1e-5 (fp32 out)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30)).item()
+
+
+SHAPES = [
+    # M, N, K
+    (128, 128, 64),
+    (128, 256, 128),
+    (256, 192, 1152),
+    (384, 3456, 1152),
+    (512, 1152, 4608),
+    (100, 72, 40),      # ragged everything (K multiple of 8 for the 16-byte TMA stride rule)
+    (32, 16, 1152),     # skinny output (last layer)
+    (4096, 1152, 16),   # tiny K (patch embed)
+    (128, 6912, 1152),  # modulation
+]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("tile_n", [0, 64, 128, 192, 256])
+def test_gemm_nt_bf16(cuda_device, M, N, K, tile_n):
+    from diffulab_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b = torch.randn(N, K, device="cuda", generator=g).bfloat16()
+    ref = a.float() @ b.float().t()
+    out = ops.gemm(a, b, tile_n=tile_n)
+    torch.cuda.synchronize()
+    assert out.dtype == torch.bfloat16 and out.shape == (M, N)
+    assert rel_l2(out, ref) < 4e-3
+    out32 = ops.gemm(a, b, out_dtype=torch.float32, tile_n=tile_n)
+    assert rel_l2(out32, ref) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_bias(cuda_device, M, N, K):
+    from diffulab_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b = torch.randn(N, K, device="cuda", generator=g).bfloat16()
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = a.float() @ b.float().t() + bias
+    out = ops.gemm(a, b, bias=bias, out_dtype=torch.float32)
+    assert rel_l2(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(256, 192, 128), (384, 1152, 3456), (1152, 1152, 4096), (1152, 16, 2048), (16, 1152, 512), (200, 136, 72)])
+@pytest.mark.parametrize("tile_n", [0, 64, 128, 256])
+def test_gemm_majors(cuda_device, a_mn, b_mn, M, N, K, tile_n):
+    """dgrad (B read MN-major) and wgrad (both operands MN-major) straight from row-major tensors."""
+    from diffulab_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b = torch.randn(N, K, device="cuda", generator=g).bfloat16()
+    ref = a.float() @ b.float().t()
+    a_in = a.t().contiguous() if a_mn else a
+    b_in = b.t().contiguous() if b_mn else b
+    out = ops.gemm(a_in, b_in, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32, tile_n=tile_n)
+    assert rel_l2(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("split_k", [1, 2, 3, 7, 64])
+def test_gemm_accumulate_split_k(cuda_device, split_k):
+    from diffulab_b200 import ops
+
+    M, N, K = 1152, 320, 4096 + 64
+    g = torch.Generator(device="cuda").manual_seed(9)
+    a = torch.randn(K, M, device="cuda", generator=g).bfloat16()  # MN-major operands: wgrad layout
+    b = torch.randn(K, N, device="cuda", generator=g).bfloat16()
+    base = torch.randn(M, N, device="cuda", generator=g)
+    out = base.clone()
+    ops.gemm(a, b, a_mn=True, b_mn=True, out=out, accumulate=True, split_k=split_k)
+    ref = base + a.float().t() @ b.float()
+    assert rel_l2(out, ref) < 1e-5
+
+
+def test_gemm_strided_views(cuda_device):
+    """Operands and outputs that are column slices of packed buffers (qkv / modulation chunks)."""
+    from diffulab_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    packed = torch.randn(512, 3 * 384, device="cuda", generator=g).bfloat16()
+    w = torch.randn(256, 384, device="cuda", generator=g).bfloat16()
+    outbuf = torch.zeros(512, 2 * 256, device="cuda", dtype=torch.bfloat16)
+    a = packed[:, 384:768]
+    ops.gemm(a, w, out=outbuf[:, 256:])
+    ref = a.float() @ w.float().t()
+    assert rel_l2(outbuf[:, 256:], ref) < 4e-3
+    assert outbuf[:, :256].abs().max().item() == 0.0
+
+
+def test_gemm_large_perf_shape(cuda_device):
+    """DiT-XL/2 qkv projection at per-GPU batch 32 (M = 8192): full persistent multi-wave path."""
+    from diffulab_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(13)
+    a = torch.randn(8192, 1152, device="cuda", generator=g).bfloat16()
+    b = (torch.randn(3456, 1152, device="cuda", generator=g) * 0.03).bfloat16()
+    ref = a.float() @ b.float().t()
+    out = ops.gemm(a, b)
+    assert rel_l2(out, ref) < 4e-3
+
+
+def test_gemm_bad_args(cuda_device):
+    from diffulab_b200 import _lib, ops
+
+    a = torch.zeros(16, 12, device="cuda", dtype=torch.bfloat16)
+    b = torch.zeros(8, 12, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(_lib.DlbError):
+        ops.gemm(a, b)  # K=12 rows are 24 bytes: violates the 16-byte stride rule, must fail loudly
