@@ -27,7 +27,63 @@ _SIGNATURES: dict[str, list] = {
     "dlb_device_check": [],
     # C[M,N] (+)= A*B^T (+bias): A, B, C, bias, M, N, K, lda, ldb, ldc, a_mn, b_mn, out_mode, split_k, tile_n, stream
     "dlb_gemm_bf16": [p, p, p, p, i64, i64, i64, i64, i64, i64, i32, i32, i32, i32, i32, p],
+    # x, w, b, scale, shift, mod_ld, rows_per_mod, y, mean, rstd, R, d, eps, stream
+    "dlb_ln_modulate_fwd": [p, p, p, p, p, i64, i64, p, p, p, i64, i32, f32, p],
+    # dy, x, mean, rstd, w, b, scale, mod_ld, groups, rows_per_group, per_token, dres, dx, dscale, dshift, dmod_ld,
+    # dscale_tok, dshift_tok, dtok_ld, dw, db, d, stream
+    "dlb_ln_modulate_bwd": [p, p, p, p, p, p, p, i64, i64, i64, i32, p, p, p, p, i64, p, p, i64, p, p, i32, p],
+    # x, a1, a2, gate, gate_ld, rows_per_mod, out, R, d, stream
+    "dlb_gate_residual_fwd": [p, p, p, p, i64, i64, p, i64, i32, p],
+    # dout, a1, a2, gate, gate_ld, groups, rows_per_group, per_token, da, dgate, dgate_ld, dgate_tok, dtok_ld, d, stream
+    "dlb_gate_residual_bwd": [p, p, p, p, i64, i64, i64, i32, p, p, i64, p, i64, i32, p],
+    "dlb_swiglu_fwd": [p, p, i64, i32, p],
+    "dlb_swiglu_bwd": [p, p, p, i64, i32, p],
+    # qkv, ld_in, sq, sk, cos, sin, rot_half, pos_idx, pos_offset, tokens_per_sample, hd, out, ld_out, rrms, R, d, eps, stream
+    "dlb_qknorm_rope_fwd": [p, i64, p, p, p, p, i32, p, i32, i32, i32, p, i64, p, i64, i32, f32, p],
+    # dqk, ld_dqk, qkv, ld_in, sq, sk, cos, sin, rot_half, pos_idx, pos_offset, tps, hd, dqkv, ld_out, dsq, dsk, R, d, eps, stream
+    "dlb_qknorm_rope_bwd": [p, i64, p, i64, p, p, p, p, i32, p, i32, i32, i32, p, i64, p, p, i64, i32, f32, p],
+    # pos, n_axes, axis_of_pair, local_of_pair, axis_dim, base, cos, sin, P, rot_half, stream
+    "dlb_rope_table": [p, i32, p, p, p, C.c_double, p, p, i64, i32, p],
+    # segs, nseg, lse, kmask, mask_len, B, H, hd, scale, stream
+    "dlb_attn_fwd": [p, i32, p, p, i32, i32, i32, i32, f32, p],
+    # segs, nseg, lse, dsum, kmask, mask_len, B, H, hd, scale, stream
+    "dlb_attn_bwd": [p, i32, p, p, p, i32, i32, i32, i32, f32, p],
+    "dlb_cast_f32_bf16": [p, p, i64, i64, i64, p],
+    "dlb_cast_bf16_f32": [p, p, i64, p],
+    "dlb_silu_fwd": [p, i32, p, i64, p],
+    "dlb_silu_bwd": [p, i32, p, i32, p, i32, i64, p],
+    "dlb_timestep_embed": [p, p, i32, i32, f32, p],
+    "dlb_cond_combine": [p, p, p, p, p, i32, i32, p],
+    "dlb_embedding_bwd": [p, p, p, i32, i32, p],
+    "dlb_patchify": [p, p, i32, i32, i32, i32, i32, i32, p],
+    "dlb_unpatchify": [p, i64, p, i32, i32, i32, i32, i32, i32, p],
+    "dlb_patchify_grad": [p, i32, p, i64, i32, i32, i32, i32, i32, p],
+    "dlb_colsum": [p, i32, i64, p, i64, i32, p],
+    "dlb_interp": [p, p, p, p, p, i64, i64, p],
+    # pred, pred_dtype, x0, eps, xt, t, B, per_sample, loss, stream
+    "dlb_mse_fwd": [p, i32, p, p, p, p, i64, i64, p, p],
+    "dlb_mse_bwd": [p, i32, p, p, p, p, i64, i64, p, p, p],
+    "dlb_repa_cos_fwd": [p, p, i64, i32, f32, p, p],
+    "dlb_repa_cos_bwd": [p, p, i64, i32, f32, p, p, p],
+    "dlb_sprint_select": [p, i32, i32, i32, p, p, p, p],
+    "dlb_gather_rows": [p, p, p, i32, i32, i32, i32, p],
+    "dlb_restore_rows": [p, p, p, p, p, i32, i32, i32, i32, p],
+    "dlb_restore_rows_bwd": [p, p, p, p, p, p, i32, i32, i32, i32, p],
+    # x, vc, vu, v_dtype, guidance, t_curr, t_prev, x_prev, x0_est, v_out, n, stream
+    "dlb_euler_step": [p, p, p, i32, f32, f32, f32, p, p, p, i64, p],
+    # p, g, m, v, shadow, ema, ema_decay, n, lr, b1, b2, eps, wd, step, grad_scale, stream
+    "dlb_adamw_step": [p, p, p, p, p, p, f32, i64, f32, f32, f32, f32, f32, i64, f32, p],
 }
+
+
+class AttnSeg(C.Structure):
+    """Mirror of `dlb_attn_seg` (include/diffulab_b200.h)."""
+
+    _fields_ = (
+        [(n, C.c_void_p) for n in ("q", "k", "v", "o", "dout", "dq", "dk", "dv")]
+        + [(n, C.c_int64) for n in ("ldq", "ldk", "ldv", "ldo", "lddo", "lddq", "lddk", "lddv")]
+        + [("len", C.c_int32)]
+    )
 _RESTYPES = {"dlb_last_error": C.c_char_p, "dlb_launch_count": C.c_longlong, "dlb_reset_launch_count": None}
 
 

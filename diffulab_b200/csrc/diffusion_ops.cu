@@ -1,0 +1,380 @@
+// Formalisation-side kernels: rectified-flow / DDPM interpolation, velocity-target MSE (+ its gradient), REPA
+// cosine loss, SPRINT token selection / gather / restore, Euler (+CFG) sampler update, fused AdamW.
+//
+// Reference: Flow.add_noise / compute_loss diffuse/modelizations/flow.py:262-315,382-408;
+// GaussianDiffusion.add_noise gaussian_diffusion.py:313-341 (same kernel with per-sample (a,b));
+// RepaLoss.forward training/losses/repa.py:159-186; SprintDiT.drop_tokens / restore_tokens
+// networks/denoisers/sprint.py:317-387; Euler.step samplers/flow/euler.py:22-41 and the CFG combine
+// flow.py:256-260; torch.optim.AdamW as used by BaseTrainer.training_step base_trainer.py:149.
+#include "common.cuh"
+
+namespace {
+typedef __nv_bfloat16 bf16;
+
+int grid_for(int64_t n) {
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)dlb_num_sms() * 16;
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+// x_t = a_b * x0 + b_b * eps with per-sample coefficients. Flow: a = 1 - t, b = t.
+__global__ void interp_kernel(const float* __restrict__ x0, const float* __restrict__ eps, const float* __restrict__ a,
+                              const float* __restrict__ b, float* __restrict__ xt, int64_t per_sample, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = i / per_sample;
+    xt[i] = a[s] * x0[i] + b[s] * eps[i];
+  }
+}
+
+// loss_sum += sum (target - v)^2 with target = eps - x0 (flow) or eps (ddpm: x0 == nullptr);
+// v = pred (v-prediction) or (x_t - pred) / t_b (x-prediction, flow.py:300-303).
+template <typename TP>
+__global__ void __launch_bounds__(256)
+mse_fwd_kernel(const TP* __restrict__ pred, const float* __restrict__ x0, const float* __restrict__ eps,
+               const float* __restrict__ xt, const float* __restrict__ t, int64_t per_sample, int64_t total,
+               float inv_total, float* __restrict__ loss) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = (float)pred[i];
+    if (xt) v = (xt[i] - v) / t[i / per_sample];
+    const float tgt = x0 ? eps[i] - x0[i] : eps[i];
+    const float d = tgt - v;
+    acc += d * d;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(loss, acc * inv_total);
+}
+// dpred = gout * d loss / d pred
+template <typename TP>
+__global__ void mse_bwd_kernel(const TP* __restrict__ pred, const float* __restrict__ x0, const float* __restrict__ eps,
+                               const float* __restrict__ xt, const float* __restrict__ t, int64_t per_sample,
+                               int64_t total, float inv_total, const float* __restrict__ gout, TP* __restrict__ dpred) {
+  const float g = gout ? *gout : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = (float)pred[i];
+    float dv_dpred = 1.f;
+    if (xt) {
+      const float ti = t[i / per_sample];
+      v = (xt[i] - v) / ti;
+      dv_dpred = -1.f / ti;
+    }
+    const float tgt = x0 ? eps[i] - x0[i] : eps[i];
+    dpred[i] = (TP)(g * (-2.f * inv_total) * (tgt - v) * dv_dpred);
+  }
+}
+
+// REPA: one warp per token row. cos = <s,z> / (max(|s|,eps) max(|z|,eps)); loss += coeff * (1 - mean cos).
+__global__ void __launch_bounds__(256)
+repa_cos_fwd_kernel(const bf16* __restrict__ s, const float* __restrict__ z, int64_t R, int E, float coeff_over_R,
+                    float* __restrict__ loss) {
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  float contrib = 0.f;
+  if (row < R) {
+    float dot = 0.f, ss = 0.f, zz = 0.f;
+    for (int c = lane * 8; c < E; c += 256) {
+      float a[8], b[8];
+      unpack8(ld8(s + row * E + c), a);
+      *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(z + row * E + c);
+      *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(z + row * E + c + 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { dot += a[j] * b[j]; ss += a[j] * a[j]; zz += b[j] * b[j]; }
+    }
+    dot = warp_sum(dot); ss = warp_sum(ss); zz = warp_sum(zz);
+    const float ns = fmaxf(sqrtf(ss), 1e-8f), nz = fmaxf(sqrtf(zz), 1e-8f);
+    if (lane == 0) contrib = coeff_over_R * (1.f - dot / (ns * nz));
+  }
+  contrib = block_sum(contrib, red);
+  if (threadIdx.x == 0) atomicAdd(loss, contrib);
+}
+// ds = gout * (-coeff/R) * ( z / (|s||z|) - cos * s / |s|^2 )
+__global__ void __launch_bounds__(256)
+repa_cos_bwd_kernel(const bf16* __restrict__ s, const float* __restrict__ z, int64_t R, int E, float coeff_over_R,
+                    const float* __restrict__ gout, bf16* __restrict__ ds) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const float g = (gout ? *gout : 1.f) * (-coeff_over_R);
+  float dot = 0.f, ss = 0.f, zz = 0.f;
+  for (int c = lane * 8; c < E; c += 256) {
+    float a[8], b[8];
+    unpack8(ld8(s + row * E + c), a);
+    *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(z + row * E + c);
+    *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(z + row * E + c + 4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dot += a[j] * b[j]; ss += a[j] * a[j]; zz += b[j] * b[j]; }
+  }
+  dot = warp_sum(dot); ss = warp_sum(ss); zz = warp_sum(zz);
+  const float ns_raw = sqrtf(ss);
+  const float ns = fmaxf(ns_raw, 1e-8f), nz = fmaxf(sqrtf(zz), 1e-8f);
+  const float inv = 1.f / (ns * nz);
+  // d/ds of max(|s|, eps) vanishes when the clamp is active
+  const float k2 = ns_raw > 1e-8f ? dot * inv / (ns * ns) : 0.f;
+  for (int c = lane * 8; c < E; c += 256) {
+    float a[8], b[8], o[8];
+    unpack8(ld8(s + row * E + c), a);
+    *reinterpret_cast<float4*>(b) = *reinterpret_cast<const float4*>(z + row * E + c);
+    *reinterpret_cast<float4*>(b + 4) = *reinterpret_cast<const float4*>(z + row * E + c + 4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = g * (b[j] * inv - k2 * a[j]);
+    st8(ds + row * E + c, pack8(o));
+  }
+}
+
+// SPRINT selection: one block per sample. kept = indices of the k largest scores, ascending; ties broken towards
+// the larger index (matches the CPU torch.topk probe in SURVEY.md A.10; exactness is defined on tie-free draws).
+// inv[b, s] = slot of token s among the kept ones, or -1.
+__global__ void __launch_bounds__(256)
+sprint_select_kernel(const float* __restrict__ scores, int S, int k, int64_t* __restrict__ kept, int32_t* __restrict__ kept32,
+                     int32_t* __restrict__ inv) {
+  extern __shared__ float sc[];              // S scores, then S flags (as int)
+  int* flag = reinterpret_cast<int*>(sc + S);
+  __shared__ int warp_tot[8];
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) sc[i] = scores[(int64_t)b * S + i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    const float v = sc[i];
+    int rank = 0;
+    for (int j = 0; j < S; ++j) {
+      const float u = sc[j];
+      rank += (u > v) || (u == v && j > i);
+    }
+    flag[i] = rank < k;
+  }
+  __syncthreads();
+  // ordered compaction: chunks of blockDim.x tokens, ballot-based exclusive scan
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int base = 0;
+  for (int c0 = 0; c0 < S; c0 += blockDim.x) {
+    const int i = c0 + threadIdx.x;
+    const int f = (i < S) ? flag[i] : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    const int slot = off + __popc(bal & ((1u << lane) - 1u));
+    if (i < S) {
+      if (f) {
+        kept[(int64_t)b * k + slot] = i;
+        if (kept32) kept32[(int64_t)b * k + slot] = i;
+      }
+      inv[(int64_t)b * S + i] = f ? slot : -1;
+    }
+    int tot = 0;
+    for (int w = 0; w < nw; ++w) tot += warp_tot[w];
+    base += tot;
+    __syncthreads();
+  }
+}
+
+// out[b, j, :] = x[b, idx[b, j], :]
+__global__ void gather_rows_kernel(const bf16* __restrict__ x, const int64_t* __restrict__ idx, bf16* __restrict__ out,
+                                   int B, int S, int k, int d) {
+  const int nv = d >> 3;
+  const int64_t total = (int64_t)B * k * nv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nv);
+    const int64_t bj = i / nv;
+    const int64_t b = bj / k;
+    const int64_t src = b * S + idx[bj];
+    st8(out + bj * d + v * 8, ld8(x + src * d + v * 8));
+  }
+}
+// out[b, s, :] = inv[b,s] >= 0 && !drop[b] ? xk[b, inv[b,s], :] : fill[:]     (fill == nullptr -> zeros)
+__global__ void restore_rows_kernel(const bf16* __restrict__ xk, const int32_t* __restrict__ inv,
+                                    const float* __restrict__ fill, const uint8_t* __restrict__ drop,
+                                    bf16* __restrict__ out, int B, int S, int k, int d) {
+  const int nv = d >> 3;
+  const int64_t total = (int64_t)B * S * nv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nv);
+    const int64_t bs = i / nv;
+    const int64_t b = bs / S;
+    const int slot = inv[bs];
+    if (slot >= 0 && !(drop && drop[b])) {
+      st8(out + bs * d + v * 8, ld8(xk + (b * k + slot) * d + v * 8));
+    } else {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fill ? fill[v * 8 + j] : 0.f;
+      st8(out + bs * d + v * 8, pack8(f));
+    }
+  }
+}
+// restore backward: dxk[b, j, :] = drop[b] ? 0 : dy[b, idx[b,j], :];  dfill[:] += sum over filled positions of dy
+__global__ void __launch_bounds__(256)
+restore_bwd_kernel(const bf16* __restrict__ dy, const int64_t* __restrict__ idx, const int32_t* __restrict__ inv,
+                   const uint8_t* __restrict__ drop, bf16* __restrict__ dxk, float* __restrict__ dfill, int B, int S,
+                   int k, int d) {
+  // part 1: gather
+  const int nv = d >> 3;
+  const int64_t total = (int64_t)B * k * nv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nv);
+    const int64_t bj = i / nv;
+    const int64_t b = bj / k;
+    bf16x8 val;
+    if (drop && drop[b]) { val.u[0] = val.u[1] = val.u[2] = val.u[3] = 0u; }
+    else val = ld8(dy + (b * S + idx[bj]) * d + v * 8);
+    st8(dxk + bj * d + v * 8, val);
+  }
+  // part 2: mask-token gradient; each thread owns channels, strides over (b, s) rows assigned to this block
+  if (!dfill) return;
+  const int64_t rows = (int64_t)B * S;
+  const int64_t rows_per_block = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, rows);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float acc = 0.f;
+    for (int64_t r = r0; r < r1; ++r) {
+      const int64_t b = r / S;
+      if (inv[r] < 0 || (drop && drop[b])) acc += __bfloat162float(dy[r * d + c]);
+    }
+    if (acc != 0.f) atomicAdd(dfill + c, acc);
+  }
+}
+
+// Euler step with optional classifier-free guidance: v = vu + g (vc - vu); x_prev = x - v dt; x0_est = x - v t.
+template <typename TV>
+__global__ void euler_step_kernel(const float* __restrict__ x, const TV* __restrict__ vc, const TV* __restrict__ vu,
+                                  float guidance, float dt, float t_curr, float* __restrict__ x_prev,
+                                  float* __restrict__ x0_est, float* __restrict__ v_out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = (float)vc[i];
+    if (vu) { const float u = (float)vu[i]; v = u + guidance * (v - u); }
+    const float xi = x[i];
+    x_prev[i] = xi - v * dt;
+    if (x0_est) x0_est[i] = xi - v * t_curr;
+    if (v_out) v_out[i] = v;
+  }
+}
+
+// torch.optim.AdamW (no amsgrad, no maximize): p *= 1 - lr*wd; m,v update; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).
+// Also refreshes the bf16 shadow copy used by the GEMMs and (optionally) the EMA copy.
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, bf16* __restrict__ shadow, float* __restrict__ ema, float ema_decay,
+                             int64_t n, float lr, float beta1, float beta2, float eps, float wd, float bc1,
+                             float bc2_sqrt, float grad_scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+    if (ema) ema[i] = ema[i] * ema_decay + pi * (1.f - ema_decay);
+  }
+}
+
+}  // namespace
+
+DLB_EXPORT int dlb_interp(const float* x0, const float* eps, const float* a, const float* b, float* xt, int64_t B,
+                          int64_t per_sample, cudaStream_t stream) {
+  DLB_REQUIRE(B > 0 && per_sample > 0, DLB_ERR_SHAPE, "interp: bad shape");
+  interp_kernel<<<grid_for(B * per_sample), 256, 0, stream>>>(x0, eps, a, b, xt, per_sample, B * per_sample);
+  dlb_count_launch();
+  return dlb_check_launch("interp");
+}
+
+// pred_dtype 0 = bf16, 1 = fp32. x0 may be null (target = eps). xt/t non-null selects x-prediction.
+// loss must be zero-initialised; receives mean over all elements.
+DLB_EXPORT int dlb_mse_fwd(const void* pred, int pred_dtype, const float* x0, const float* eps, const float* xt,
+                           const float* t, int64_t B, int64_t per_sample, float* loss, cudaStream_t stream) {
+  DLB_REQUIRE(B > 0 && per_sample > 0 && ((xt == nullptr) == (t == nullptr)), DLB_ERR_SHAPE, "mse_fwd: bad args");
+  const int64_t total = B * per_sample;
+  int g = grid_for(total);
+  if (g > dlb_num_sms() * 4) g = dlb_num_sms() * 4;
+  if (pred_dtype == 0)
+    mse_fwd_kernel<bf16><<<g, 256, 0, stream>>>((const bf16*)pred, x0, eps, xt, t, per_sample, total, 1.f / (float)total, loss);
+  else
+    mse_fwd_kernel<float><<<g, 256, 0, stream>>>((const float*)pred, x0, eps, xt, t, per_sample, total, 1.f / (float)total, loss);
+  dlb_count_launch();
+  return dlb_check_launch("mse_fwd");
+}
+DLB_EXPORT int dlb_mse_bwd(const void* pred, int pred_dtype, const float* x0, const float* eps, const float* xt,
+                           const float* t, int64_t B, int64_t per_sample, const float* gout, void* dpred,
+                           cudaStream_t stream) {
+  DLB_REQUIRE(B > 0 && per_sample > 0 && ((xt == nullptr) == (t == nullptr)), DLB_ERR_SHAPE, "mse_bwd: bad args");
+  const int64_t total = B * per_sample;
+  if (pred_dtype == 0)
+    mse_bwd_kernel<bf16><<<grid_for(total), 256, 0, stream>>>((const bf16*)pred, x0, eps, xt, t, per_sample, total, 1.f / (float)total, gout, (bf16*)dpred);
+  else
+    mse_bwd_kernel<float><<<grid_for(total), 256, 0, stream>>>((const float*)pred, x0, eps, xt, t, per_sample, total, 1.f / (float)total, gout, (float*)dpred);
+  dlb_count_launch();
+  return dlb_check_launch("mse_bwd");
+}
+
+DLB_EXPORT int dlb_repa_cos_fwd(const void* s, const float* z, int64_t R, int E, float coeff, float* loss,
+                                cudaStream_t stream) {
+  DLB_REQUIRE(R > 0 && E > 0 && E % 8 == 0, DLB_ERR_SHAPE, "repa_cos_fwd: bad shape R=%lld E=%d", (long long)R, E);
+  repa_cos_fwd_kernel<<<(unsigned)((R + 7) / 8), 256, 0, stream>>>((const bf16*)s, z, R, E, coeff / (float)R, loss);
+  dlb_count_launch();
+  return dlb_check_launch("repa_cos_fwd");
+}
+DLB_EXPORT int dlb_repa_cos_bwd(const void* s, const float* z, int64_t R, int E, float coeff, const float* gout, void* ds,
+                                cudaStream_t stream) {
+  DLB_REQUIRE(R > 0 && E > 0 && E % 8 == 0, DLB_ERR_SHAPE, "repa_cos_bwd: bad shape");
+  repa_cos_bwd_kernel<<<(unsigned)((R + 7) / 8), 256, 0, stream>>>((const bf16*)s, z, R, E, coeff / (float)R, gout, (bf16*)ds);
+  dlb_count_launch();
+  return dlb_check_launch("repa_cos_bwd");
+}
+
+DLB_EXPORT int dlb_sprint_select(const float* scores, int B, int S, int k, int64_t* kept, int32_t* kept32, int32_t* inv,
+                                 cudaStream_t stream) {
+  DLB_REQUIRE(B > 0 && S > 0 && k > 0 && k <= S && S <= 8192, DLB_ERR_SHAPE, "sprint_select: B=%d S=%d k=%d", B, S, k);
+  sprint_select_kernel<<<B, 256, (size_t)S * 8, stream>>>(scores, S, k, kept, kept32, inv);
+  dlb_count_launch();
+  return dlb_check_launch("sprint_select");
+}
+DLB_EXPORT int dlb_gather_rows(const void* x, const int64_t* idx, void* out, int B, int S, int k, int d,
+                               cudaStream_t stream) {
+  DLB_REQUIRE(B > 0 && S > 0 && k > 0 && d > 0 && d % 8 == 0, DLB_ERR_SHAPE, "gather_rows: bad shape");
+  gather_rows_kernel<<<grid_for((int64_t)B * k * (d / 8)), 256, 0, stream>>>((const bf16*)x, idx, (bf16*)out, B, S, k, d);
+  dlb_count_launch();
+  return dlb_check_launch("gather_rows");
+}
+DLB_EXPORT int dlb_restore_rows(const void* xk, const int32_t* inv, const float* fill, const uint8_t* drop, void* out,
+                                int B, int S, int k, int d, cudaStream_t stream) {
+  DLB_REQUIRE(B > 0 && S > 0 && k > 0 && d > 0 && d % 8 == 0, DLB_ERR_SHAPE, "restore_rows: bad shape");
+  restore_rows_kernel<<<grid_for((int64_t)B * S * (d / 8)), 256, 0, stream>>>((const bf16*)xk, inv, fill, drop, (bf16*)out, B, S, k, d);
+  dlb_count_launch();
+  return dlb_check_launch("restore_rows");
+}
+DLB_EXPORT int dlb_restore_rows_bwd(const void* dy, const int64_t* idx, const int32_t* inv, const uint8_t* drop, void* dxk,
+                                    float* dfill, int B, int S, int k, int d, cudaStream_t stream) {
+  DLB_REQUIRE(B > 0 && S > 0 && k > 0 && d > 0 && d % 8 == 0, DLB_ERR_SHAPE, "restore_rows_bwd: bad shape");
+  int g = grid_for((int64_t)B * k * (d / 8));
+  if (g > dlb_num_sms() * 2) g = dlb_num_sms() * 2;
+  restore_bwd_kernel<<<g, 256, 0, stream>>>((const bf16*)dy, idx, inv, drop, (bf16*)dxk, dfill, B, S, k, d);
+  dlb_count_launch();
+  return dlb_check_launch("restore_rows_bwd");
+}
+
+// v_dtype 0 = bf16, 1 = fp32; vu may be null (no guidance); x0_est and v_out optional.
+DLB_EXPORT int dlb_euler_step(const float* x, const void* vc, const void* vu, int v_dtype, float guidance, float t_curr,
+                              float t_prev, float* x_prev, float* x0_est, float* v_out, int64_t n, cudaStream_t stream) {
+  DLB_REQUIRE(n > 0, DLB_ERR_SHAPE, "euler_step: empty");
+  const float dt = t_curr - t_prev;
+  if (v_dtype == 0)
+    euler_step_kernel<bf16><<<grid_for(n), 256, 0, stream>>>(x, (const bf16*)vc, (const bf16*)vu, guidance, dt, t_curr, x_prev, x0_est, v_out, n);
+  else
+    euler_step_kernel<float><<<grid_for(n), 256, 0, stream>>>(x, (const float*)vc, (const float*)vu, guidance, dt, t_curr, x_prev, x0_est, v_out, n);
+  dlb_count_launch();
+  return dlb_check_launch("euler_step");
+}
+
+DLB_EXPORT int dlb_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, float* ema, float ema_decay,
+                              int64_t n, float lr, float beta1, float beta2, float eps, float wd, int64_t step,
+                              float grad_scale, cudaStream_t stream) {
+  DLB_REQUIRE(n > 0 && step >= 1, DLB_ERR_SHAPE, "adamw_step: bad args");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  adamw_kernel<<<grid_for(n), 256, 0, stream>>>(p, g, m, v, (bf16*)shadow, ema, ema_decay, n, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
+  dlb_count_launch();
+  return dlb_check_launch("adamw_step");
+}

@@ -1,0 +1,268 @@
+// QK-RMSNorm over the full inner dimension + N-D interleaved-pair RoPE, applied to the packed qkv projection.
+// One warp per token row; q and k rows live in registers; pairs (2j, 2j+1) sit in the same 16-byte vector.
+//
+// Reference: QKNorm/RMSNorm networks/utils/nn.py:423-475 (norm over all heads jointly, eps 1e-6, fp32 math, cast
+// back, learnable scale, cast to v's dtype) and RotaryPositionalEmbeddingNDim nn.py:331-400 (cos/sin cast to the
+// activation dtype, rotation evaluated in that dtype) as called from DiTAttention.forward mmdit.py:81-89.
+#include "common.cuh"
+
+namespace {
+typedef __nv_bfloat16 bf16;
+
+struct RopeArgs {
+  const float* cos_t;   // [positions, rot_half]
+  const float* sin_t;
+  const int32_t* pos_idx;  // optional [R]: table row per token (SPRINT-gathered sequences); else offset + row % tps
+  int rot_half;            // rotary pairs per head
+  int pos_offset;
+  int tokens_per_sample;
+  int hd;
+};
+
+__device__ __forceinline__ int rope_pos(const RopeArgs& ra, int64_t row) {
+  return ra.pos_idx ? ra.pos_idx[row] : ra.pos_offset + (int)(row % ra.tokens_per_sample);
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256)
+qknorm_rope_fwd_kernel(const bf16* __restrict__ qkv, int64_t ld_in, const float* __restrict__ sq,
+                       const float* __restrict__ sk, RopeArgs ra, bf16* __restrict__ out, int64_t ld_out,
+                       float* __restrict__ rrms_out, int64_t R, int d, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const int nv = d >> 3;
+  const int pos = rope_pos(ra, row);
+  const float* cr = ra.cos_t + (int64_t)pos * ra.rot_half;
+  const float* sr = ra.sin_t + (int64_t)pos * ra.rot_half;
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    const bf16* src = qkv + row * ld_in + which * d;
+    const float* sc = which ? sk : sq;
+    float xv[VPL][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nv) {
+        unpack8(ld8(src + v * 8), xv[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += xv[i][j] * xv[i][j];
+      }
+    }
+    const float rrms = rsqrtf(warp_sum(ss) / d + eps);
+    if (lane == 0 && rrms_out) rrms_out[row * 2 + which] = rrms;
+    bf16* dst = out + row * ld_out + which * d;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nv) {
+        const int c = v * 8;
+        const int cl = c % ra.hd;  // channel inside the head; hd % 8 == 0 keeps a vector inside one head
+        float y[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) y[j] = bf16_round(bf16_round(xv[i][j] * rrms) * __ldg(sc + c + j));
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const int pj = (cl + j) >> 1;
+          if (pj < ra.rot_half) {
+            const float cs = bf16_round(__ldg(cr + pj)), sn = bf16_round(__ldg(sr + pj));
+            const float e = y[j], o = y[j + 1];
+            y[j] = bf16_round(e * cs) - bf16_round(o * sn);
+            y[j + 1] = bf16_round(e * sn) + bf16_round(o * cs);
+          }
+        }
+        st8(dst + c, pack8(y));
+      }
+    }
+  }
+}
+
+// backward: dqk (grad wrt normalised+rotated q,k) -> dq, dk (written into the packed dqkv buffer) and
+// column-accumulated scale gradients.
+template <int VPL>
+__global__ void __launch_bounds__(256)
+qknorm_rope_bwd_kernel(const bf16* __restrict__ dqk, int64_t ld_dqk, const bf16* __restrict__ qkv, int64_t ld_in,
+                       const float* __restrict__ sq, const float* __restrict__ sk, RopeArgs ra,
+                       bf16* __restrict__ dqkv, int64_t ld_out, float* __restrict__ dsq, float* __restrict__ dsk,
+                       int64_t R, int d, float eps, int rows_per_warp) {
+  extern __shared__ float red[];  // [warps][d]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int nv = d >> 3;
+  const int64_t r_begin = ((int64_t)blockIdx.x * nwarps + warp) * rows_per_warp;
+  const int64_t r_end = min(r_begin + rows_per_warp, R);
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    const float* sc = which ? sk : sq;
+    float S[VPL][8];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) S[i][j] = 0.f;
+    for (int64_t row = r_begin; row < r_end; ++row) {
+      const int pos = rope_pos(ra, row);
+      const float* cr = ra.cos_t + (int64_t)pos * ra.rot_half;
+      const float* sr = ra.sin_t + (int64_t)pos * ra.rot_half;
+      const bf16* src = qkv + row * ld_in + which * d;
+      const bf16* gsrc = dqk + row * ld_dqk + which * d;
+      float xn[VPL][8], gn[VPL][8];
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nv) {
+          unpack8(ld8(src + v * 8), xn[i]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ss += xn[i][j] * xn[i][j];
+        }
+      }
+      const float rrms = rsqrtf(warp_sum(ss) / d + eps);
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nv) {
+          const int c = v * 8;
+          const int cl = c % ra.hd;
+          float g[8];
+          unpack8(ld8(gsrc + c), g);
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {  // transpose of the rotation
+            const int pj = (cl + j) >> 1;
+            if (pj < ra.rot_half) {
+              const float cs = bf16_round(__ldg(cr + pj)), sn = bf16_round(__ldg(sr + pj));
+              const float ge = g[j], go = g[j + 1];
+              g[j] = ge * cs + go * sn;
+              g[j + 1] = -ge * sn + go * cs;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            xn[i][j] *= rrms;                      // normalised value (fp32)
+            S[i][j] += g[j] * bf16_round(xn[i][j]);  // d scale: the reference multiplies the bf16-rounded value
+            gn[i][j] = g[j] * __ldg(sc + c + j);   // grad wrt the normalised value
+            dot += gn[i][j] * xn[i][j];
+          }
+        }
+      }
+      dot = warp_sum(dot) / d;
+      bf16* dst = dqkv + row * ld_out + which * d;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nv) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = rrms * (gn[i][j] - xn[i][j] * dot);
+          st8(dst + v * 8, pack8(o));
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nv) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[(size_t)warp * d + v * 8 + j] = S[i][j];
+      }
+    }
+    __syncthreads();
+    float* dsc = which ? dsk : dsq;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      float a = 0.f;
+      for (int wi = 0; wi < nwarps; ++wi) a += red[(size_t)wi * d + c];
+      atomicAdd(dsc + c, a);
+    }
+  }
+}
+
+int vpl_for(int d) { return (d / 8 + 31) / 32; }
+}  // namespace
+
+#define VPL_SWITCH(d, ...)                                                                       \
+  switch (vpl_for(d)) {                                                                          \
+    case 1: { constexpr int VPL = 1; __VA_ARGS__; break; }                                       \
+    case 2: { constexpr int VPL = 2; __VA_ARGS__; break; }                                       \
+    case 3: { constexpr int VPL = 3; __VA_ARGS__; break; }                                       \
+    case 4: { constexpr int VPL = 4; __VA_ARGS__; break; }                                       \
+    case 5: { constexpr int VPL = 5; __VA_ARGS__; break; }                                       \
+    case 6: { constexpr int VPL = 6; __VA_ARGS__; break; }                                       \
+    case 7: case 8: { constexpr int VPL = 8; __VA_ARGS__; break; }                               \
+    default: dlb_set_error("channel count %d unsupported (max 2048)", d); return DLB_ERR_SHAPE;  \
+  }
+
+static int check_rope(const char* who, int d, int hd, int rot_half, int tokens_per_sample, const int32_t* pos_idx) {
+  DLB_REQUIRE(d > 0 && d % 8 == 0 && hd > 0 && hd % 8 == 0 && d % hd == 0, DLB_ERR_SHAPE, "%s: d=%d hd=%d", who, d, hd);
+  DLB_REQUIRE(rot_half >= 0 && 2 * rot_half <= hd, DLB_ERR_SHAPE, "%s: rotary dim %d exceeds head dim %d", who, 2 * rot_half, hd);
+  DLB_REQUIRE(pos_idx != nullptr || tokens_per_sample > 0, DLB_ERR_SHAPE, "%s: need pos_idx or tokens_per_sample", who);
+  return DLB_OK;
+}
+
+// qkv: [R, >=2d] packed (q | k | ...) with row stride ld_in; out: [R, 2d] rotated (q | k) with row stride ld_out.
+DLB_EXPORT int dlb_qknorm_rope_fwd(const void* qkv, int64_t ld_in, const float* sq, const float* sk, const float* cos_t,
+                                   const float* sin_t, int rot_half, const int32_t* pos_idx, int pos_offset,
+                                   int tokens_per_sample, int hd, void* out, int64_t ld_out, float* rrms, int64_t R,
+                                   int d, float eps, cudaStream_t stream) {
+  int rc = check_rope("qknorm_rope_fwd", d, hd, rot_half, tokens_per_sample, pos_idx);
+  if (rc) return rc;
+  DLB_REQUIRE(R > 0 && ld_in % 8 == 0 && ld_out % 8 == 0, DLB_ERR_SHAPE, "qknorm_rope_fwd: bad strides");
+  RopeArgs ra{cos_t, sin_t, pos_idx, rot_half, pos_offset, tokens_per_sample > 0 ? tokens_per_sample : 1, hd};
+  const int warps = 8;
+  const int grid = (int)((R + warps - 1) / warps);
+  VPL_SWITCH(d, (qknorm_rope_fwd_kernel<VPL><<<grid, warps * 32, 0, stream>>>((const bf16*)qkv, ld_in, sq, sk, ra,
+                                                                             (bf16*)out, ld_out, rrms, R, d, eps)));
+  dlb_count_launch();
+  return dlb_check_launch("qknorm_rope_fwd");
+}
+
+DLB_EXPORT int dlb_qknorm_rope_bwd(const void* dqk, int64_t ld_dqk, const void* qkv, int64_t ld_in, const float* sq,
+                                   const float* sk, const float* cos_t, const float* sin_t, int rot_half,
+                                   const int32_t* pos_idx, int pos_offset, int tokens_per_sample, int hd, void* dqkv,
+                                   int64_t ld_out, float* dsq, float* dsk, int64_t R, int d, float eps,
+                                   cudaStream_t stream) {
+  int rc = check_rope("qknorm_rope_bwd", d, hd, rot_half, tokens_per_sample, pos_idx);
+  if (rc) return rc;
+  DLB_REQUIRE(R > 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && ld_dqk % 8 == 0, DLB_ERR_SHAPE, "qknorm_rope_bwd: bad strides");
+  RopeArgs ra{cos_t, sin_t, pos_idx, rot_half, pos_offset, tokens_per_sample > 0 ? tokens_per_sample : 1, hd};
+  const int warps = 8;
+  int64_t rpw = R / ((int64_t)dlb_num_sms() * 4 * warps);
+  rpw = rpw < 1 ? 1 : (rpw > 8 ? 8 : rpw);
+  const int grid = (int)((R + warps * rpw - 1) / (warps * rpw));
+  const size_t smem = (size_t)warps * d * sizeof(float);
+  VPL_SWITCH(d, {
+    auto k = qknorm_rope_bwd_kernel<VPL>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<grid, warps * 32, smem, stream>>>((const bf16*)dqk, ld_dqk, (const bf16*)qkv, ld_in, sq, sk, ra, (bf16*)dqkv,
+                                         ld_out, dsq, dsk, R, d, eps, (int)rpw);
+  });
+  dlb_count_launch();
+  return dlb_check_launch("qknorm_rope_bwd");
+}
+
+// cos/sin table of get_cos_sin_ndim_grid (nn.py:262-307): fp64 angles, stored fp32. pos: [P, n_axes] int32.
+__global__ void rope_table_kernel(const int32_t* __restrict__ pos, int n_axes, const int32_t* __restrict__ axis_of_pair,
+                                  const int32_t* __restrict__ local_of_pair, const int32_t* __restrict__ axis_dim,
+                                  double base, float* __restrict__ cos_t, float* __restrict__ sin_t, int64_t P,
+                                  int rot_half) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * rot_half) return;
+  const int64_t p = i / rot_half;
+  const int j = (int)(i - p * rot_half);
+  const int ax = axis_of_pair[j];
+  const double freq = 1.0 / pow(base, (double)(2 * local_of_pair[j]) / (double)axis_dim[ax]);
+  const double ang = (double)pos[p * n_axes + ax] * freq;
+  cos_t[i] = (float)cos(ang);
+  sin_t[i] = (float)sin(ang);
+}
+
+DLB_EXPORT int dlb_rope_table(const int32_t* pos, int n_axes, const int32_t* axis_of_pair, const int32_t* local_of_pair,
+                              const int32_t* axis_dim, double base, float* cos_t, float* sin_t, int64_t P, int rot_half,
+                              cudaStream_t stream) {
+  DLB_REQUIRE(P > 0 && rot_half > 0 && n_axes > 0, DLB_ERR_SHAPE, "rope_table: bad shape");
+  const int64_t total = P * rot_half;
+  rope_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(pos, n_axes, axis_of_pair, local_of_pair,
+                                                                        axis_dim, base, cos_t, sin_t, P, rot_half);
+  dlb_count_launch();
+  return dlb_check_launch("rope_table");
+}

@@ -76,3 +76,452 @@ def gemm(
     )
     _lib.check(rc, "dlb_gemm_bf16")
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------------------
+def _lib_call(name: str, *args) -> None:
+    rc = getattr(_lib.load(), name)(*args)
+    _lib.check(rc, name)
+
+
+def _rows(x: Tensor) -> int:
+    return x.numel() // x.shape[-1]
+
+
+def _req(t: Tensor, dtype: torch.dtype, name: str, contiguous: bool = True) -> None:
+    if t.dtype != dtype:
+        raise ValueError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (diffulab_b200 has no CPU path)")
+    if contiguous and not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous tensor")
+
+
+def _mod_view(m: Tensor, d: int, name: str) -> tuple[int, int, int]:
+    """Modulation chunk [G, d] (a column slice of the [G, k*d] adaLN output). Returns (ptr, ld, groups)."""
+    m2 = m.reshape(-1, m.shape[-1]) if m.is_contiguous() else m
+    if m2.dim() == 3:  # [B, 1, d] or [B, N, d] views keep their strides
+        if m2.shape[1] == 1:
+            m2 = m2[:, 0, :]
+        else:
+            if m2.stride(0) != m2.shape[1] * m2.stride(1):
+                raise ValueError(f"{name}: unsupported per-token modulation strides {m.stride()}")
+            m2 = m2.as_strided((m2.shape[0] * m2.shape[1], m2.shape[2]), (m2.stride(1), 1), m2.storage_offset())
+    if m2.dim() != 2 or m2.shape[1] != d or m2.stride(1) != 1 or m2.dtype != BF16:
+        raise ValueError(f"{name}: expected a bf16 [G, {d}] view with unit inner stride, got {tuple(m.shape)} {m.stride()} {m.dtype}")
+    return m2.data_ptr(), m2.stride(0) if m2.shape[0] > 1 else d, m2.shape[0]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# LayerNorm + modulate
+# ---------------------------------------------------------------------------------------------------------
+def ln_modulate_fwd(x: Tensor, w: Tensor | None, b: Tensor | None, scale: Tensor, shift: Tensor, eps: float):
+    _req(x, BF16, "x")
+    d = x.shape[-1]
+    R = _rows(x)
+    sp, sld, G = _mod_view(scale, d, "scale")
+    hp, hld, G2 = _mod_view(shift, d, "shift")
+    if G != G2 or sld != hld or R % G != 0:
+        raise ValueError("ln_modulate: scale/shift layout mismatch")
+    y = torch.empty_like(x)
+    mean = torch.empty(R, device=x.device, dtype=F32)
+    rstd = torch.empty(R, device=x.device, dtype=F32)
+    _lib_call("dlb_ln_modulate_fwd", x.data_ptr(), _ptr(w), _ptr(b), sp, hp, sld, R // G, y.data_ptr(),
+              mean.data_ptr(), rstd.data_ptr(), R, d, eps, _stream())
+    return y, mean, rstd
+
+
+def ln_modulate_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, w: Tensor | None, b: Tensor | None,
+                    scale: Tensor, dres: Tensor | None, dscale: Tensor, dshift: Tensor,
+                    dw: Tensor | None, db: Tensor | None) -> Tensor:
+    """Returns dx (+dres). Accumulates into dscale/dshift (fp32 [G,d] views for per-sample modulation; bf16 [R,d]
+    views written (not accumulated) for per-token modulation) and into dw/db (fp32 [d])."""
+    _req(dy, BF16, "dy")
+    _req(x, BF16, "x")
+    d = x.shape[-1]
+    R = _rows(x)
+    sp, sld, G = _mod_view(scale, d, "scale")
+    per_token = G == R and R > 1 and dscale.dtype == BF16
+    dx = torch.empty_like(x)
+    if per_token:
+        ds2 = dscale.reshape(-1, d) if dscale.is_contiguous() else dscale.as_strided((R, d), (dscale.stride(-2), 1), dscale.storage_offset())
+        dh2 = dshift.reshape(-1, d) if dshift.is_contiguous() else dshift.as_strided((R, d), (dshift.stride(-2), 1), dshift.storage_offset())
+        _lib_call("dlb_ln_modulate_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(w), _ptr(b),
+                  sp, sld, 1, R, 1, _ptr(dres), dx.data_ptr(), None, None, 0, ds2.data_ptr(), dh2.data_ptr(),
+                  ds2.stride(0), _ptr(dw), _ptr(db), d, _stream())
+    else:
+        if dscale.dtype != F32 or dshift.dtype != F32 or dscale.stride(-1) != 1:
+            raise ValueError("ln_modulate_bwd: dscale/dshift must be fp32 views")
+        ds2 = dscale.reshape(-1, d) if dscale.dim() != 2 else dscale
+        dh2 = dshift.reshape(-1, d) if dshift.dim() != 2 else dshift
+        ld = ds2.stride(0) if ds2.shape[0] > 1 else d
+        _lib_call("dlb_ln_modulate_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(w), _ptr(b),
+                  sp, sld, G, R // G, 0, _ptr(dres), dx.data_ptr(), ds2.data_ptr(), dh2.data_ptr(), ld, None, None, 0,
+                  _ptr(dw), _ptr(db), d, _stream())
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------------------
+# gated residual
+# ---------------------------------------------------------------------------------------------------------
+def gate_residual_fwd(x: Tensor, a1: Tensor, a2: Tensor | None, gate: Tensor) -> Tensor:
+    _req(x, BF16, "x")
+    _req(a1, BF16, "a1")
+    d = x.shape[-1]
+    R = _rows(x)
+    gp, gld, G = _mod_view(gate, d, "gate")
+    out = torch.empty_like(x)
+    _lib_call("dlb_gate_residual_fwd", x.data_ptr(), a1.data_ptr(), _ptr(a2), gp, gld, R // G, out.data_ptr(), R, d, _stream())
+    return out
+
+
+def gate_residual_bwd(dout: Tensor, a1: Tensor, a2: Tensor | None, gate: Tensor, dgate: Tensor) -> Tensor:
+    """Returns da (= dout * gate). dgate: fp32 [G,d] view (accumulated) or bf16 [R,d] view (per-token, written)."""
+    _req(dout, BF16, "dout")
+    d = dout.shape[-1]
+    R = _rows(dout)
+    gp, gld, G = _mod_view(gate, d, "gate")
+    da = torch.empty_like(dout)
+    per_token = G == R and R > 1 and dgate.dtype == BF16
+    if per_token:
+        dg2 = dgate.reshape(-1, d) if dgate.is_contiguous() else dgate.as_strided((R, d), (dgate.stride(-2), 1), dgate.storage_offset())
+        _lib_call("dlb_gate_residual_bwd", dout.data_ptr(), a1.data_ptr(), _ptr(a2), gp, gld, 1, R, 1, da.data_ptr(), None, 0,
+                  dg2.data_ptr(), dg2.stride(0), d, _stream())
+    else:
+        dg2 = dgate.reshape(-1, d) if dgate.dim() != 2 else dgate
+        ld = dg2.stride(0) if dg2.shape[0] > 1 else d
+        _lib_call("dlb_gate_residual_bwd", dout.data_ptr(), a1.data_ptr(), _ptr(a2), gp, gld, G, R // G, 0, da.data_ptr(),
+                  dg2.data_ptr(), ld, None, 0, d, _stream())
+    return da
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SwiGLU
+# ---------------------------------------------------------------------------------------------------------
+def swiglu_fwd(h: Tensor) -> Tensor:
+    _req(h, BF16, "h")
+    F = h.shape[-1] // 2
+    out = torch.empty(*h.shape[:-1], F, device=h.device, dtype=BF16)
+    _lib_call("dlb_swiglu_fwd", h.data_ptr(), out.data_ptr(), _rows(h), F, _stream())
+    return out
+
+
+def swiglu_bwd(dout: Tensor, h: Tensor) -> Tensor:
+    _req(dout, BF16, "dout")
+    _req(h, BF16, "h")
+    dh = torch.empty_like(h)
+    _lib_call("dlb_swiglu_bwd", dout.data_ptr(), h.data_ptr(), dh.data_ptr(), _rows(h), h.shape[-1] // 2, _stream())
+    return dh
+
+
+# ---------------------------------------------------------------------------------------------------------
+# RoPE table, QK-norm + RoPE
+# ---------------------------------------------------------------------------------------------------------
+def rope_table(pos_ids: Tensor, axes_dim: list[int], base: float) -> tuple[Tensor, Tensor]:
+    """pos_ids: int32 [P, n_axes] on device -> cos, sin fp32 [P, sum(axes)/2] (nn.py:262-307)."""
+    _req(pos_ids, torch.int32, "pos_ids")
+    P, n_axes = pos_ids.shape
+    axis_of, local_of = [], []
+    for a, dim in enumerate(axes_dim):
+        for j in range(dim // 2):
+            axis_of.append(a)
+            local_of.append(j)
+    rot_half = len(axis_of)
+    dev = pos_ids.device
+    ax = torch.tensor(axis_of, dtype=torch.int32, device=dev)
+    lo = torch.tensor(local_of, dtype=torch.int32, device=dev)
+    ad = torch.tensor(axes_dim, dtype=torch.int32, device=dev)
+    cos = torch.empty(P, rot_half, device=dev, dtype=F32)
+    sin = torch.empty(P, rot_half, device=dev, dtype=F32)
+    _lib_call("dlb_rope_table", pos_ids.data_ptr(), n_axes, ax.data_ptr(), lo.data_ptr(), ad.data_ptr(), float(base),
+              cos.data_ptr(), sin.data_ptr(), P, rot_half, _stream())
+    return cos, sin
+
+
+def qknorm_rope_fwd(qkv: Tensor, sq: Tensor, sk: Tensor, cos: Tensor, sin: Tensor, hd: int, *, tokens_per_sample: int,
+                    pos_offset: int = 0, pos_idx: Tensor | None = None, eps: float = 1e-6) -> Tensor:
+    """qkv: [R, 3d] packed projection -> [R, 2d] normalised + rotated (q | k)."""
+    _req(qkv, BF16, "qkv")
+    R = _rows(qkv)
+    d = qkv.shape[-1] // 3
+    out = torch.empty(R, 2 * d, device=qkv.device, dtype=BF16)
+    _lib_call("dlb_qknorm_rope_fwd", qkv.data_ptr(), 3 * d, sq.data_ptr(), sk.data_ptr(), cos.data_ptr(), sin.data_ptr(),
+              cos.shape[-1], _ptr(pos_idx), pos_offset, tokens_per_sample, hd, out.data_ptr(), 2 * d, None, R, d, eps, _stream())
+    return out
+
+
+def qknorm_rope_bwd(dqk: Tensor, qkv: Tensor, sq: Tensor, sk: Tensor, cos: Tensor, sin: Tensor, hd: int, dqkv: Tensor,
+                    dsq: Tensor, dsk: Tensor, *, tokens_per_sample: int, pos_offset: int = 0,
+                    pos_idx: Tensor | None = None, eps: float = 1e-6) -> None:
+    """Writes dq, dk into dqkv[:, :2d] (dv at [:, 2d:] is produced by attention bwd); accumulates dsq/dsk (fp32)."""
+    R = _rows(qkv)
+    d = qkv.shape[-1] // 3
+    _lib_call("dlb_qknorm_rope_bwd", dqk.data_ptr(), 2 * d, qkv.data_ptr(), 3 * d, sq.data_ptr(), sk.data_ptr(),
+              cos.data_ptr(), sin.data_ptr(), cos.shape[-1], _ptr(pos_idx), pos_offset, tokens_per_sample, hd,
+              dqkv.data_ptr(), 3 * d, dsq.data_ptr(), dsk.data_ptr(), R, d, eps, _stream())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# attention over one or two packed segments
+# ---------------------------------------------------------------------------------------------------------
+class AttnSegSpec:
+    """One sequence segment: qk [B*len, 2d] (rotated q|k), qkv [B*len, 3d] (v read in place), out [B*len, d]."""
+
+    def __init__(self, qk: Tensor, qkv: Tensor, length: int):
+        self.qk, self.qkv, self.len = qk, qkv, length
+        self.d = qk.shape[-1] // 2
+
+
+def _seg_array(specs, outs, douts=None, dqks=None, dqkvs=None):
+    arr = (_lib.AttnSeg * len(specs))()
+    for i, s in enumerate(specs):
+        d = s.d
+        e = arr[i]
+        e.q = s.qk.data_ptr()
+        e.k = s.qk.data_ptr() + d * 2
+        e.v = s.qkv.data_ptr() + 2 * d * 2
+        e.ldq = e.ldk = 2 * d
+        e.ldv = 3 * d
+        e.o = outs[i].data_ptr()
+        e.ldo = d
+        e.len = s.len
+        if douts is not None:
+            e.dout = douts[i].data_ptr()
+            e.lddo = d
+            e.dq = dqks[i].data_ptr()
+            e.dk = dqks[i].data_ptr() + d * 2
+            e.lddq = e.lddk = 2 * d
+            e.dv = dqkvs[i].data_ptr() + 2 * d * 2
+            e.lddv = 3 * d
+    return arr
+
+
+def attn_fwd(specs: list[AttnSegSpec], B: int, H: int, hd: int, scale: float, kmask: Tensor | None = None):
+    S = sum(s.len for s in specs)
+    dev = specs[0].qk.device
+    outs = [torch.empty(B * s.len, s.d, device=dev, dtype=BF16) for s in specs]
+    lse = torch.empty(B, H, S, device=dev, dtype=F32)
+    arr = _seg_array(specs, outs)
+    mask_len = 0
+    if kmask is not None:
+        _req(kmask, torch.uint8, "kmask")
+        mask_len = kmask.shape[1]
+    import ctypes as C
+    _lib_call("dlb_attn_fwd", C.cast(arr, C.c_void_p), len(specs), lse.data_ptr(), _ptr(kmask), mask_len, B, H, hd, scale, _stream())
+    return outs, lse
+
+
+def attn_bwd(specs: list[AttnSegSpec], outs: list[Tensor], douts: list[Tensor], lse: Tensor, B: int, H: int, hd: int,
+             scale: float, dqkvs: list[Tensor], kmask: Tensor | None = None) -> list[Tensor]:
+    """Returns dqk (grad wrt rotated q|k) per segment; writes dv into dqkvs[i][:, 2d:]."""
+    dev = specs[0].qk.device
+    dqks = [torch.empty(B * s.len, 2 * s.d, device=dev, dtype=BF16) for s in specs]
+    dsum = torch.empty_like(lse)
+    arr = _seg_array(specs, outs, douts, dqks, dqkvs)
+    mask_len = kmask.shape[1] if kmask is not None else 0
+    import ctypes as C
+    _lib_call("dlb_attn_bwd", C.cast(arr, C.c_void_p), len(specs), lse.data_ptr(), dsum.data_ptr(), _ptr(kmask), mask_len,
+              B, H, hd, scale, _stream())
+    return dqks
+
+
+# ---------------------------------------------------------------------------------------------------------
+# glue
+# ---------------------------------------------------------------------------------------------------------
+def cast_bf16(x: Tensor, ld_out: int | None = None) -> Tensor:
+    """fp32 [rows, cols] (or any shape, treated flat) -> bf16; ld_out > cols zero-pads each row."""
+    _req(x, F32, "x")
+    if ld_out is None or ld_out == x.shape[-1]:
+        out = torch.empty_like(x, dtype=BF16)
+        _lib_call("dlb_cast_f32_bf16", x.data_ptr(), out.data_ptr(), 1, x.numel(), x.numel(), _stream())
+        return out
+    rows, cols = _rows(x), x.shape[-1]
+    out = torch.empty(rows, ld_out, device=x.device, dtype=BF16)
+    _lib_call("dlb_cast_f32_bf16", x.data_ptr(), out.data_ptr(), rows, cols, ld_out, _stream())
+    return out
+
+
+def cast_f32(x: Tensor) -> Tensor:
+    _req(x, BF16, "x")
+    out = torch.empty_like(x, dtype=F32)
+    _lib_call("dlb_cast_bf16_f32", x.data_ptr(), out.data_ptr(), x.numel(), _stream())
+    return out
+
+
+def _dt(t: Tensor) -> int:
+    if t.dtype == BF16:
+        return 0
+    if t.dtype == F32:
+        return 1
+    raise ValueError(f"unsupported dtype {t.dtype}")
+
+
+def silu_fwd(x: Tensor) -> Tensor:
+    _req(x, x.dtype, "x")
+    y = torch.empty_like(x, dtype=BF16)
+    _lib_call("dlb_silu_fwd", x.data_ptr(), _dt(x), y.data_ptr(), x.numel(), _stream())
+    return y
+
+
+def silu_bwd(dy: Tensor, x: Tensor, out_dtype: torch.dtype) -> Tensor:
+    _req(dy, dy.dtype, "dy")
+    dx = torch.empty_like(x, dtype=out_dtype)
+    _lib_call("dlb_silu_bwd", dy.data_ptr(), _dt(dy), x.data_ptr(), _dt(x), dx.data_ptr(), _dt(dx), x.numel(), _stream())
+    return dx
+
+
+def timestep_embed(t: Tensor, dim: int, max_period: float = 10000.0) -> Tensor:
+    _req(t, F32, "t")
+    out = torch.empty(t.shape[0], dim, device=t.device, dtype=BF16)
+    _lib_call("dlb_timestep_embed", t.data_ptr(), out.data_ptr(), t.shape[0], dim, max_period, _stream())
+    return out
+
+
+def cond_combine(te: Tensor, table: Tensor | None, labels: Tensor | None) -> tuple[Tensor, Tensor]:
+    _req(te, BF16, "te")
+    B, E = te.shape
+    emb = torch.empty(B, E, device=te.device, dtype=F32)
+    emb_silu = torch.empty(B, E, device=te.device, dtype=BF16)
+    _lib_call("dlb_cond_combine", te.data_ptr(), _ptr(table), _ptr(labels), emb.data_ptr(), emb_silu.data_ptr(), B, E, _stream())
+    return emb, emb_silu
+
+
+def embedding_bwd(g: Tensor, labels: Tensor, dtable: Tensor) -> None:
+    _req(g, F32, "g")
+    _lib_call("dlb_embedding_bwd", g.data_ptr(), labels.data_ptr(), dtable.data_ptr(), g.shape[0], g.shape[1], _stream())
+
+
+def patchify(x: Tensor, p: int) -> Tensor:
+    _req(x, F32, "x")
+    B, C, H, W = x.shape
+    Kp = (C * p * p + 7) // 8 * 8
+    out = torch.empty(B * (H // p) * (W // p), Kp, device=x.device, dtype=BF16)
+    _lib_call("dlb_patchify", x.data_ptr(), out.data_ptr(), B, C, H, W, p, Kp, _stream())
+    return out
+
+
+def unpatchify(tok: Tensor, B: int, C: int, H: int, W: int, p: int, out_dtype: torch.dtype = BF16) -> Tensor:
+    _req(tok, BF16, "tok", contiguous=False)
+    img = torch.empty(B, C, H, W, device=tok.device, dtype=out_dtype)
+    _lib_call("dlb_unpatchify", tok.data_ptr(), tok.stride(-2), img.data_ptr(), 0 if out_dtype == BF16 else 1, B, C, H, W, p, _stream())
+    return img
+
+
+def patchify_grad(img: Tensor, p: int, ld: int | None = None) -> Tensor:
+    B, C, H, W = img.shape
+    ppc = p * p * C
+    ld = ld or (ppc + 7) // 8 * 8
+    if ld != ppc:
+        tok = torch.zeros(B * (H // p) * (W // p), ld, device=img.device, dtype=BF16)
+    else:
+        tok = torch.empty(B * (H // p) * (W // p), ld, device=img.device, dtype=BF16)
+    _lib_call("dlb_patchify_grad", img.data_ptr(), _dt(img), tok.data_ptr(), ld, B, C, H, W, p, _stream())
+    return tok
+
+
+def colsum_(x: Tensor, out: Tensor) -> None:
+    """out[c] += sum_r x[r, c]; x bf16/fp32 2-D (row stride allowed), out fp32 [C]."""
+    _lib_call("dlb_colsum", x.data_ptr(), _dt(x), x.stride(0), out.data_ptr(), x.shape[0], x.shape[1], _stream())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# formalisation-side kernels
+# ---------------------------------------------------------------------------------------------------------
+def interp(x0: Tensor, eps: Tensor, a: Tensor, b: Tensor) -> Tensor:
+    _req(x0, F32, "x0")
+    _req(eps, F32, "eps")
+    xt = torch.empty_like(x0)
+    B = x0.shape[0]
+    _lib_call("dlb_interp", x0.data_ptr(), eps.data_ptr(), a.data_ptr(), b.data_ptr(), xt.data_ptr(), B, x0.numel() // B, _stream())
+    return xt
+
+
+def mse_fwd(pred: Tensor, x0: Tensor | None, eps: Tensor, xt: Tensor | None = None, t: Tensor | None = None) -> Tensor:
+    _req(pred, pred.dtype, "pred")
+    B = pred.shape[0]
+    loss = torch.zeros((), device=pred.device, dtype=F32)
+    _lib_call("dlb_mse_fwd", pred.data_ptr(), _dt(pred), _ptr(x0), eps.data_ptr(), _ptr(xt), _ptr(t), B, pred.numel() // B,
+              loss.data_ptr(), _stream())
+    return loss
+
+
+def mse_bwd(pred: Tensor, x0: Tensor | None, eps: Tensor, gout: Tensor | None, xt: Tensor | None = None,
+            t: Tensor | None = None) -> Tensor:
+    B = pred.shape[0]
+    dpred = torch.empty_like(pred)
+    _lib_call("dlb_mse_bwd", pred.data_ptr(), _dt(pred), _ptr(x0), eps.data_ptr(), _ptr(xt), _ptr(t), B, pred.numel() // B,
+              _ptr(gout), dpred.data_ptr(), _stream())
+    return dpred
+
+
+def repa_cos_fwd(s: Tensor, z: Tensor, coeff: float) -> Tensor:
+    _req(s, BF16, "s")
+    _req(z, F32, "z")
+    loss = torch.zeros((), device=s.device, dtype=F32)
+    _lib_call("dlb_repa_cos_fwd", s.data_ptr(), z.data_ptr(), _rows(s), s.shape[-1], coeff, loss.data_ptr(), _stream())
+    return loss
+
+
+def repa_cos_bwd(s: Tensor, z: Tensor, coeff: float, gout: Tensor | None) -> Tensor:
+    ds = torch.empty_like(s)
+    _lib_call("dlb_repa_cos_bwd", s.data_ptr(), z.data_ptr(), _rows(s), s.shape[-1], coeff, _ptr(gout), ds.data_ptr(), _stream())
+    return ds
+
+
+def sprint_select(scores: Tensor, k: int) -> tuple[Tensor, Tensor, Tensor]:
+    """scores fp32 [B,S] -> kept int64 [B,k] ascending, kept32 int32 [B,k], inv int32 [B,S] (slot or -1)."""
+    _req(scores, F32, "scores")
+    B, S = scores.shape
+    kept = torch.empty(B, k, device=scores.device, dtype=torch.int64)
+    kept32 = torch.empty(B, k, device=scores.device, dtype=torch.int32)
+    inv = torch.empty(B, S, device=scores.device, dtype=torch.int32)
+    _lib_call("dlb_sprint_select", scores.data_ptr(), B, S, k, kept.data_ptr(), kept32.data_ptr(), inv.data_ptr(), _stream())
+    return kept, kept32, inv
+
+
+def gather_rows(x: Tensor, idx: Tensor) -> Tensor:
+    _req(x, BF16, "x")
+    B, S, d = x.shape
+    k = idx.shape[1]
+    out = torch.empty(B, k, d, device=x.device, dtype=BF16)
+    _lib_call("dlb_gather_rows", x.data_ptr(), idx.data_ptr(), out.data_ptr(), B, S, k, d, _stream())
+    return out
+
+
+def restore_rows(xk: Tensor, inv: Tensor, fill: Tensor | None, drop: Tensor | None) -> Tensor:
+    _req(xk, BF16, "xk")
+    B, k, d = xk.shape
+    S = inv.shape[1]
+    out = torch.empty(B, S, d, device=xk.device, dtype=BF16)
+    _lib_call("dlb_restore_rows", xk.data_ptr(), inv.data_ptr(), _ptr(fill), _ptr(drop), out.data_ptr(), B, S, k, d, _stream())
+    return out
+
+
+def restore_rows_bwd(dy: Tensor, idx: Tensor, inv: Tensor, drop: Tensor | None, dfill: Tensor | None) -> Tensor:
+    _req(dy, BF16, "dy")
+    B, S, d = dy.shape
+    k = idx.shape[1]
+    dxk = torch.empty(B, k, d, device=dy.device, dtype=BF16)
+    _lib_call("dlb_restore_rows_bwd", dy.data_ptr(), idx.data_ptr(), inv.data_ptr(), _ptr(drop), dxk.data_ptr(), _ptr(dfill),
+              B, S, k, d, _stream())
+    return dxk
+
+
+def euler_step(x: Tensor, vc: Tensor, vu: Tensor | None, guidance: float, t_curr: float, t_prev: float,
+               want_x0: bool = True) -> tuple[Tensor, Tensor | None]:
+    _req(x, F32, "x")
+    _req(vc, vc.dtype, "vc")
+    x_prev = torch.empty_like(x)
+    x0 = torch.empty_like(x) if want_x0 else None
+    _lib_call("dlb_euler_step", x.data_ptr(), vc.data_ptr(), _ptr(vu), _dt(vc), guidance, t_curr, t_prev, x_prev.data_ptr(),
+              _ptr(x0), None, x.numel(), _stream())
+    return x_prev, x0
+
+
+def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, shadow: Tensor | None, *, lr: float, beta1: float, beta2: float,
+               eps: float, weight_decay: float, step: int, grad_scale: float = 1.0, ema: Tensor | None = None,
+               ema_decay: float = 0.0) -> None:
+    _lib_call("dlb_adamw_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(shadow), _ptr(ema), ema_decay,
+              p.numel(), lr, beta1, beta2, eps, weight_decay, step, grad_scale, _stream())
