@@ -296,7 +296,7 @@ def test_flow_interp_and_loss(gen, pred_dtype):
     assert rel_l2(xt, ref_xt) < 1e-6
     pred = mk(gen, B, C, H, W, dtype=pred_dtype)
     loss = ops.mse_fwd(pred, x0, eps)
-    pr = pred.float().requires_grad_(True)
+    pr = pred.float().clone().requires_grad_(True)
     ref = (((eps - x0) - pr) ** 2).reshape(B, -1).mean(-1).mean()
     assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
     ref.backward()
@@ -306,7 +306,7 @@ def test_flow_interp_and_loss(gen, pred_dtype):
     # x-prediction variant (flow.py:300-303)
     tc = t.clamp(min=0.05)
     loss_x = ops.mse_fwd(pred, x0, eps, xt=xt, t=tc)
-    pr2 = pred.float().requires_grad_(True)
+    pr2 = pred.float().clone().requires_grad_(True)
     v = (xt - pr2) / tc.view(-1, 1, 1, 1)
     ref2 = (((eps - x0) - v) ** 2).reshape(B, -1).mean(-1).mean()
     assert abs(loss_x.item() - ref2.item()) < 1e-4 * abs(ref2.item())
