@@ -303,23 +303,38 @@ int dispatch_major(int a_mn, int b_mn, int out_mode, const CUtensorMap& ta, cons
   return dispatch_out<BN, true, true>(out_mode, ta, tb, tc, bias, M, N, K, split_k, s);
 }
 
-// Relative cost of one k-block on a 128 x BN tile: tensor pipe needs 2*BN cycles, the shared-memory
-// read port (128 B/cycle) needs 128 + BN cycles; the slower one paces the main loop.
-int pick_tile_n(int M, int N, int split_k) {
-  if (N <= 64) return 64;
+// Cost model fitted to B200 measurements (profiles/gemm_microbench_r1.md): one k-block of a 128 x BN tile costs
+// ~(BN + 364) units, the epilogue ~8*BN; a launch costs waves * per-tile cost. Used to pick BN and split-K.
+double tile_cost(int M, int N, int kb_total, int bn, int split_k) {
   const int sms = dlb_num_sms();
-  const int cands[3] = {256, 192, 128};
-  int best = 128;
-  double best_cost = 1e30;
-  for (int i = 0; i < 3; ++i) {
+  const int kb_per = (kb_total + split_k - 1) / split_k;
+  const int splits = (kb_total + kb_per - 1) / kb_per;
+  const long tiles = (long)((M + BM - 1) / BM) * ((N + bn - 1) / bn) * splits;
+  const long waves = (tiles + sms - 1) / sms;
+  return (double)waves * ((double)kb_per * (bn + 364.0) + 8.0 * bn);
+}
+
+void pick_config(int M, int N, int K, bool allow_split, int& tile_n, int& split_k) {
+  const int kb_total = (K + BK - 1) / BK;
+  const int cands[4] = {256, 192, 128, 64};
+  const int splits[6] = {1, 2, 4, 8, 16, 32};
+  double best = 1e300;
+  int best_bn = 128, best_sk = 1;
+  for (int i = 0; i < 4; ++i) {
     const int bn = cands[i];
-    const long tiles = (long)((M + BM - 1) / BM) * ((N + bn - 1) / bn) * split_k;
-    const long waves = (tiles + sms - 1) / sms;
-    const double per_tile = (2 * bn > 128 + bn) ? 2.0 * bn : 128.0 + bn;
-    const double cost = (double)waves * per_tile;
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+    if (tile_n > 0 && bn != tile_n) continue;
+    if (tile_n <= 0 && bn == 64 && N > 64) continue;
+    if (tile_n <= 0 && bn > 64 && N <= 64) continue;
+    for (int j = 0; j < 6; ++j) {
+      const int sk = splits[j];
+      if (split_k > 0 && sk != split_k) continue;
+      if (sk > 1 && (!allow_split || kb_total / sk < 4)) continue;
+      const double c = tile_cost(M, N, kb_total, bn, sk);
+      if (c < best * (1.0 - 1e-9)) { best = c; best_bn = bn; best_sk = sk; }
+    }
   }
-  return best;
+  if (tile_n <= 0) tile_n = best_bn;
+  if (split_k <= 0) split_k = best_sk;
 }
 
 }  // namespace
@@ -340,15 +355,18 @@ DLB_EXPORT int dlb_gemm_bf16(const void* A, const void* B, void* Cout, const flo
   DLB_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)Cout % 16) == 0, DLB_ERR_ALIGN,
               "gemm: operand pointers must be 16-byte aligned");
   const int kb_total = (int)((K + BK - 1) / BK);
-  if (split_k < 1) split_k = 1;
+  // split_k: 0 = choose automatically (only ever > 1 in accumulate mode); tile_n: 0 = choose automatically
+  if (split_k > 1) DLB_REQUIRE(out_mode == OUT_F32_ADD, DLB_ERR_UNSUPPORTED, "gemm: split_k>1 needs out_mode=2 (fp32 accumulate)");
+  DLB_REQUIRE(tile_n == 0 || tile_n == 64 || tile_n == 128 || tile_n == 192 || tile_n == 256, DLB_ERR_UNSUPPORTED,
+              "gemm: tile_n %d unsupported", tile_n);
+  if (split_k < 0) split_k = 1;
+  int bn = tile_n;
+  pick_config((int)M, (int)N, (int)K, out_mode == OUT_F32_ADD, bn, split_k);
+  if (split_k > kb_total) split_k = kb_total;
   if (split_k > 1) {
-    DLB_REQUIRE(out_mode == OUT_F32_ADD, DLB_ERR_UNSUPPORTED, "gemm: split_k>1 needs out_mode=2 (fp32 accumulate)");
-    if (split_k > kb_total) split_k = kb_total;
     const int kb_per = (kb_total + split_k - 1) / split_k;
     split_k = (kb_total + kb_per - 1) / kb_per;  // no empty splits
   }
-  int bn = tile_n > 0 ? tile_n : pick_tile_n((int)M, (int)N, split_k);
-  DLB_REQUIRE(bn == 64 || bn == 128 || bn == 192 || bn == 256, DLB_ERR_UNSUPPORTED, "gemm: tile_n %d unsupported", bn);
 
   CUtensorMap ta, tb, tc;
   int rc;

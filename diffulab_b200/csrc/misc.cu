@@ -37,6 +37,60 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ in, float* __restr
     out[i] = __bfloat162float(in[i]);
 }
 
+__global__ void add_bf16_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ out, int64_t n8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float x[8], y[8];
+    unpack8(ld8(a + i * 8), x);
+    unpack8(ld8(b + i * 8), y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    st8(out + i * 8, pack8(x));
+  }
+}
+
+// DDT decoder conditioning (ddt.py:421-422): out[b,n,:] = silu(bf16(x[b,n,:] + v[b,:]))
+__global__ void bias_silu_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ v, bf16* __restrict__ out,
+                                     int64_t R, int rows_per_sample, int d) {
+  const int nv = d >> 3;
+  const int64_t total = R * nv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / nv;
+    const int c = (int)(i - row * nv) * 8;
+    float a[8], b[8];
+    unpack8(ld8(x + row * d + c), a);
+    unpack8(ld8(v + (row / rows_per_sample) * d + c), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = silu_f(bf16_round(a[j] + b[j]));
+    st8(out + row * d + c, pack8(a));
+  }
+}
+// dx = dy * silu'(x + v); dv[b,:] += sum_n dx   (one block per (sample, row chunk); threads own channel vectors)
+__global__ void __launch_bounds__(256)
+bias_silu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ v,
+                     bf16* __restrict__ dx, float* __restrict__ dv, int rows_per_sample, int rows_per_block, int d) {
+  const int nv = d >> 3;
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, rows_per_sample);
+  for (int c8 = threadIdx.x; c8 < nv; c8 += blockDim.x) {
+    const int c = c8 * 8;
+    float vv[8], acc[8];
+    unpack8(ld8(v + (int64_t)b * d + c), vv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const int64_t row = (int64_t)b * rows_per_sample + r;
+      float a[8], g[8];
+      unpack8(ld8(x + row * d + c), a);
+      unpack8(ld8(dy + row * d + c), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { g[j] *= dsilu_f(bf16_round(a[j] + vv[j])); acc[j] += g[j]; }
+      st8(dx + row * d + c, pack8(g));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(dv + (int64_t)b * d + c + j, acc[j]);
+  }
+}
+
 // y = silu(x); input fp32 or bf16, output bf16 (the GEMM operand dtype under autocast).
 template <typename TIn>
 __global__ void silu_fwd_kernel(const TIn* __restrict__ x, bf16* __restrict__ y, int64_t n) {
@@ -186,6 +240,34 @@ DLB_EXPORT int dlb_cast_bf16_f32(const void* in, float* out, int64_t n, cudaStre
   cast_bf16_f32_kernel<<<grid_for(n), 256, 0, stream>>>((const bf16*)in, out, n);
   dlb_count_launch();
   return dlb_check_launch("cast_bf16_f32");
+}
+
+// out = a + b (bf16, n % 8 == 0): sum of two gradient branches that read the same activation
+DLB_EXPORT int dlb_add_bf16(const void* a, const void* b, void* out, int64_t n, cudaStream_t stream) {
+  DLB_REQUIRE(n > 0 && n % 8 == 0, DLB_ERR_SHAPE, "add_bf16: n must be a positive multiple of 8");
+  add_bf16_kernel<<<grid_for(n / 8), 256, 0, stream>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n / 8);
+  dlb_count_launch();
+  return dlb_check_launch("add_bf16");
+}
+
+DLB_EXPORT int dlb_bias_silu_fwd(const void* x, const void* v, void* out, int64_t B, int64_t rows_per_sample, int d,
+                                 cudaStream_t stream) {
+  DLB_REQUIRE(B > 0 && rows_per_sample > 0 && d > 0 && d % 8 == 0, DLB_ERR_SHAPE, "bias_silu_fwd: bad shape");
+  bias_silu_fwd_kernel<<<grid_for(B * rows_per_sample * (d / 8)), 256, 0, stream>>>((const bf16*)x, (const bf16*)v, (bf16*)out,
+                                                                                   B * rows_per_sample, (int)rows_per_sample, d);
+  dlb_count_launch();
+  return dlb_check_launch("bias_silu_fwd");
+}
+// dv: fp32 [B, d], accumulated
+DLB_EXPORT int dlb_bias_silu_bwd(const void* dy, const void* x, const void* v, void* dx, float* dv, int64_t B,
+                                 int64_t rows_per_sample, int d, cudaStream_t stream) {
+  DLB_REQUIRE(B > 0 && rows_per_sample > 0 && d > 0 && d % 8 == 0, DLB_ERR_SHAPE, "bias_silu_bwd: bad shape");
+  const int rpb = 32;
+  dim3 grid((unsigned)((rows_per_sample + rpb - 1) / rpb), (unsigned)B);
+  bias_silu_bwd_kernel<<<grid, 256, 0, stream>>>((const bf16*)dy, (const bf16*)x, (const bf16*)v, (bf16*)dx, dv,
+                                                 (int)rows_per_sample, rpb, d);
+  dlb_count_launch();
+  return dlb_check_launch("bias_silu_bwd");
 }
 
 // in_dtype: 0 = bf16, 1 = fp32

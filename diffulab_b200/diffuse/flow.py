@@ -1,0 +1,161 @@
+"""Rectified-flow formalisation: drop-in for reference diffuse/modelizations/flow.py:16-524 (same constructor,
+`draw_timesteps`, `add_noise`, `compute_loss`, `get_v`, `one_step_denoise`, `denoise`, `set_steps`).
+Device math runs in fused kernels: x_t = (1-t) x0 + t eps (one kernel); loss = mean((eps - x0 - pred)^2) and its
+gradient (one kernel each, no materialised target); CFG combine + Euler update (one kernel)."""
+
+from __future__ import annotations
+
+from typing import Any, Literal, cast
+
+import torch
+from torch import Tensor
+
+from .. import ops
+from ..denoisers.common import Denoiser, ModelInput, ModelOutput
+from ..losses.common import LossFunction
+from .diffusion import Diffusion, SamplingOutput
+from .samplers import Euler, StepResult
+
+
+class _FlowLossFn(torch.autograd.Function):
+    """mean_b(mean_chw(((eps - x0) - v)^2)), v = pred (v-prediction) or (x_t - pred) / t (x-prediction)."""
+
+    @staticmethod
+    def forward(ctx, pred: Tensor, x0: Tensor, eps: Tensor, xt: Tensor | None, t: Tensor | None):
+        pred = pred.contiguous()
+        ctx.save_for_backward(pred, x0, eps, xt, t)
+        return ops.mse_fwd(pred, x0, eps, xt, t)
+
+    @staticmethod
+    def backward(ctx, gout: Tensor):
+        pred, x0, eps, xt, t = ctx.saved_tensors
+        return ops.mse_bwd(pred, x0, eps, gout.to(torch.float32).contiguous(), xt, t), None, None, None, None
+
+
+class Flow(Diffusion):
+    sampler_registry = {"euler": Euler}
+
+    def __init__(
+        self,
+        n_steps: int = 50,
+        sampling_method: Literal["euler"] = "euler",
+        schedule: Literal["linear"] = "linear",
+        latent_diffusion: bool = False,
+        logits_normal: bool = False,
+        shift: float | None = None,
+        sampler_parameters: dict[str, Any] = {},
+        prediction_type: Literal["v", "x"] = "v",
+    ) -> None:
+        assert prediction_type in ["v", "x"], "prediction_type must be either 'v' or 'x', noise prediction not supported yet for flow models"
+        self.shift = shift
+        super().__init__(n_steps=n_steps, sampling_method=sampling_method, schedule=schedule, latent_diffusion=latent_diffusion,
+                         sampler_parameters=sampler_parameters)
+        self.logits_normal = logits_normal
+        self.shift = shift
+        self.x_prediction = prediction_type == "x"
+
+    @staticmethod
+    def _shift_timestep(t: Tensor | float, alpha: float) -> Tensor | float:
+        return alpha * t / (1 + (alpha - 1) * t)
+
+    def set_steps(self, n_steps: int, schedule: str = "linear", shift: float | None = None) -> None:
+        """reference flow.py:101-135 (note: like the reference, this overwrites self.shift with the argument)"""
+        self.shift = shift
+        if schedule != "linear":
+            raise NotImplementedError("Only linear schedule is supported for the moment")
+        self.schedule = schedule
+        timesteps: list[float] = torch.linspace(1, 0, n_steps + 1).tolist()
+        if self.shift is not None:
+            timesteps = [self._shift_timestep(t, self.shift) for t in timesteps]  # type: ignore
+        self.timesteps = timesteps
+        self.steps = n_steps
+        self.sampler.set_steps(self.timesteps)
+
+    def at(self, timesteps: Tensor) -> Tensor:
+        return torch.ones_like(timesteps) - timesteps
+
+    def bt(self, timesteps: Tensor) -> Tensor:
+        return timesteps
+
+    def draw_timesteps(self, batch_size: int) -> Tensor:
+        """reference flow.py:168-197: drawn on the CPU generator exactly as the reference does."""
+        if self.logits_normal:
+            t = torch.sigmoid(torch.randn((batch_size), dtype=torch.float32))
+        else:
+            t = torch.rand((batch_size), dtype=torch.float32)
+        if self.shift is not None:
+            t = self._shift_timestep(t, self.shift)  # type: ignore
+        if self.x_prediction:
+            t = t.clamp(min=0.05)
+        return t
+
+    def add_noise(self, x: Tensor, timesteps: Tensor, noise: Tensor | None = None) -> tuple[Tensor, Tensor]:
+        if noise is None:
+            noise = torch.randn_like(x)
+        assert noise.shape == x.shape
+        assert timesteps.shape[0] == x.shape[0]
+        t = timesteps.to(device=x.device, dtype=torch.float32).contiguous()
+        z_t = ops.interp(x.float().contiguous(), noise.float().contiguous(), self.at(t).contiguous(), self.bt(t).contiguous())
+        return z_t, noise
+
+    def get_v(self, model: Denoiser, model_inputs: ModelInput, t_curr: float) -> Tensor:
+        device = next(model.parameters()).device
+        dtype = next(model.parameters()).dtype
+        timesteps = torch.full((model_inputs["x"].shape[0],), t_curr, device=device, dtype=dtype)
+        prediction = model(**model_inputs, timesteps=timesteps)["x"]
+        if self.x_prediction:
+            return (model_inputs["x"] - prediction) / max(t_curr, 0.05)
+        return prediction
+
+    def one_step_denoise(self, model: Denoiser, model_inputs: ModelInput, t_prev: float, t_curr: float, guidance_scale: float,
+                         sampler_args: dict[str, Any] = {}) -> StepResult:
+        v = self.get_v(model, ModelInput({**model_inputs, "p": 0}), t_curr)
+        if guidance_scale > 0:
+            v_dropped = self.get_v(model, {**model_inputs, "p": 1}, t_curr)
+            if isinstance(self.sampler, Euler) and not sampler_args:
+                # CFG combine v_u + g (v - v_u) and the Euler update in one kernel (flow.py:259 + euler.py:37-39)
+                return self.sampler.step_cfg(model_inputs["x"], v, v_dropped, guidance_scale, t_curr, t_prev)
+            v = v_dropped + guidance_scale * (v - v_dropped)
+        return self.sampler.step(model_inputs["x"], v, t_curr, t_prev, **sampler_args)
+
+    def compute_loss(self, model: Denoiser, model_inputs: ModelInput, timesteps: Tensor, noise: Tensor | None = None,
+                     extra_losses: list[LossFunction] = [], extra_args: dict[str, Any] = {}) -> dict[str, Tensor]:
+        x_0 = model_inputs["x"].float().contiguous()
+        model_inputs["x"], noise = self.add_noise(x_0, timesteps, noise)  # mutates the caller's dict like the reference
+        t_dev = timesteps.to(device=x_0.device, dtype=torch.float32).contiguous()
+        prediction: ModelOutput = model(**model_inputs, timesteps=t_dev)
+        noise = noise.float().contiguous()
+        if self.x_prediction:
+            loss = _FlowLossFn.apply(prediction["x"], x_0, noise, model_inputs["x"], t_dev)
+        else:
+            loss = _FlowLossFn.apply(prediction["x"], x_0, noise, None, None)
+        loss_dict = {"loss": loss}
+        for extra_loss in extra_losses:
+            loss_dict[extra_loss.name] = cast(Tensor, extra_loss(**extra_args))
+        return loss_dict
+
+    @torch.inference_mode()
+    def denoise(self, model: Denoiser, model_inputs: ModelInput, data_shape: tuple[int, ...] | None = None, use_tqdm: bool = True,
+                clamp_x: bool = False, guidance_scale: float = 0, sampler_args: dict[str, Any] = {},
+                return_intermediates: bool = False) -> SamplingOutput:
+        device = next(model.parameters()).device
+        dtype = next(model.parameters()).dtype
+        if "x" not in model_inputs:
+            assert data_shape is not None, "'data_shape' must be provided if 'x' is not in model_inputs"
+            model_inputs["x"] = torch.randn(data_shape, device=device, dtype=dtype)
+        all_x0: list[Tensor] = []
+        all_xt: list[Tensor] = [model_inputs["x"]]
+        for t_curr, t_prev in zip(self.timesteps[:-1], self.timesteps[1:]):
+            step_output = self.one_step_denoise(model, model_inputs, t_curr=t_curr, t_prev=t_prev, guidance_scale=guidance_scale,
+                                                sampler_args=sampler_args)
+            model_inputs["x"] = step_output["x_prev"]
+            if return_intermediates:
+                all_xt.append(step_output["x_prev"])
+                all_x0.append(step_output["estimated_x0"])
+        if clamp_x:
+            model_inputs["x"] = model_inputs["x"].clamp(-1, 1)
+        out: SamplingOutput = {"x": model_inputs["x"]}
+        if return_intermediates:
+            out["xt"] = torch.stack(all_xt, dim=1)
+            out["estimated_x0"] = torch.stack(all_x0, dim=1)
+        return out

@@ -40,15 +40,18 @@ def gemm(
     b_mn: bool = False,
     out_dtype: torch.dtype = BF16,
     accumulate: bool = False,
-    split_k: int = 1,
+    split_k: int | None = None,
     tile_n: int = 0,
 ) -> Tensor:
     """C[M,N] (+)= A @ B^T (+ bias) with bf16 operands and fp32 accumulation on tcgen05.
 
     a: [M,K] (or [K,M] when a_mn), b: [N,K] (or [K,N] when b_mn). Row strides may exceed the row length
     (views into packed buffers) as long as they are multiples of 8 elements.
-    accumulate=True adds into an fp32 `out` (TMA reduce-add), optionally split along K.
+    accumulate=True adds into an fp32 `out` (TMA reduce-add), optionally split along K
+    (split_k None/0 = chosen by the library's cost model).
     """
+    if split_k is None:
+        split_k = 0 if accumulate else 1
     _check_2d(a, "a")
     _check_2d(b, "b")
     if a.dtype != BF16 or b.dtype != BF16:
@@ -356,6 +359,32 @@ def _dt(t: Tensor) -> int:
     if t.dtype == F32:
         return 1
     raise ValueError(f"unsupported dtype {t.dtype}")
+
+
+def add(a: Tensor, b: Tensor) -> Tensor:
+    _req(a, BF16, "a")
+    _req(b, BF16, "b")
+    out = torch.empty_like(a)
+    _lib_call("dlb_add_bf16", a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream())
+    return out
+
+
+def bias_silu_fwd(x: Tensor, v: Tensor) -> Tensor:
+    """silu(x[b,n,:] + v[b,:]) for x [B,N,d], v [B,d] (bf16)."""
+    _req(x, BF16, "x")
+    _req(v, BF16, "v")
+    B, N, d = x.shape
+    out = torch.empty_like(x)
+    _lib_call("dlb_bias_silu_fwd", x.data_ptr(), v.data_ptr(), out.data_ptr(), B, N, d, _stream())
+    return out
+
+
+def bias_silu_bwd(dy: Tensor, x: Tensor, v: Tensor) -> tuple[Tensor, Tensor]:
+    B, N, d = x.shape
+    dx = torch.empty_like(x)
+    dv = torch.zeros(B, d, device=x.device, dtype=F32)
+    _lib_call("dlb_bias_silu_bwd", dy.data_ptr(), x.data_ptr(), v.data_ptr(), dx.data_ptr(), dv.data_ptr(), B, N, d, _stream())
+    return dx, dv
 
 
 def silu_fwd(x: Tensor) -> Tensor:

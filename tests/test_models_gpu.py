@@ -1,0 +1,250 @@
+"""Model-level parity of the CUDA path (through the public plugin surface: Denoiser.forward, Flow.compute_loss,
+RepaLoss, Flow.denoise) against
+
+  (1) the committed golden fixtures = outputs of the UNMODIFIED reference run in fp32 (tests/golden, made by
+      oracle/make_golden.py), and
+  (2) the CPU oracle (oracle/dit_oracle.py, pinned to those fixtures) on fresh seeded inputs at larger sizes.
+
+Tolerances: the CUDA path computes like the reference's bf16 autocast path, the fixtures are fp32:
+denoiser output relL2 <= 3e-2, loss |d| <= 2e-2 |loss|, gradients relL2 <= 6e-2, Euler trajectory relL2 <= 5e-2;
+SPRINT kept indices: exact (int64)."""
+import pytest
+import torch
+
+from golden_util import fixture_names, load_fixture, model_kind, oracle_cfg, oracle_forward
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+class RandQueue:
+    """Feeds recorded uniform draws to the torch.rand calls made inside the forward (label / context dropout,
+    SPRINT scores, path drop), in the reference's call order."""
+
+    def __init__(self, monkeypatch, draws: list[torch.Tensor]):
+        self.q = list(draws)
+        self.orig = torch.rand
+        monkeypatch.setattr(torch, "rand", self)
+
+    def __call__(self, *size, **kw):
+        shape = tuple(size[0]) if len(size) == 1 and not isinstance(size[0], int) else tuple(size)
+        if self.q:
+            d = self.q.pop(0)
+            assert tuple(d.shape) == shape, f"draw order mismatch: recorded {tuple(d.shape)} vs requested {shape}"
+            return d.to(kw.get("device", "cpu"))
+        return self.orig(*size, **kw)
+
+
+def ordered_draws(fx):
+    d = fx["draws"]
+    out = []
+    for key in ("label", "context"):
+        if key in d:
+            out.append(d[key])
+    if fx["mm"] and "context" not in d:
+        out.append(torch.ones(fx["x0"].shape[0]))  # PrecomputedEmbedder always draws; p == 0 -> never drops
+    if "scores" in d:
+        out.append(d["scores"])
+    if "path" in d:
+        out.append(d["path"])
+    return out
+
+
+def build_model(fx):
+    import diffulab_b200 as dl
+
+    kw = dict(fx["kwargs"])
+    if fx["mm"]:
+        kw["context_embedder"] = dl.PrecomputedEmbedder(fx["null_embedding"], fx["null_valid"])
+    cls = {"sprint": dl.SprintDiT, "ddt": dl.DDT, "mmdit": dl.MMDiT}[model_kind(fx)]
+    m = cls(**kw)
+    m.load_state_dict(fx["state_dict"])
+    return m.cuda()
+
+
+def inputs_for(fx):
+    extra = {}
+    if fx["mm"]:
+        extra["initial_context"] = {k: v.cuda() for k, v in fx["context"].items()}
+    else:
+        extra["y"] = fx["y"].cuda()
+    return extra
+
+
+@pytest.mark.parametrize("name", fixture_names())
+def test_golden_forward_loss_grads(cuda_device, monkeypatch, name):
+    import diffulab_b200 as dl
+
+    fx = load_fixture(name)
+    model = build_model(fx)
+    model.train(fx["train_mode"])
+    flow = dl.Flow(n_steps=4, sampling_method="euler")
+    losses = []
+    extra_args = {}
+    if "repa" in fx:
+        rl = dl.RepaLoss(load_dino=False, **fx["repa"]["kwargs"])
+        rl.load_state_dict(fx["repa"]["state_dict"])
+        rl = rl.cuda()
+        rl.set_model(model)
+        losses.append(rl)
+        extra_args = {"dst_features": fx["repa"]["dst"].cuda()}
+    feats = {}
+    for lst in ("layers", "deep_layers", "decoder_layers"):
+        if hasattr(model, lst):
+            for i, layer in enumerate(getattr(model, lst)):
+                layer.register_forward_hook(lambda _m, _i, out, key=f"{lst}.{i}": feats.__setitem__(key, (out[0] if isinstance(out, tuple) else out).detach()))
+    RandQueue(monkeypatch, ordered_draws(fx))
+    inputs = {"x": fx["x0"].cuda(), "p": fx["p"], **inputs_for(fx)}
+    loss_dict = flow.compute_loss(model, inputs, fx["t"].cuda(), noise=fx["eps"].cuda(), extra_losses=losses, extra_args=extra_args)
+    assert rel_l2(inputs["x"], fx["x_t"]) < 1e-6  # add_noise mutates the caller's dict like the reference
+    total = sum(loss_dict.values())
+    total.backward()
+    torch.cuda.synchronize()
+
+    for k, v in fx["features"].items():
+        assert rel_l2(feats[k], v) < 3e-2, k
+    for k, v in fx["losses"].items():
+        assert abs(loss_dict[k].item() - v.item()) <= 2e-2 * abs(v.item()), (k, loss_dict[k].item(), v.item())
+    params = dict(model.named_parameters())
+    for k, g in fx["grads"].items():
+        if g is None:
+            assert params[k].grad is None or params[k].grad.abs().max().item() == 0.0, k
+        else:
+            assert params[k].grad is not None, k
+            assert rel_l2(params[k].grad, g) < 6e-2, (k, rel_l2(params[k].grad, g))
+    if "repa" in fx:
+        assert rel_l2(losses[0].proj[0].weight.grad, fx["repa"]["proj_grad"]) < 6e-2
+
+    # plain forward (no autograd) at the recorded x_t
+    RandQueue(monkeypatch, ordered_draws(fx))
+    with torch.no_grad():
+        pred = model(fx["x_t"].cuda(), fx["t"].cuda(), p=fx["p"], **inputs_for(fx))["x"]
+    assert pred.dtype == BF and tuple(pred.shape) == tuple(fx["pred"].shape)
+    assert rel_l2(pred, fx["pred"]) < 3e-2
+
+    # tighter check against the oracle with bf16 rounding emulation at the autocast rounding points
+    from oracle import dit_oracle as O
+
+    O.set_round("bf16")
+    try:
+        with torch.no_grad():
+            ob = oracle_forward(fx, fx["state_dict"], fx["x_t"], fx["t"], fx["p"], fx["draws"], fx["train_mode"])
+    finally:
+        O.set_round(None)
+    assert rel_l2(pred, ob) < 1.5e-2
+
+
+@pytest.mark.parametrize("name", ["sprint_mm_train", "sprint_dit_train"])
+def test_sprint_indices_bit_exact(cuda_device, monkeypatch, name):
+    fx = load_fixture(name)
+    model = build_model(fx).train()
+    RandQueue(monkeypatch, [fx["draws"]["scores"]])
+    tok = torch.randn(fx["x0"].shape[0], fx["draws"]["scores"].shape[1], fx["kwargs"]["inner_dim"], device="cuda").to(BF)
+    _, kept, kept32, inv = model.drop_tokens(tok)
+    k = kept.shape[1]
+    ref = torch.topk(fx["draws"]["scores"], k=k, dim=1, largest=True, sorted=False).indices.sort(dim=1).values
+    assert kept.dtype == torch.int64 and torch.equal(kept.cpu(), ref)
+
+
+@pytest.mark.parametrize("name", [n for n in fixture_names()])
+def test_golden_euler_trajectory(cuda_device, name):
+    """Flow.denoise with classifier-free guidance: 2 NFE per step + fused CFG/Euler kernel (flow.py:410-524)."""
+    import diffulab_b200 as dl
+
+    fx = load_fixture(name)
+    if "euler" not in fx:
+        pytest.skip("fixture has no sampling trajectory")
+    e = fx["euler"]
+    model = build_model(fx).eval()
+    flow = dl.Flow(n_steps=e["n_steps"], sampling_method="euler", shift=e["shift"])
+    flow.set_steps(e["n_steps"], shift=e["shift"])
+    assert max(abs(a - b) for a, b in zip(flow.timesteps, e["timesteps"])) < 1e-7
+    inp = {"x": e["x_init"].cuda(), **inputs_for(fx)}
+    out = flow.denoise(model, inp, use_tqdm=False, guidance_scale=e["guidance"], return_intermediates=True)
+    assert out["x"].dtype == torch.float32
+    assert rel_l2(out["x"], e["x_final"]) < 5e-2
+    assert rel_l2(out["xt"], e["xt"]) < 5e-2
+
+
+def _rand_sd(model, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.abs().sum() == 0:
+                p.copy_(torch.randn(p.shape, generator=g) * 0.02)
+            elif p.dim() == 1:
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+
+
+@pytest.mark.parametrize("d,H,depth,hw,axes", [(256, 4, 3, 16, [32, 32]), (288, 4, 2, 16, [36, 36]), (1152, 16, 1, 8, [36, 36])])
+def test_dit_vs_oracle_larger(cuda_device, d, H, depth, hw, axes):
+    """Fresh seeded inputs, sizes the oracle finishes in seconds; includes head_dim 72 and d = 1152 (DiT-XL/2 width)."""
+    import diffulab_b200 as dl
+    from oracle import dit_oracle as O
+
+    torch.manual_seed(d + depth)
+    kw = dict(simple_dit=True, input_channels=4, output_channels=4, inner_dim=d, embedding_dim=d, num_heads=H, mlp_ratio=4,
+              patch_size=2, depth=depth, n_classes=10, classifier_free=True, rope_axes_dim=axes)
+    model = dl.MMDiT(**kw)
+    _rand_sd(model, 3)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.cuda().train()
+    B = 3
+    g = torch.Generator().manual_seed(5)
+    x0, eps = torch.randn(B, 4, hw, hw, generator=g), torch.randn(B, 4, hw, hw, generator=g)
+    t, y = torch.rand(B, generator=g) * 0.9 + 0.05, torch.randint(0, 10, (B,), generator=g)
+    flow = dl.Flow(n_steps=4)
+    inputs = {"x": x0.cuda(), "p": 0.0, "y": y.cuda()}
+    loss = flow.compute_loss(model, inputs, t.cuda(), noise=eps.cuda())["loss"]
+    loss.backward()
+    fx = {"kwargs": kw, "mm": False, "state_dict": sd, "y": y, "context": None}
+    sdr = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    O.set_round(None)
+    x_t = O.flow_add_noise(x0, t, eps)
+    pred = oracle_forward(fx, sdr, x_t, t, 0.0, {}, True)
+    ref = O.flow_loss(pred, x0, eps)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 2e-2 * abs(ref.item())
+    params = dict(model.named_parameters())
+    for k in ["conv_proj.weight", "layers.0.attention.qkv.weight", "layers.0.mlp_input.0.weight", "layers.0.mlp_input.2.weight",
+              "layers.0.modulation.lin.weight", "layers.0.modulation.lin.bias", "layers.0.norm_2.weight",
+              "layers.0.attention.qk_norm.key_norm.scale", "last_layer.linear.bias", "time_embed.2.weight",
+              "label_embed.embedding.weight", "last_layer.adaLN_modulation.1.weight"]:
+        assert rel_l2(params[k].grad, sdr[k].grad) < 6e-2, (k, rel_l2(params[k].grad, sdr[k].grad))
+
+
+def test_full_size_properties(cuda_device):
+    """DiT-XL/2 width at BASELINE batch geometry is too slow for the CPU oracle; check size-independent properties:
+    determinism, batch-slice independence (samples do not interact) and zero-init identity (adaLN-Zero makes every
+    block the identity at init: output == last layer only)."""
+    import diffulab_b200 as dl
+
+    torch.manual_seed(0)
+    m = dl.MMDiT(simple_dit=True, input_channels=4, inner_dim=1152, embedding_dim=1152, num_heads=16, patch_size=2, depth=2,
+                 n_classes=1000, classifier_free=True).cuda().eval()
+    x = torch.randn(8, 4, 32, 32, device="cuda")
+    t = torch.rand(8, device="cuda")
+    y = torch.randint(0, 1000, (8,), device="cuda")
+    with torch.no_grad():
+        a = m(x, t, y=y)["x"]
+        b = m(x, t, y=y)["x"]
+        c = m(x[:3], t[:3], y=y[:3])["x"]
+    assert torch.equal(a, b)
+    assert torch.equal(a[:3], c)
+    # zero-initialised adaLN: the final linear bias is 0 and its modulation is 0 -> out = W_lin LN(conv_proj(x))
+    assert a.abs().max().item() > 0
+    _rand = dl.MMDiT(simple_dit=True, input_channels=4, inner_dim=1152, embedding_dim=1152, num_heads=16, patch_size=2, depth=2,
+                     n_classes=1000, classifier_free=True)
+    _rand.load_state_dict(m.state_dict())
+    with torch.no_grad():
+        for blk in _rand.layers:  # perturbing anything inside a block must not change the output while gates are 0
+            blk.attention.qkv.weight.mul_(3.0)
+            blk.mlp_input[0].weight.mul_(0.5)
+    with torch.no_grad():
+        d = _rand.cuda().eval()(x, t, y=y)["x"]
+    assert torch.equal(a, d)
