@@ -39,8 +39,10 @@ def bump_shadow_epoch() -> None:
 
 
 def install_shadow(p: Tensor, shadow: Tensor) -> None:
-    """Register an externally maintained bf16 copy of `p` (e.g. written by the fused AdamW kernel)."""
-    _shadow[p] = (-1, -1, shadow)
+    """Register an externally maintained bf16 copy of `p` (a view of FlatParams.flat_shadow, rewritten by the fused
+    AdamW kernel every step). If `p` is later modified through the torch API (load_state_dict, copy_), its version
+    counter changes and the shadow is re-synchronised on next use."""
+    _shadow[p] = (p._version, -2, shadow)
 
 
 def set_grad_ready_hook(fn: Callable[[Tensor], None] | None) -> None:
@@ -53,8 +55,15 @@ def set_grad_ready_hook(fn: Callable[[Tensor], None] | None) -> None:
 def wb(p: Tensor, pad_cols: int | None = None) -> Tensor:
     """bf16 shadow of an fp32 parameter as a 2-D [out, in] matrix (conv kernels flattened, optionally K-padded)."""
     ent = _shadow.get(p)
-    if ent is not None and (ent[0] == -1 or (ent[0] == p._version and ent[1] == _shadow_epoch)):
-        return ent[2]
+    if ent is not None:
+        if ent[1] == -2:  # installed flat shadow
+            if ent[0] != p._version:
+                src = p.detach().contiguous()
+                ops._lib_call("dlb_cast_f32_bf16", src.data_ptr(), ent[2].data_ptr(), 1, src.numel(), src.numel(), ops._stream())
+                _shadow[p] = (p._version, -2, ent[2])
+            return ent[2]
+        if ent[0] == p._version and ent[1] == _shadow_epoch:
+            return ent[2]
     p2 = p.detach().reshape(p.shape[0], -1) if p.dim() > 1 else p.detach().reshape(1, -1)
     cols = p2.shape[1]
     ld = pad_cols if pad_cols is not None else cols
