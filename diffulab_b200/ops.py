@@ -19,6 +19,50 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# Optional per-call device timing (CUDA events on the launching stream). `profile_start()` turns it on; every C-ABI
+# call then records (name, work, start_event, end_event); `profile_stop()` synchronises and returns
+# {name: {"calls", "ms", "work"}} where work = FLOPs for the GEMM and 0 otherwise. Used by bench.py's roofline.
+_prof: list | None = None
+
+
+def profile_start() -> None:
+    global _prof
+    _prof = []
+
+
+def profile_stop() -> dict[str, dict[str, float]]:
+    global _prof
+    rec, _prof = _prof or [], None
+    torch.cuda.synchronize()
+    out: dict[str, dict[str, float]] = {}
+    for name, work, e0, e1 in rec:
+        d = out.setdefault(name, {"calls": 0, "ms": 0.0, "work": 0.0})
+        d["calls"] += 1
+        d["ms"] += e0.elapsed_time(e1)
+        d["work"] += work
+    return out
+
+
+class _Timed:
+    __slots__ = ("name", "work", "e0")
+
+    def __init__(self, name: str, work: float = 0.0):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _prof is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof.append((self.name, self.work, self.e0, e1))
+        return False
+
+
 def _ptr(t: Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
 
@@ -73,10 +117,12 @@ def gemm(
         raise ValueError(f"gemm: out has shape {tuple(out.shape)}, expected {(M, N)}")
     if bias is not None and (bias.dtype != F32 or bias.numel() != N or not bias.is_contiguous()):
         raise ValueError("gemm: bias must be a contiguous fp32 vector of length N")
-    rc = _lib.load().dlb_gemm_bf16(
-        a.data_ptr(), b.data_ptr(), out.data_ptr(), _ptr(bias), M, N, K,
-        a.stride(0), b.stride(0), out.stride(0), int(a_mn), int(b_mn), mode, split_k, tile_n, _stream(),
-    )
+    kind = "gemm_wgrad" if (a_mn and b_mn) else ("gemm_dgrad" if b_mn else "gemm_fwd")
+    with _Timed(kind, 2.0 * M * N * K):
+        rc = _lib.load().dlb_gemm_bf16(
+            a.data_ptr(), b.data_ptr(), out.data_ptr(), _ptr(bias), M, N, K,
+            a.stride(0), b.stride(0), out.stride(0), int(a_mn), int(b_mn), mode, split_k, tile_n, _stream(),
+        )
     _lib.check(rc, "dlb_gemm_bf16")
     return out
 
@@ -85,7 +131,11 @@ def gemm(
 # helpers
 # ---------------------------------------------------------------------------------------------------------
 def _lib_call(name: str, *args) -> None:
-    rc = getattr(_lib.load(), name)(*args)
+    if _prof is not None:
+        with _Timed(name[4:]):
+            rc = getattr(_lib.load(), name)(*args)
+    else:
+        rc = getattr(_lib.load(), name)(*args)
     _lib.check(rc, name)
 
 
