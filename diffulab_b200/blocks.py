@@ -238,17 +238,18 @@ def attn_fwd(hs: list[Tensor], streams: list[StreamSpec], rope: RopeCtx, B: int,
     w_out is None (single-stream block handles the projection itself), else after it."""
     d = hs[0].shape[-1]
     hd = d // H
-    qkvs, qks, specs = [], [], []
+    qkvs, qks, rrmss, specs = [], [], [], []
     for h, s in zip(hs, streams):
         qkv = ops.gemm(h, wb(s.w_qkv))
-        qk = ops.qknorm_rope_fwd(qkv, s.sq.detach(), s.sk.detach(), rope.cos, rope.sin, hd, tokens_per_sample=s.len,
-                                 pos_offset=s.pos_offset, pos_idx=s.pos_idx)
+        qk, rrms = ops.qknorm_rope_fwd(qkv, s.sq.detach(), s.sk.detach(), rope.cos, rope.sin, hd, tokens_per_sample=s.len,
+                                       pos_offset=s.pos_offset, pos_idx=s.pos_idx)
         qkvs.append(qkv)
         qks.append(qk)
+        rrmss.append(rrms)
         specs.append(ops.AttnSegSpec(qk, qkv, s.len))
     outs, lse = ops.attn_fwd(specs, B, H, hd, hd**-0.5, kmask)
     projs = [ops.gemm(o, wb(s.w_out)) for o, s in zip(outs, streams)]
-    save.update(hs=hs, qkvs=qkvs, qks=qks, outs=outs, lse=lse)
+    save.update(hs=hs, qkvs=qkvs, qks=qks, rrmss=rrmss, outs=outs, lse=lse)
     return projs
 
 
@@ -267,11 +268,8 @@ def attn_bwd(dprojs: list[Tensor | None], streams: list[StreamSpec], rope: RopeC
     dqkvs = [torch.empty_like(q) for q in save["qkvs"]]
     dqks = ops.attn_bwd(specs, save["outs"], douts, save["lse"], B, H, hd, hd**-0.5, dqkvs, kmask)
     dhs = []
-    for dqk, dqkv, qkv, h, s in zip(dqks, dqkvs, save["qkvs"], save["hs"], streams):
-        dsq, dsk = vgrad(s.sq), vgrad(s.sk)
-        if dsq is None:  # frozen scales: still need scratch accumulators for the kernel
-            dsq, dsk = torch.zeros(d, device=h.device, dtype=F32), torch.zeros(d, device=h.device, dtype=F32)
-        ops.qknorm_rope_bwd(dqk, qkv, s.sq.detach(), s.sk.detach(), rope.cos, rope.sin, hd, dqkv, dsq, dsk,
+    for dqk, dqkv, qkv, rrms, h, s in zip(dqks, dqkvs, save["qkvs"], save["rrmss"], save["hs"], streams):
+        ops.qknorm_rope_bwd(dqk, qkv, rrms, s.sq.detach(), s.sk.detach(), rope.cos, rope.sin, hd, dqkv, vgrad(s.sq), vgrad(s.sk),
                             tokens_per_sample=s.len, pos_offset=s.pos_offset, pos_idx=s.pos_idx)
         _ready(s.sq)
         _ready(s.sk)

@@ -79,127 +79,134 @@ ln_modulate_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// LayerNorm + modulate backward.
-//   grid.y = modulation group (a sample, or 1 group holding every row in per-token mode)
-//   Each warp walks `rows_per_warp` rows of its group and keeps two column accumulators:
-//     per-sample mode : S1 = sum dy           S2 = sum dy * xhat
-//     per-token  mode : S1 = sum dy*(1+scale) S2 = sum dy*(1+scale)*xhat   (dscale/dshift written per row)
-//   which are enough for dshift, dscale, dw and db ("LN backward algebra").
+// LayerNorm + modulate backward, two bandwidth-shaped kernels:
+//  (1) rows: one warp per token row -> dx (+dres); per-token mode also writes dscale/dshift rows.
+//  (2) cols: one thread per 8-channel vector, marching down a chunk of rows -> two column accumulators
+//        per-sample mode : S1 = sum dy           S2 = sum dy * xhat
+//        per-token  mode : S1 = sum dy*(1+scale) S2 = sum dy*(1+scale)*xhat
+//      which are enough for dshift, dscale, dw and db ("LN backward algebra"); one atomic per column
+//      per block. Keeping the column sums out of kernel (1) keeps it at ~100 registers (2+ CTAs per SM).
 // ---------------------------------------------------------------------------------------------------------
 template <int VPL, bool PER_TOKEN>
-__global__ void __launch_bounds__(256)
-ln_modulate_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean_in,
-                       const float* __restrict__ rstd_in, const float* __restrict__ w, const float* __restrict__ b,
-                       const bf16* __restrict__ scale, int64_t mod_ld, int64_t rows_per_group,
-                       const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dscale,
-                       float* __restrict__ dshift, int64_t dmod_ld, bf16* __restrict__ dscale_tok,
-                       bf16* __restrict__ dshift_tok, int64_t dtok_ld, float* __restrict__ dw,
-                       float* __restrict__ db, int d, int rows_per_warp) {
-  extern __shared__ float red[];  // [2][warps][d]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+__global__ void __launch_bounds__(128)
+ln_modulate_bwd_rows_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean_in,
+                            const float* __restrict__ rstd_in, const float* __restrict__ w, const float* __restrict__ b,
+                            const bf16* __restrict__ scale, int64_t mod_ld, int64_t rows_per_mod,
+                            const bf16* __restrict__ dres, bf16* __restrict__ dx, bf16* __restrict__ dscale_tok,
+                            bf16* __restrict__ dshift_tok, int64_t dtok_ld, int64_t R, int d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
   const int nv = d >> 3;
-  const int64_t group = blockIdx.y;
-  const int64_t r_begin = ((int64_t)blockIdx.x * nwarps + warp) * rows_per_warp;
-  const int64_t r_end = min(r_begin + rows_per_warp, rows_per_group);
-
-  float S1[VPL][8], S2[VPL][8];
-#pragma unroll
-  for (int i = 0; i < VPL; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { S1[i][j] = 0.f; S2[i][j] = 0.f; }
-
-  for (int64_t rl = r_begin; rl < r_end; ++rl) {
-    const int64_t row = group * rows_per_group + rl;
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    const bf16* sc = scale + (PER_TOKEN ? row : group) * mod_ld;
-    float xh[VPL][8], gw[VPL][8];
-    float m1 = 0.f, m2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nv) {
-        float g[8], s[8];
-        unpack8(ld8(x + row * d + v * 8), xh[i]);
-        unpack8(ld8(dy + row * d + v * 8), g);
-        unpack8(ld8(sc + v * 8), s);
-        float wv[8];
-        if (w) {
-          *reinterpret_cast<float4*>(wv) = __ldg(reinterpret_cast<const float4*>(w + v * 8));
-          *reinterpret_cast<float4*>(wv + 4) = __ldg(reinterpret_cast<const float4*>(w + v * 8 + 4));
-        }
-        float ds_tok[8], dsh_tok[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xh[i][j] - mean) * rstd;
-          const float one_s = bf16_round(1.f + s[j]);
-          const float gu = g[j] * one_s;  // grad wrt the affine LayerNorm output u
-          if (PER_TOKEN) {
-            S1[i][j] += gu;
-            S2[i][j] += gu * xh[i][j];
-            float u = xh[i][j];
-            if (w) u = u * wv[j] + __ldg(b + v * 8 + j);
-            ds_tok[j] = g[j] * u;
-            dsh_tok[j] = g[j];
-          } else {
-            S1[i][j] += g[j];
-            S2[i][j] += g[j] * xh[i][j];
-          }
-          gw[i][j] = w ? gu * wv[j] : gu;
-          m1 += gw[i][j];
-          m2 += gw[i][j] * xh[i][j];
-        }
-        if (PER_TOKEN) {
-          st8(dscale_tok + row * dtok_ld + v * 8, pack8(ds_tok));
-          st8(dshift_tok + row * dtok_ld + v * 8, pack8(dsh_tok));
-        }
-      }
-    }
-    m1 = warp_sum(m1) / d;
-    m2 = warp_sum(m2) / d;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nv) {
-        float o[8];
-        if (dres) unpack8(ld8(dres + row * d + v * 8), o);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float t = rstd * (gw[i][j] - m1 - xh[i][j] * m2);
-          o[j] = dres ? o[j] + t : t;
-        }
-        st8(dx + row * d + v * 8, pack8(o));
-      }
-    }
-  }
-
-  // cross-warp reduction of the column accumulators, then one atomic per column per block
-  float* r1 = red;
-  float* r2 = red + (size_t)nwarps * d;
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  const bf16* sc = scale + (row / rows_per_mod) * mod_ld;
+  float xh[VPL][8], gw[VPL][8];
+  float m1 = 0.f, m2 = 0.f;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int v = lane + 32 * i;
     if (v < nv) {
+      float g[8], s[8];
+      unpack8(ld8(x + row * d + v * 8), xh[i]);
+      unpack8(ld8(dy + row * d + v * 8), g);
+      unpack8(ld8(sc + v * 8), s);
+      float wv[8], bv[8];
+      if (w) {
+        *reinterpret_cast<float4*>(wv) = __ldg(reinterpret_cast<const float4*>(w + v * 8));
+        *reinterpret_cast<float4*>(wv + 4) = __ldg(reinterpret_cast<const float4*>(w + v * 8 + 4));
+        if (PER_TOKEN) {
+          *reinterpret_cast<float4*>(bv) = __ldg(reinterpret_cast<const float4*>(b + v * 8));
+          *reinterpret_cast<float4*>(bv + 4) = __ldg(reinterpret_cast<const float4*>(b + v * 8 + 4));
+        }
+      }
+      float ds_tok[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        r1[(size_t)warp * d + v * 8 + j] = S1[i][j];
-        r2[(size_t)warp * d + v * 8 + j] = S2[i][j];
+        xh[i][j] = (xh[i][j] - mean) * rstd;
+        const float gu = g[j] * bf16_round(1.f + s[j]);  // grad wrt the affine LayerNorm output u
+        if (PER_TOKEN) ds_tok[j] = g[j] * (w ? xh[i][j] * wv[j] + bv[j] : xh[i][j]);
+        gw[i][j] = w ? gu * wv[j] : gu;
+        m1 += gw[i][j];
+        m2 += gw[i][j] * xh[i][j];
+      }
+      if (PER_TOKEN) {
+        st8(dscale_tok + row * dtok_ld + v * 8, pack8(ds_tok));
+        st8(dshift_tok + row * dtok_ld + v * 8, pack8(g));
       }
     }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float a1 = 0.f, a2 = 0.f;
-    for (int wi = 0; wi < nwarps; ++wi) { a1 += r1[(size_t)wi * d + c]; a2 += r2[(size_t)wi * d + c]; }
+  m1 = warp_sum(m1) / d;
+  m2 = warp_sum(m2) / d;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nv) {
+      float o[8];
+      if (dres) unpack8(ld8(dres + row * d + v * 8), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = rstd * (gw[i][j] - m1 - xh[i][j] * m2);
+        o[j] = dres ? o[j] + t : t;
+      }
+      st8(dx + row * d + v * 8, pack8(o));
+    }
+  }
+}
+
+// grid (col chunks, row chunks, groups); thread = one 8-channel vector, marching down its row chunk
+template <bool PER_TOKEN>
+__global__ void __launch_bounds__(256)
+ln_modulate_bwd_cols_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean_in,
+                            const float* __restrict__ rstd_in, const float* __restrict__ w, const float* __restrict__ b,
+                            const bf16* __restrict__ scale, int64_t mod_ld, int64_t rows_per_group,
+                            float* __restrict__ dscale, float* __restrict__ dshift, int64_t dmod_ld,
+                            float* __restrict__ dw, float* __restrict__ db, int d, int rows_per_block) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= (d >> 3)) return;
+  const int c = v * 8;
+  const int64_t group = blockIdx.z;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(r0 + rows_per_block, rows_per_group);
+  float S1[8], S2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { S1[j] = 0.f; S2[j] = 0.f; }
+  const int64_t base = group * rows_per_group;
+#pragma unroll 4
+  for (int64_t rl = r0; rl < r1; ++rl) {
+    const int64_t row = base + rl;
+    float xv[8], g[8];
+    unpack8(ld8(x + row * d + c), xv);
+    unpack8(ld8(dy + row * d + c), g);
+    const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
     if (PER_TOKEN) {
-      if (dw) { atomicAdd(dw + c, a2); atomicAdd(db + c, a1); }
-    } else {
-      const float wc = w ? w[c] : 1.f, bc = w ? b[c] : 0.f;
-      atomicAdd(dshift + group * dmod_ld + c, a1);
-      atomicAdd(dscale + group * dmod_ld + c, wc * a2 + bc * a1);
+      float s[8];
+      unpack8(ld8(scale + row * mod_ld + c), s);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] *= bf16_round(1.f + s[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      S1[j] += g[j];
+      S2[j] += g[j] * (xv[j] - mean) * rstd;
+    }
+  }
+  if (PER_TOKEN) {
+    if (dw) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { atomicAdd(dw + c + j, S2[j]); atomicAdd(db + c + j, S1[j]); }
+    }
+  } else {
+    float s[8];
+    unpack8(ld8(scale + group * mod_ld + c), s);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float wc = w ? __ldg(w + c + j) : 1.f, bc = w ? __ldg(b + c + j) : 0.f;
+      atomicAdd(dshift + group * dmod_ld + c + j, S1[j]);
+      atomicAdd(dscale + group * dmod_ld + c + j, wc * S2[j] + bc * S1[j]);
       if (dw) {
-        const float one_s = bf16_round(1.f + __bfloat162float(scale[group * mod_ld + c]));
-        atomicAdd(dw + c, one_s * a2);
-        atomicAdd(db + c, one_s * a1);
+        const float one_s = bf16_round(1.f + s[j]);
+        atomicAdd(dw + c + j, one_s * S2[j]);
+        atomicAdd(db + c + j, one_s * S1[j]);
       }
     }
   }
@@ -383,28 +390,38 @@ DLB_EXPORT int dlb_ln_modulate_bwd(const void* dy, const void* x, const float* m
   DLB_REQUIRE((w == nullptr) == (b == nullptr) && (w != nullptr || dw == nullptr) && (dw == nullptr) == (db == nullptr),
               DLB_ERR_SHAPE, "ln_modulate_bwd: inconsistent affine arguments");
   DLB_REQUIRE(!per_token || groups == 1, DLB_ERR_SHAPE, "ln_modulate_bwd: per-token mode takes a single group");
-  const int warps = 8;
-  // aim for >= 4 blocks per SM, at most 8 rows per warp
-  int64_t rpw = rows_per_group * groups / ((int64_t)dlb_num_sms() * 4 * warps);
-  rpw = rpw < 1 ? 1 : (rpw > 8 ? 8 : rpw);
-  dim3 grid((unsigned)((rows_per_group + warps * rpw - 1) / (warps * rpw)), (unsigned)groups);
-  const size_t smem = (size_t)2 * warps * d * sizeof(float);
+  const int64_t R = groups * rows_per_group;
+  const int64_t rows_per_mod = per_token ? 1 : rows_per_group;
+  const int warps = 4;
+  const int grid_rows = (int)((R + warps - 1) / warps);
   if (per_token) {
-    VPL_SWITCH(d, {
-      auto k = ln_modulate_bwd_kernel<VPL, true>;
-      if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k<<<grid, warps * 32, smem, stream>>>((const bf16*)dy, (const bf16*)x, mean, rstd, w, b, (const bf16*)scale, mod_ld,
-                                           rows_per_group, (const bf16*)dres, (bf16*)dx, dscale, dshift, dmod_ld,
-                                           (bf16*)dscale_tok, (bf16*)dshift_tok, dtok_ld, dw, db, d, (int)rpw);
-    });
+    VPL_SWITCH(d, (ln_modulate_bwd_rows_kernel<VPL, true><<<grid_rows, warps * 32, 0, stream>>>(
+                      (const bf16*)dy, (const bf16*)x, mean, rstd, w, b, (const bf16*)scale, mod_ld, rows_per_mod,
+                      (const bf16*)dres, (bf16*)dx, (bf16*)dscale_tok, (bf16*)dshift_tok, dtok_ld, R, d)));
   } else {
-    VPL_SWITCH(d, {
-      auto k = ln_modulate_bwd_kernel<VPL, false>;
-      if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k<<<grid, warps * 32, smem, stream>>>((const bf16*)dy, (const bf16*)x, mean, rstd, w, b, (const bf16*)scale, mod_ld,
-                                           rows_per_group, (const bf16*)dres, (bf16*)dx, dscale, dshift, dmod_ld,
-                                           (bf16*)dscale_tok, (bf16*)dshift_tok, dtok_ld, dw, db, d, (int)rpw);
-    });
+    VPL_SWITCH(d, (ln_modulate_bwd_rows_kernel<VPL, false><<<grid_rows, warps * 32, 0, stream>>>(
+                      (const bf16*)dy, (const bf16*)x, mean, rstd, w, b, (const bf16*)scale, mod_ld, rows_per_mod,
+                      (const bf16*)dres, (bf16*)dx, nullptr, nullptr, 0, R, d)));
+  }
+  if (!per_token || dw != nullptr) {
+    const int nv = d / 8;
+    int threads = nv < 256 ? (nv + 31) / 32 * 32 : 256;
+    const int col_chunks = (nv + threads - 1) / threads;
+    // ~4 blocks per SM in total, at least 16 rows per block so the final atomics stay a small fraction
+    int64_t want_blocks = (int64_t)dlb_num_sms() * 4 / (col_chunks * groups);
+    if (want_blocks < 1) want_blocks = 1;
+    int64_t rpb = (rows_per_group + want_blocks - 1) / want_blocks;
+    if (rpb < 16) rpb = 16;
+    dim3 grid(col_chunks, (unsigned)((rows_per_group + rpb - 1) / rpb), (unsigned)groups);
+    if (per_token)
+      ln_modulate_bwd_cols_kernel<true><<<grid, threads, 0, stream>>>((const bf16*)dy, (const bf16*)x, mean, rstd, w, b,
+                                                                     (const bf16*)scale, mod_ld, rows_per_group, dscale,
+                                                                     dshift, dmod_ld, dw, db, d, (int)rpb);
+    else
+      ln_modulate_bwd_cols_kernel<false><<<grid, threads, 0, stream>>>((const bf16*)dy, (const bf16*)x, mean, rstd, w, b,
+                                                                      (const bf16*)scale, mod_ld, rows_per_group, dscale,
+                                                                      dshift, dmod_ld, dw, db, d, (int)rpb);
+    dlb_count_launch();
   }
   dlb_count_launch();
   return dlb_check_launch("ln_modulate_bwd");

@@ -78,103 +78,111 @@ qknorm_rope_fwd_kernel(const bf16* __restrict__ qkv, int64_t ld_in, const float*
   }
 }
 
-// backward: dqk (grad wrt normalised+rotated q,k) -> dq, dk (written into the packed dqkv buffer) and
-// column-accumulated scale gradients.
+// backward, two kernels (same split as the LayerNorm backward):
+//  rows: dqk (grad wrt normalised+rotated q,k) -> dq, dk written into the packed dqkv buffer (one warp per token);
+//  cols: column-accumulated gradients of the learnable RMS scales (one thread per 8-channel vector).
 template <int VPL>
-__global__ void __launch_bounds__(256)
-qknorm_rope_bwd_kernel(const bf16* __restrict__ dqk, int64_t ld_dqk, const bf16* __restrict__ qkv, int64_t ld_in,
-                       const float* __restrict__ sq, const float* __restrict__ sk, RopeArgs ra,
-                       bf16* __restrict__ dqkv, int64_t ld_out, float* __restrict__ dsq, float* __restrict__ dsk,
-                       int64_t R, int d, float eps, int rows_per_warp) {
-  extern __shared__ float red[];  // [warps][d]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+__global__ void __launch_bounds__(128)
+qknorm_rope_bwd_rows_kernel(const bf16* __restrict__ dqk, int64_t ld_dqk, const bf16* __restrict__ qkv, int64_t ld_in,
+                            const float* __restrict__ sq, const float* __restrict__ sk, RopeArgs ra,
+                            const float* __restrict__ rrms_in, bf16* __restrict__ dqkv, int64_t ld_out, int64_t R, int d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
   const int nv = d >> 3;
-  const int64_t r_begin = ((int64_t)blockIdx.x * nwarps + warp) * rows_per_warp;
-  const int64_t r_end = min(r_begin + rows_per_warp, R);
+  const int pos = rope_pos(ra, row);
+  const float* cr = ra.cos_t + (int64_t)pos * ra.rot_half;
+  const float* sr = ra.sin_t + (int64_t)pos * ra.rot_half;
 #pragma unroll 1
   for (int which = 0; which < 2; ++which) {
     const float* sc = which ? sk : sq;
-    float S[VPL][8];
-#pragma unroll
-    for (int i = 0; i < VPL; ++i)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) S[i][j] = 0.f;
-    for (int64_t row = r_begin; row < r_end; ++row) {
-      const int pos = rope_pos(ra, row);
-      const float* cr = ra.cos_t + (int64_t)pos * ra.rot_half;
-      const float* sr = ra.sin_t + (int64_t)pos * ra.rot_half;
-      const bf16* src = qkv + row * ld_in + which * d;
-      const bf16* gsrc = dqk + row * ld_dqk + which * d;
-      float xn[VPL][8], gn[VPL][8];
-      float ss = 0.f;
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        const int v = lane + 32 * i;
-        if (v < nv) {
-          unpack8(ld8(src + v * 8), xn[i]);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) ss += xn[i][j] * xn[i][j];
-        }
-      }
-      const float rrms = rsqrtf(warp_sum(ss) / d + eps);
-      float dot = 0.f;
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        const int v = lane + 32 * i;
-        if (v < nv) {
-          const int c = v * 8;
-          const int cl = c % ra.hd;
-          float g[8];
-          unpack8(ld8(gsrc + c), g);
-#pragma unroll
-          for (int j = 0; j < 8; j += 2) {  // transpose of the rotation
-            const int pj = (cl + j) >> 1;
-            if (pj < ra.rot_half) {
-              const float cs = bf16_round(__ldg(cr + pj)), sn = bf16_round(__ldg(sr + pj));
-              const float ge = g[j], go = g[j + 1];
-              g[j] = ge * cs + go * sn;
-              g[j + 1] = -ge * sn + go * cs;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            xn[i][j] *= rrms;                      // normalised value (fp32)
-            S[i][j] += g[j] * bf16_round(xn[i][j]);  // d scale: the reference multiplies the bf16-rounded value
-            gn[i][j] = g[j] * __ldg(sc + c + j);   // grad wrt the normalised value
-            dot += gn[i][j] * xn[i][j];
-          }
-        }
-      }
-      dot = warp_sum(dot) / d;
-      bf16* dst = dqkv + row * ld_out + which * d;
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        const int v = lane + 32 * i;
-        if (v < nv) {
-          float o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = rrms * (gn[i][j] - xn[i][j] * dot);
-          st8(dst + v * 8, pack8(o));
-        }
-      }
-    }
-    __syncthreads();
+    const bf16* src = qkv + row * ld_in + which * d;
+    const bf16* gsrc = dqk + row * ld_dqk + which * d;
+    const float rrms = rrms_in[row * 2 + which];
+    float xn[VPL][8], gn[VPL][8];
+    float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + 32 * i;
       if (v < nv) {
+        const int c = v * 8;
+        const int cl = c % ra.hd;
+        float g[8];
+        unpack8(ld8(src + c), xn[i]);
+        unpack8(ld8(gsrc + c), g);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) red[(size_t)warp * d + v * 8 + j] = S[i][j];
+        for (int j = 0; j < 8; j += 2) {  // transpose of the rotation
+          const int pj = (cl + j) >> 1;
+          if (pj < ra.rot_half) {
+            const float cs = bf16_round(__ldg(cr + pj)), sn = bf16_round(__ldg(sr + pj));
+            const float ge = g[j], go = g[j + 1];
+            g[j] = ge * cs + go * sn;
+            g[j + 1] = -ge * sn + go * cs;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xn[i][j] *= rrms;                     // normalised value (fp32)
+          gn[i][j] = g[j] * __ldg(sc + c + j);  // grad wrt the normalised value
+          dot += gn[i][j] * xn[i][j];
+        }
       }
     }
-    __syncthreads();
-    float* dsc = which ? dsk : dsq;
-    for (int c = threadIdx.x; c < d; c += blockDim.x) {
-      float a = 0.f;
-      for (int wi = 0; wi < nwarps; ++wi) a += red[(size_t)wi * d + c];
-      atomicAdd(dsc + c, a);
+    dot = warp_sum(dot) / d;
+    bf16* dst = dqkv + row * ld_out + which * d;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nv) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rrms * (gn[i][j] - xn[i][j] * dot);
+        st8(dst + v * 8, pack8(o));
+      }
     }
   }
+}
+
+// grid (col chunks, row chunks, 2 = q/k)
+__global__ void __launch_bounds__(256)
+qknorm_rope_bwd_cols_kernel(const bf16* __restrict__ dqk, int64_t ld_dqk, const bf16* __restrict__ qkv, int64_t ld_in,
+                            RopeArgs ra, const float* __restrict__ rrms_in, float* __restrict__ dsq,
+                            float* __restrict__ dsk, int64_t R, int d, int rows_per_block) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= (d >> 3)) return;
+  const int c = v * 8;
+  const int cl = c % ra.hd;
+  const int which = blockIdx.z;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(r0 + rows_per_block, R);
+  float S[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) S[j] = 0.f;
+#pragma unroll 4
+  for (int64_t row = r0; row < r1; ++row) {
+    float xq[8], g[8];
+    unpack8(ld8(qkv + row * ld_in + which * d + c), xq);
+    unpack8(ld8(dqk + row * ld_dqk + which * d + c), g);
+    const float rrms = __ldg(rrms_in + row * 2 + which);
+    const int pos = rope_pos(ra, row);
+    const float* cr = ra.cos_t + (int64_t)pos * ra.rot_half;
+    const float* sr = ra.sin_t + (int64_t)pos * ra.rot_half;
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const int pj = (cl + j) >> 1;
+      if (pj < ra.rot_half) {
+        const float cs = bf16_round(__ldg(cr + pj)), sn = bf16_round(__ldg(sr + pj));
+        const float ge = g[j], go = g[j + 1];
+        g[j] = ge * cs + go * sn;
+        g[j + 1] = -ge * sn + go * cs;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) S[j] += g[j] * bf16_round(xq[j] * rrms);  // the reference multiplies the bf16-rounded value
+  }
+  float* dsc = which ? dsk : dsq;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(dsc + c + j, S[j]);
 }
 
 int vpl_for(int d) { return (d / 8 + 31) / 32; }
@@ -218,25 +226,32 @@ DLB_EXPORT int dlb_qknorm_rope_fwd(const void* qkv, int64_t ld_in, const float* 
 
 DLB_EXPORT int dlb_qknorm_rope_bwd(const void* dqk, int64_t ld_dqk, const void* qkv, int64_t ld_in, const float* sq,
                                    const float* sk, const float* cos_t, const float* sin_t, int rot_half,
-                                   const int32_t* pos_idx, int pos_offset, int tokens_per_sample, int hd, void* dqkv,
-                                   int64_t ld_out, float* dsq, float* dsk, int64_t R, int d, float eps,
-                                   cudaStream_t stream) {
+                                   const int32_t* pos_idx, int pos_offset, int tokens_per_sample, int hd,
+                                   const float* rrms, void* dqkv, int64_t ld_out, float* dsq, float* dsk, int64_t R,
+                                   int d, cudaStream_t stream) {
   int rc = check_rope("qknorm_rope_bwd", d, hd, rot_half, tokens_per_sample, pos_idx);
   if (rc) return rc;
   DLB_REQUIRE(R > 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && ld_dqk % 8 == 0, DLB_ERR_SHAPE, "qknorm_rope_bwd: bad strides");
+  DLB_REQUIRE(rrms != nullptr, DLB_ERR_SHAPE, "qknorm_rope_bwd: the rrms buffer saved by the forward pass is required");
   RopeArgs ra{cos_t, sin_t, pos_idx, rot_half, pos_offset, tokens_per_sample > 0 ? tokens_per_sample : 1, hd};
-  const int warps = 8;
-  int64_t rpw = R / ((int64_t)dlb_num_sms() * 4 * warps);
-  rpw = rpw < 1 ? 1 : (rpw > 8 ? 8 : rpw);
-  const int grid = (int)((R + warps * rpw - 1) / (warps * rpw));
-  const size_t smem = (size_t)warps * d * sizeof(float);
-  VPL_SWITCH(d, {
-    auto k = qknorm_rope_bwd_kernel<VPL>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, warps * 32, smem, stream>>>((const bf16*)dqk, ld_dqk, (const bf16*)qkv, ld_in, sq, sk, ra, (bf16*)dqkv,
-                                         ld_out, dsq, dsk, R, d, eps, (int)rpw);
-  });
+  const int warps = 4;
+  const int grid = (int)((R + warps - 1) / warps);
+  VPL_SWITCH(d, (qknorm_rope_bwd_rows_kernel<VPL><<<grid, warps * 32, 0, stream>>>(
+                    (const bf16*)dqk, ld_dqk, (const bf16*)qkv, ld_in, sq, sk, ra, rrms, (bf16*)dqkv, ld_out, R, d)));
   dlb_count_launch();
+  if (dsq != nullptr && dsk != nullptr) {
+    const int nv = d / 8;
+    const int threads = nv < 256 ? (nv + 31) / 32 * 32 : 256;
+    const int col_chunks = (nv + threads - 1) / threads;
+    int64_t want_blocks = (int64_t)dlb_num_sms() * 4 / (col_chunks * 2);
+    if (want_blocks < 1) want_blocks = 1;
+    int64_t rpb = (R + want_blocks - 1) / want_blocks;
+    if (rpb < 16) rpb = 16;
+    dim3 g2(col_chunks, (unsigned)((R + rpb - 1) / rpb), 2);
+    qknorm_rope_bwd_cols_kernel<<<g2, threads, 0, stream>>>((const bf16*)dqk, ld_dqk, (const bf16*)qkv, ld_in, ra, rrms, dsq,
+                                                          dsk, R, d, (int)rpb);
+    dlb_count_launch();
+  }
   return dlb_check_launch("qknorm_rope_bwd");
 }
 

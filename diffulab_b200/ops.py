@@ -294,26 +294,28 @@ def rope_table(pos_ids: Tensor, axes_dim: list[int], base: float) -> tuple[Tenso
 
 
 def qknorm_rope_fwd(qkv: Tensor, sq: Tensor, sk: Tensor, cos: Tensor, sin: Tensor, hd: int, *, tokens_per_sample: int,
-                    pos_offset: int = 0, pos_idx: Tensor | None = None, eps: float = 1e-6) -> Tensor:
-    """qkv: [R, 3d] packed projection -> [R, 2d] normalised + rotated (q | k)."""
+                    pos_offset: int = 0, pos_idx: Tensor | None = None, eps: float = 1e-6) -> tuple[Tensor, Tensor]:
+    """qkv: [R, 3d] packed projection -> ([R, 2d] normalised + rotated (q | k), rrms fp32 [R, 2] for the backward)."""
     _req(qkv, BF16, "qkv")
     R = _rows(qkv)
     d = qkv.shape[-1] // 3
     out = torch.empty(R, 2 * d, device=qkv.device, dtype=BF16)
+    rrms = torch.empty(R, 2, device=qkv.device, dtype=F32)
     _lib_call("dlb_qknorm_rope_fwd", qkv.data_ptr(), 3 * d, sq.data_ptr(), sk.data_ptr(), cos.data_ptr(), sin.data_ptr(),
-              cos.shape[-1], _ptr(pos_idx), pos_offset, tokens_per_sample, hd, out.data_ptr(), 2 * d, None, R, d, eps, _stream())
-    return out
+              cos.shape[-1], _ptr(pos_idx), pos_offset, tokens_per_sample, hd, out.data_ptr(), 2 * d, rrms.data_ptr(), R, d, eps,
+              _stream())
+    return out, rrms
 
 
-def qknorm_rope_bwd(dqk: Tensor, qkv: Tensor, sq: Tensor, sk: Tensor, cos: Tensor, sin: Tensor, hd: int, dqkv: Tensor,
-                    dsq: Tensor, dsk: Tensor, *, tokens_per_sample: int, pos_offset: int = 0,
-                    pos_idx: Tensor | None = None, eps: float = 1e-6) -> None:
+def qknorm_rope_bwd(dqk: Tensor, qkv: Tensor, rrms: Tensor, sq: Tensor, sk: Tensor, cos: Tensor, sin: Tensor, hd: int,
+                    dqkv: Tensor, dsq: Tensor | None, dsk: Tensor | None, *, tokens_per_sample: int, pos_offset: int = 0,
+                    pos_idx: Tensor | None = None) -> None:
     """Writes dq, dk into dqkv[:, :2d] (dv at [:, 2d:] is produced by attention bwd); accumulates dsq/dsk (fp32)."""
     R = _rows(qkv)
     d = qkv.shape[-1] // 3
     _lib_call("dlb_qknorm_rope_bwd", dqk.data_ptr(), 2 * d, qkv.data_ptr(), 3 * d, sq.data_ptr(), sk.data_ptr(),
               cos.data_ptr(), sin.data_ptr(), cos.shape[-1], _ptr(pos_idx), pos_offset, tokens_per_sample, hd,
-              dqkv.data_ptr(), 3 * d, dsq.data_ptr(), dsk.data_ptr(), R, d, eps, _stream())
+              rrms.data_ptr(), dqkv.data_ptr(), 3 * d, _ptr(dsq), _ptr(dsk), R, d, _stream())
 
 
 # ---------------------------------------------------------------------------------------------------------

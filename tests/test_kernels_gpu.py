@@ -175,7 +175,7 @@ def test_qknorm_rope(gen, B, S, H, hd, axes):
     qkv = mk(gen, B * S, 3 * d)
     sq = 1 + 0.2 * torch.randn(d, device="cuda", generator=gen)
     sk = 1 + 0.2 * torch.randn(d, device="cuda", generator=gen)
-    out = ops.qknorm_rope_fwd(qkv, sq, sk, cos, sin, hd, tokens_per_sample=S)
+    out, rrms = ops.qknorm_rope_fwd(qkv, sq, sk, cos, sin, hd, tokens_per_sample=S)
     x = qkv.float().view(B, S, 3 * d).requires_grad_(True)
     sqr, skr = sq.clone().requires_grad_(True), sk.clone().requires_grad_(True)
     cb, sb = cr.to(BF).float(), sr_.to(BF).float()  # the reference casts cos/sin to the activation dtype
@@ -187,7 +187,7 @@ def test_qknorm_rope(gen, B, S, H, hd, axes):
     ref.backward(dqk.float())
     dqkv = torch.zeros(B * S, 3 * d, device="cuda", dtype=BF)
     dsq, dsk = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
-    ops.qknorm_rope_bwd(dqk, qkv, sq, sk, cos, sin, hd, dqkv, dsq, dsk, tokens_per_sample=S)
+    ops.qknorm_rope_bwd(dqk, qkv, rrms, sq, sk, cos, sin, hd, dqkv, dsq, dsk, tokens_per_sample=S)
     g = x.grad.view(B * S, 3 * d)
     assert rel_l2(dqkv[:, : 2 * d], g[:, : 2 * d]) < 1e-2
     assert dqkv[:, 2 * d :].abs().max().item() == 0.0
@@ -205,10 +205,10 @@ def test_qknorm_rope_pos_idx(gen):
     kept = torch.stack([torch.randperm(S, device="cuda", generator=gen)[:k].sort().values for _ in range(B)]).int()
     qkv = mk(gen, B * k, 3 * d)
     ones = torch.ones(d, device="cuda")
-    a = ops.qknorm_rope_fwd(qkv, ones, ones, cos, sin, hd, tokens_per_sample=k, pos_idx=kept.reshape(-1).contiguous())
+    a, _ = ops.qknorm_rope_fwd(qkv, ones, ones, cos, sin, hd, tokens_per_sample=k, pos_idx=kept.reshape(-1).contiguous())
     for b in range(B):
         cb, sb = cos[kept[b].long()], sin[kept[b].long()]
-        single = ops.qknorm_rope_fwd(qkv[b * k : (b + 1) * k].contiguous(), ones, ones, cb.contiguous(), sb.contiguous(), hd, tokens_per_sample=k)
+        single, _ = ops.qknorm_rope_fwd(qkv[b * k : (b + 1) * k].contiguous(), ones, ones, cb.contiguous(), sb.contiguous(), hd, tokens_per_sample=k)
         assert torch.equal(a[b * k : (b + 1) * k], single)
 
 
