@@ -1,0 +1,79 @@
+"""CPU, world_size 2 over gloo: host logic of the bucketed gradient reducer (bucket membership, ready counting,
+flush of never-produced gradients, mean over ranks). The device path (NCCL) is exercised by tests/test_dp_gpu.py."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _worker(rank: int, world: int, port: int, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from diffulab_b200.training import GradReducer
+
+        torch.manual_seed(0)
+        params = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 7, 3, 11)]
+        red = GradReducer(params=params)
+        assert len(red.buckets) == 4 and red.world == world
+        for step in range(2):
+            for p in params:
+                p.grad.zero_()
+            red.begin()
+            # gradients arrive last-to-first; parameter 2 never receives one (reference quirk)
+            for i in (3, 1, 0):
+                params[i].grad += float(rank + 1) * (i + 1) + step
+                red._ready(params[i])
+            assert red.launched[red.bucket_of[id(params[3])]]
+            assert not red.launched[red.bucket_of[id(params[2])]]
+            red.finish()
+            assert all(red.launched)
+            for i in (3, 1, 0):
+                expect = sum((r + 1) * (i + 1) + step for r in range(world)) / world
+                assert torch.allclose(params[i].grad, torch.full_like(params[i].grad, expect)), (i, params[i].grad)
+            assert params[2].grad.abs().max().item() == 0.0
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_reducer_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_bucket_layout_reverse_order():
+    """Flat-store bucketing logic on fake stores (no CUDA): contiguous slices, reverse parameter order, size cap."""
+    from diffulab_b200.training import _ALIGN, GradReducer
+
+    class FakeStore:
+        def __init__(self, sizes):
+            self.params = [torch.nn.Parameter(torch.zeros(n)) for n in sizes]
+            self.offsets, off = [], 0
+            for p in self.params:
+                self.offsets.append(off)
+                off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            self.flat_g = torch.zeros(off)
+
+    st = FakeStore([100, 64, 300, 10, 129])
+    red = GradReducer(stores=[st], bucket_mb=4 * 320 / (1024 * 1024))  # cap = 320 elements
+    sizes = [b.numel() for b in red.buckets]
+    assert sum(sizes) == st.flat_g.numel()
+    # last parameters form the first bucket
+    assert red.bucket_of[id(st.params[4])] == 0 and red.bucket_of[id(st.params[0])] == len(red.buckets) - 1
+    for p, o in zip(st.params, st.offsets):
+        b = red.buckets[red.bucket_of[id(p)]]
+        lo = (b.data_ptr() - st.flat_g.data_ptr()) // 4
+        assert lo <= o and o + p.numel() <= lo + b.numel()
