@@ -115,6 +115,10 @@ int dlb_attn_fwd(const dlb_attn_seg* segs, int nseg, float* lse, const uint8_t* 
 int dlb_attn_bwd(const dlb_attn_seg* segs, int nseg, const float* lse, float* dsum, const uint8_t* kmask,
                  int mask_len, int B, int H, int hd, float scale, dlb_stream_t stream);
 
+/* development probe: D[128,N] = A*B^T from thread-staged non-swizzled UMMA operands (pins LBO/SBO semantics) */
+int dlb_umma_probe(const void* A, const void* B, float* D, int N, int K, int a_mn, int b_mn, int swap_lbo_sbo,
+                   dlb_stream_t stream);
+
 /* ---- glue ------------------------------------------------------------------------------------------------ */
 int dlb_cast_f32_bf16(const float* in, void* out, int64_t rows, int64_t cols, int64_t ld_out, dlb_stream_t stream);
 int dlb_cast_bf16_f32(const void* in, float* out, int64_t n, dlb_stream_t stream);
