@@ -46,6 +46,7 @@ _SIGNATURES: dict[str, list] = {
     "dlb_rope_table": [p, i32, p, p, p, C.c_double, p, p, i64, i32, p],
     # segs, nseg, lse, kmask, mask_len, B, H, hd, scale, stream
     "dlb_attn_fwd": [p, i32, p, p, i32, i32, i32, i32, f32, p],
+    "dlb_attn_fwd_tc": [p, i32, p, p, i32, i32, i32, i32, f32, p],
     # segs, nseg, lse, dsum, kmask, mask_len, B, H, hd, scale, stream
     "dlb_attn_bwd": [p, i32, p, p, p, i32, i32, i32, i32, f32, p],
     "dlb_cast_f32_bf16": [p, p, i64, i64, i64, p],

@@ -1,0 +1,272 @@
+// tcgen05 joint attention (forward), sm_100a. One CTA = 128 query rows of one (sample, head); TMEM lane = query row.
+//   S = Q K^T   : tcgen05.mma M=128 N=128 K=16 x (HDP/16), A = Q tile, B = K tile (both K-major, non-swizzled smem)
+//   softmax     : thread = row (no shuffles): two passes over the 128 S columns with tcgen05.ld, online max/sum
+//   O_j = P V   : P (bf16) staged in smem as the K-major A operand; B = V tile read MN-major straight from its
+//                 [key][hd] row layout; per-tile result read back from TMEM and accumulated (rescaled) in registers
+// Operands are staged by the threads (cp.async, 16-byte chunks) into the canonical 8x8 core-matrix layout, because the
+// sequence is a concatenation of up to two segments with a key-padding mask (reference mmdit.py:184-204).
+// Head dims that are not a multiple of 16 (DiT-XL/2: 72) are zero-padded in shared memory only.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace attn_tc {
+typedef __nv_bfloat16 bf16;
+
+struct Seg {
+  const bf16* q; const bf16* k; const bf16* v; bf16* out;
+  int64_t ldq, ldk, ldv, ldo;
+  int len;
+};
+struct Params {
+  Seg seg[2];
+  float* lse;
+  const uint8_t* kmask;
+  int mask_len, B, H, S, hd;
+  float scale, scale_log2;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory"); }
+
+enum { T_Q = 0, T_K = 1, T_V = 2 };
+
+// 128-row tile of tokens s0.. -> smem. K-major core layout (Q, K): chunk (row r, hd-chunk c) at (r/8)*SBO + c*128 + (r%8)*16,
+// SBO = (HDP/8)*128. MN-major layout (V as the B operand of P*V): chunk (key r, hd-chunk c) at c*2048 + (r/8)*128 + (r%8)*16.
+template <int HDP, int WHICH>
+__device__ __forceinline__ void load_tile(uint8_t* sm, const Params& p, int b, int h, int s0, int tid, int nthreads) {
+  constexpr int CPR = HDP / 8;
+  for (int idx = tid; idx < 128 * CPR; idx += nthreads) {
+    const int c = idx / 128, r = idx - c * 128;  // consecutive threads -> consecutive rows (conflict-free smem writes)
+    const int s = s0 + r;
+    uint8_t* dst = (WHICH == T_V) ? sm + c * 2048 + (r >> 3) * 128 + (r & 7) * 16
+                                  : sm + (r >> 3) * (CPR * 128) + c * 128 + (r & 7) * 16;
+    if (s < p.S && c * 8 < p.hd) {
+      const int sg = s < p.seg[0].len ? 0 : 1;
+      const Seg& g = p.seg[sg];
+      const int64_t row = (int64_t)b * g.len + (sg ? s - p.seg[0].len : s);
+      const bf16* base = WHICH == T_Q ? g.q : (WHICH == T_K ? g.k : g.v);
+      const int64_t ld = WHICH == T_Q ? g.ldq : (WHICH == T_K ? g.ldk : g.ldv);
+      cp_async16(dst, base + row * ld + (int64_t)h * p.hd + c * 8);
+    } else {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
+template <int HDP>
+__global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const Params p) {
+  constexpr int CPR = HDP / 8;
+  constexpr int QK_BYTES = 128 * HDP * 2;  // 20480 for HDP = 80
+  constexpr uint32_t SBO_QK = CPR * 128;   // stride between 8-row groups of a K-major [128][HDP] tile
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + QK_BYTES;
+  uint8_t* sV = sK + QK_BYTES;
+  uint8_t* sP = sV + QK_BYTES;                            // [128 q][128 keys] bf16, K-major core layout, 32 KB
+  float* sBias = reinterpret_cast<float*>(sP + 32768);    // 128 additive key biases (0 / -inf)
+  __shared__ uint64_t bar_s, bar_o;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+
+  if (tid == 0) {
+    ptx::mbar_init(&bar_s, 1);
+    ptx::mbar_init(&bar_o, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) ptx::tmem_alloc<256>(&tmem_slot);
+  load_tile<HDP, T_Q>(sQ, p, b, h, q0, tid, 128);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tS = tmem, tO = tmem + 128;  // S: 128 fp32 columns, O tile: HDP columns
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, 128, false, false);
+  constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, HDP, false, true);
+
+  float o[HDP];
+#pragma unroll
+  for (int i = 0; i < HDP; ++i) o[i] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  uint32_t phase = 0;
+
+  for (int kv0 = 0; kv0 < p.S; kv0 += 128) {
+    load_tile<HDP, T_K>(sK, p, b, h, kv0, tid, 128);
+    load_tile<HDP, T_V>(sV, p, b, h, kv0, tid, 128);
+    {
+      const int key = kv0 + tid;
+      float bias = 0.f;
+      if (key >= p.S) bias = -INFINITY;
+      else if (p.kmask && key < p.mask_len && p.kmask[(int64_t)b * p.mask_len + key] == 0) bias = -INFINITY;
+      sBias[tid] = bias;
+    }
+    cp_async_wait_all();
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      const uint32_t qa = ptx::smem_u32(sQ), ka = ptx::smem_u32(sK);
+#pragma unroll
+      for (int ks = 0; ks < HDP / 16; ++ks)
+        ptx::umma_bf16(tS, ptx::make_smem_desc_noswz(qa + ks * 256, 128, SBO_QK), ptx::make_smem_desc_noswz(ka + ks * 256, 128, SBO_QK),
+                       idesc_s, ks > 0);
+      ptx::umma_commit(&bar_s);
+    }
+    ptx::mbar_wait(&bar_s, phase);
+    ptx::tc_fence_after();
+
+    // pass 1: row maximum
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < 128; c += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld32(tS + lane_off + c, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]) + sBias[c + j]);
+    }
+    const float m_new = fmaxf(m, mx);
+    const float ms = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
+    const float alpha = ex2(m * p.scale_log2 - ms);
+    // pass 2: probabilities -> bf16 A operand in smem
+    float lsum = 0.f;
+    uint8_t* prow = sP + (tid >> 3) * 2048 + (tid & 7) * 16;
+#pragma unroll 1
+    for (int c = 0; c < 128; c += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld32(tS + lane_off + c, r);
+      ptx::tmem_ld_wait();
+      float pv[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        pv[j] = ex2((__uint_as_float(r[j]) + sBias[c + j]) * p.scale_log2 - ms);
+        lsum += pv[j];
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint4 v;
+        v.x = pack_bf16x2(pv[8 * q4 + 0], pv[8 * q4 + 1]);
+        v.y = pack_bf16x2(pv[8 * q4 + 2], pv[8 * q4 + 3]);
+        v.z = pack_bf16x2(pv[8 * q4 + 4], pv[8 * q4 + 5]);
+        v.w = pack_bf16x2(pv[8 * q4 + 6], pv[8 * q4 + 7]);
+        *reinterpret_cast<uint4*>(prow + ((c >> 3) + q4) * 128) = v;
+      }
+    }
+    l = l * alpha + lsum;
+    m = m_new;
+    ptx::fence_proxy_async_smem();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      const uint32_t pa = ptx::smem_u32(sP), va = ptx::smem_u32(sV);
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+        ptx::umma_bf16(tO, ptx::make_smem_desc_noswz(pa + ks * 256, 128, 2048), ptx::make_smem_desc_noswz(va + ks * 256, 128, 2048),
+                       idesc_o, ks > 0);
+      ptx::umma_commit(&bar_o);
+    }
+    ptx::mbar_wait(&bar_o, phase);
+    ptx::tc_fence_after();
+    // o = o * alpha + O_tile
+#pragma unroll
+    for (int c = 0; c < HDP; c += 16) {
+      uint32_t r[16];
+      ptx::tmem_ld16(tO + lane_off + c, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[c + j] = o[c + j] * alpha + __uint_as_float(r[j]);
+    }
+    phase ^= 1;
+    ptx::tc_fence_before();
+    __syncthreads();  // every thread is done with S / O tiles and sK / sV / sP before they are overwritten
+  }
+
+  // finalise: normalise, stage rows in smem (row-major [128][HDP]), coalesced 16-byte stores
+  const float inv = l > 0.f ? 1.f / l : 0.f;
+  const int row = q0 + tid;
+  if (p.lse && row < p.S) p.lse[((int64_t)b * p.H + h) * p.S + row] = m * p.scale + logf(l);
+  bf16* stage = reinterpret_cast<bf16*>(sP);
+#pragma unroll
+  for (int c = 0; c < HDP; c += 8) {
+    float t8[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t8[j] = o[c + j] * inv;
+    st8(stage + tid * HDP + c, pack8(t8));
+  }
+  __syncthreads();
+  const int cpr = p.hd >> 3;
+  for (int idx = tid; idx < 128 * cpr; idx += 128) {
+    const int r = idx / cpr, c = idx - r * cpr;
+    const int s = q0 + r;
+    if (s < p.S) {
+      const int sg = s < p.seg[0].len ? 0 : 1;
+      const Seg& g = p.seg[sg];
+      const int64_t grow = (int64_t)b * g.len + (sg ? s - p.seg[0].len : s);
+      *reinterpret_cast<uint4*>(g.out + grow * g.ldo + (int64_t)h * p.hd + c * 8) = *reinterpret_cast<const uint4*>(stage + r * HDP + c * 8);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc<256>(tmem);
+}
+
+}  // namespace attn_tc
+
+// plain-C segment description shared with attention.cu (include/diffulab_b200.h: dlb_attn_seg)
+struct dlb_attn_seg {
+  const void* q; const void* k; const void* v;
+  void* o;
+  const void* dout;
+  void* dq; void* dk; void* dv;
+  int64_t ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
+  int32_t len;
+};
+
+// Same contract as dlb_attn_fwd (attention.cu); tcgen05 implementation.
+DLB_EXPORT int dlb_attn_fwd_tc(const dlb_attn_seg* segs, int nseg, float* lse, const uint8_t* kmask, int mask_len, int B,
+                               int H, int hd, float scale, cudaStream_t stream) {
+  using namespace attn_tc;
+  DLB_REQUIRE(nseg == 1 || nseg == 2, DLB_ERR_SHAPE, "attn_fwd_tc: 1 or 2 segments supported (got %d)", nseg);
+  DLB_REQUIRE(B > 0 && H > 0 && hd > 0 && hd % 8 == 0 && hd <= 128, DLB_ERR_SHAPE, "attn_fwd_tc: B=%d H=%d hd=%d", B, H, hd);
+  Params p{};
+  int S = 0;
+  for (int i = 0; i < nseg; ++i) {
+    const dlb_attn_seg& s = segs[i];
+    DLB_REQUIRE(s.len >= 0 && s.ldq % 8 == 0 && s.ldk % 8 == 0 && s.ldv % 8 == 0 && s.ldo % 8 == 0, DLB_ERR_ALIGN,
+                "attn_fwd_tc: strides must be multiples of 8");
+    p.seg[i] = Seg{(const bf16*)s.q, (const bf16*)s.k, (const bf16*)s.v, (bf16*)s.o, s.ldq, s.ldk, s.ldv, s.ldo, s.len};
+    S += s.len;
+  }
+  DLB_REQUIRE(S > 0 && mask_len >= 0 && mask_len <= S && (kmask != nullptr || mask_len == 0), DLB_ERR_SHAPE, "attn_fwd_tc: bad sequence / mask");
+  p.lse = lse; p.kmask = kmask; p.mask_len = mask_len; p.B = B; p.H = H; p.S = S; p.hd = hd;
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((S + 127) / 128, H, B);
+  const int hdp = (hd + 15) / 16 * 16;
+#define LAUNCH_FWD(HDPV)                                                                                          \
+  {                                                                                                               \
+    const size_t smem = (size_t)3 * 128 * HDPV * 2 + 32768 + 512;                                                 \
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<HDPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    DLB_REQUIRE(e == cudaSuccess, (int)e, "attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));        \
+    attn_fwd_tc_kernel<HDPV><<<grid, 128, smem, stream>>>(p);                                                     \
+  }
+  switch (hdp) {
+    case 16: case 32: case 48: case 64: LAUNCH_FWD(64); break;
+    case 80: LAUNCH_FWD(80); break;
+    case 96: LAUNCH_FWD(96); break;
+    default: LAUNCH_FWD(128); break;
+  }
+#undef LAUNCH_FWD
+  dlb_count_launch();
+  return dlb_check_launch("attn_fwd_tc");
+}

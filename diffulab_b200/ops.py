@@ -353,7 +353,10 @@ def _seg_array(specs, outs, douts=None, dqks=None, dqkvs=None):
     return arr
 
 
-def attn_fwd(specs: list[AttnSegSpec], B: int, H: int, hd: int, scale: float, kmask: Tensor | None = None):
+ATTN_FWD_IMPL = "dlb_attn_fwd_tc"  # tcgen05 forward; "dlb_attn_fwd" is the mma.sync kernel (kept for comparison tests)
+
+
+def attn_fwd(specs: list[AttnSegSpec], B: int, H: int, hd: int, scale: float, kmask: Tensor | None = None, impl: str | None = None):
     S = sum(s.len for s in specs)
     dev = specs[0].qk.device
     outs = [torch.empty(B * s.len, s.d, device=dev, dtype=BF16) for s in specs]
@@ -364,7 +367,7 @@ def attn_fwd(specs: list[AttnSegSpec], B: int, H: int, hd: int, scale: float, km
         _req(kmask, torch.uint8, "kmask")
         mask_len = kmask.shape[1]
     import ctypes as C
-    _lib_call("dlb_attn_fwd", C.cast(arr, C.c_void_p), len(specs), lse.data_ptr(), _ptr(kmask), mask_len, B, H, hd, scale, _stream())
+    _lib_call(impl or ATTN_FWD_IMPL, C.cast(arr, C.c_void_p), len(specs), lse.data_ptr(), _ptr(kmask), mask_len, B, H, hd, scale, _stream())
     return outs, lse
 
 

@@ -112,6 +112,9 @@ typedef struct dlb_attn_seg {
 } dlb_attn_seg;
 int dlb_attn_fwd(const dlb_attn_seg* segs, int nseg, float* lse, const uint8_t* kmask, int mask_len, int B, int H,
                  int hd, float scale, dlb_stream_t stream);
+/* tcgen05 / TMEM implementation of dlb_attn_fwd (same contract) */
+int dlb_attn_fwd_tc(const dlb_attn_seg* segs, int nseg, float* lse, const uint8_t* kmask, int mask_len, int B, int H,
+                    int hd, float scale, dlb_stream_t stream);
 int dlb_attn_bwd(const dlb_attn_seg* segs, int nseg, const float* lse, float* dsum, const uint8_t* kmask,
                  int mask_len, int B, int H, int hd, float scale, dlb_stream_t stream);
 

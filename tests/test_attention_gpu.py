@@ -31,11 +31,13 @@ CASES = [
     (2, 3, 72, 7, 50, True),      # ragged lengths: partial tiles on both axes
     (1, 2, 128, 0, 100, False),
     (2, 2, 32, 5, 20, True),
+    (2, 4, 72, 100, 300, True),   # S = 400: four 128-key tiles, ragged tail
 ]
 
 
+@pytest.mark.parametrize("impl", ["dlb_attn_fwd_tc", "dlb_attn_fwd"])
 @pytest.mark.parametrize("B,H,hd,L,N,masked", CASES)
-def test_attention_fwd_bwd(cuda_device, B, H, hd, L, N, masked):
+def test_attention_fwd_bwd(cuda_device, B, H, hd, L, N, masked, impl):
     from diffulab_b200 import ops
 
     g = torch.Generator(device="cuda").manual_seed(B * 100 + H * 10 + hd + L)
@@ -53,7 +55,7 @@ def test_attention_fwd_bwd(cuda_device, B, H, hd, L, N, masked):
         mask_full = torch.cat([m, torch.ones(B, N, device="cuda", dtype=torch.bool)], 1)
     scale = hd ** -0.5
     specs = [ops.AttnSegSpec(qk, qkv, l) for qk, qkv, l in zip(qks, qkvs, segs_len)]
-    outs, lse = ops.attn_fwd(specs, B, H, hd, scale, kmask)
+    outs, lse = ops.attn_fwd(specs, B, H, hd, scale, kmask, impl=impl)
 
     def cat(parts, lo, hi):
         return torch.cat([p.view(B, l, -1)[..., lo:hi] for p, l in zip(parts, segs_len)], 1).float()
