@@ -38,26 +38,29 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.com
 
 enum { T_Q = 0, T_K = 1, T_V = 2 };
 
-// 128-row tile of tokens s0.. -> smem. K-major core layout (Q, K): chunk (row r, hd-chunk c) at (r/8)*SBO + c*128 + (r%8)*16,
-// SBO = (HDP/8)*128. MN-major layout (V as the B operand of P*V): chunk (key r, hd-chunk c) at c*2048 + (r/8)*128 + (r%8)*16.
+// 128-row tile of tokens s0.. -> smem; thread r stages row r (its 16-byte chunks are contiguous in global memory).
+// K-major core layout (Q, K): chunk (row r, hd-chunk c) at (r/8)*SBO + c*128 + (r%8)*16, SBO = (HDP/8)*128.
+// MN-major layout (V as the B operand of P*V): chunk (key r, hd-chunk c) at c*2048 + (r/8)*128 + (r%8)*16.
 template <int HDP, int WHICH>
-__device__ __forceinline__ void load_tile(uint8_t* sm, const Params& p, int b, int h, int s0, int tid, int nthreads) {
+__device__ __forceinline__ void load_tile(uint8_t* sm, const Params& p, int b, int h, int s0, int r) {
   constexpr int CPR = HDP / 8;
-  for (int idx = tid; idx < 128 * CPR; idx += nthreads) {
-    const int c = idx / 128, r = idx - c * 128;  // consecutive threads -> consecutive rows (conflict-free smem writes)
-    const int s = s0 + r;
-    uint8_t* dst = (WHICH == T_V) ? sm + c * 2048 + (r >> 3) * 128 + (r & 7) * 16
-                                  : sm + (r >> 3) * (CPR * 128) + c * 128 + (r & 7) * 16;
-    if (s < p.S && c * 8 < p.hd) {
-      const int sg = s < p.seg[0].len ? 0 : 1;
-      const Seg& g = p.seg[sg];
-      const int64_t row = (int64_t)b * g.len + (sg ? s - p.seg[0].len : s);
-      const bf16* base = WHICH == T_Q ? g.q : (WHICH == T_K ? g.k : g.v);
-      const int64_t ld = WHICH == T_Q ? g.ldq : (WHICH == T_K ? g.ldk : g.ldv);
-      cp_async16(dst, base + row * ld + (int64_t)h * p.hd + c * 8);
-    } else {
-      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+  const int s = s0 + r;
+  uint8_t* dst = (WHICH == T_V) ? sm + (r >> 3) * 128 + (r & 7) * 16 : sm + (r >> 3) * (CPR * 128) + (r & 7) * 16;
+  constexpr int CSTRIDE = (WHICH == T_V) ? 2048 : 128;
+  const int nvalid = p.hd >> 3;
+  if (s < p.S) {
+    const int sg = s < p.seg[0].len ? 0 : 1;
+    const Seg& g = p.seg[sg];
+    const int64_t row = (int64_t)b * g.len + (sg ? s - p.seg[0].len : s);
+    const bf16* src = (WHICH == T_Q ? g.q + row * g.ldq : (WHICH == T_K ? g.k + row * g.ldk : g.v + row * g.ldv)) + (int64_t)h * p.hd;
+#pragma unroll
+    for (int c = 0; c < CPR; ++c) {
+      if (c < nvalid) cp_async16(dst + c * CSTRIDE, src + c * 8);
+      else *reinterpret_cast<uint4*>(dst + c * CSTRIDE) = make_uint4(0, 0, 0, 0);
     }
+  } else {
+#pragma unroll
+    for (int c = 0; c < CPR; ++c) *reinterpret_cast<uint4*>(dst + c * CSTRIDE) = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const Params p) {
     ptx::fence_mbar_init();
   }
   if (warp == 0) ptx::tmem_alloc<256>(&tmem_slot);
-  load_tile<HDP, T_Q>(sQ, p, b, h, q0, tid, 128);
+  load_tile<HDP, T_Q>(sQ, p, b, h, q0, tid);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -100,19 +103,19 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const Params p) {
   uint32_t phase = 0;
 
   for (int kv0 = 0; kv0 < p.S; kv0 += 128) {
-    load_tile<HDP, T_K>(sK, p, b, h, kv0, tid, 128);
-    load_tile<HDP, T_V>(sV, p, b, h, kv0, tid, 128);
+    load_tile<HDP, T_K>(sK, p, b, h, kv0, tid);
+    load_tile<HDP, T_V>(sV, p, b, h, kv0, tid);
+    float my_bias = 0.f;
     {
       const int key = kv0 + tid;
-      float bias = 0.f;
-      if (key >= p.S) bias = -INFINITY;
-      else if (p.kmask && key < p.mask_len && p.kmask[(int64_t)b * p.mask_len + key] == 0) bias = -INFINITY;
-      sBias[tid] = bias;
+      if (key >= p.S) my_bias = -INFINITY;
+      else if (p.kmask && key < p.mask_len && p.kmask[(int64_t)b * p.mask_len + key] == 0) my_bias = -INFINITY;
+      sBias[tid] = my_bias;
     }
     cp_async_wait_all();
     ptx::fence_proxy_async_smem();
     ptx::tc_fence_before();
-    __syncthreads();
+    const bool masked_tile = __syncthreads_or(my_bias != 0.f);  // uniform: any masked / out-of-range key in this tile
     if (tid == 0) {
       ptx::tc_fence_after();
       const uint32_t qa = ptx::smem_u32(sQ), ka = ptx::smem_u32(sK);
@@ -132,8 +135,13 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const Params p) {
       uint32_t r[32];
       ptx::tmem_ld32(tS + lane_off + c, r);
       ptx::tmem_ld_wait();
+      if (masked_tile) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]) + sBias[c + j]);
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]) + sBias[c + j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+      }
     }
     const float m_new = fmaxf(m, mx);
     const float ms = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
@@ -147,11 +155,15 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const Params p) {
       ptx::tmem_ld32(tS + lane_off + c, r);
       ptx::tmem_ld_wait();
       float pv[32];
+      if (masked_tile) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        pv[j] = ex2((__uint_as_float(r[j]) + sBias[c + j]) * p.scale_log2 - ms);
-        lsum += pv[j];
+        for (int j = 0; j < 32; ++j) pv[j] = ex2((__uint_as_float(r[j]) + sBias[c + j]) * p.scale_log2 - ms);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pv[j] = ex2(__uint_as_float(r[j]) * p.scale_log2 - ms);
       }
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) lsum += (pv[j] + pv[j + 1]) + (pv[j + 2] + pv[j + 3]);
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         uint4 v;
