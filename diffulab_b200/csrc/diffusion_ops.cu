@@ -254,20 +254,55 @@ __global__ void euler_step_kernel(const float* __restrict__ x, const TV* __restr
 
 // torch.optim.AdamW (no amsgrad, no maximize): p *= 1 - lr*wd; m,v update; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).
 // Also refreshes the bf16 shadow copy used by the GEMMs and (optionally) the EMA copy.
-__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                             float* __restrict__ v, bf16* __restrict__ shadow, float* __restrict__ ema, float ema_decay,
-                             int64_t n, float lr, float beta1, float beta2, float eps, float wd, float bc1,
-                             float bc2_sqrt, float grad_scale) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float gi = g[i] * grad_scale;
-    float pi = p[i] * (1.f - lr * wd);
-    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    pi -= (lr / bc1) * (mi / denom);
-    p[i] = pi; m[i] = mi; v[i] = vi;
-    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
-    if (ema) ema[i] = ema[i] * ema_decay + pi * (1.f - ema_decay);
+__device__ __forceinline__ void adamw_one(float& pi, float gi, float& mi, float& vi, float lr, float beta1, float beta2,
+                                          float eps, float wd, float bc1, float bc2_sqrt) {
+  pi *= (1.f - lr * wd);
+  mi = beta1 * mi + (1.f - beta1) * gi;
+  vi = beta2 * vi + (1.f - beta2) * gi * gi;
+  pi -= (lr / bc1) * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+}
+// 4 parameters per thread per iteration (128-bit loads / stores; n4 = n / 4), scalar tail handled by the last block
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             bf16* __restrict__ shadow, float* __restrict__ ema, float ema_decay, int64_t n, float lr, float beta1,
+             float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adamw_one(pv.x, gv.x * grad_scale, mv.x, vv.x, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
+    adamw_one(pv.y, gv.y * grad_scale, mv.y, vv.y, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
+    adamw_one(pv.z, gv.z * grad_scale, mv.z, vv.z, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
+    adamw_one(pv.w, gv.w * grad_scale, mv.w, vv.w, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (shadow) {
+      uint2 s2;
+      s2.x = pack_bf16x2(pv.x, pv.y);
+      s2.y = pack_bf16x2(pv.z, pv.w);
+      reinterpret_cast<uint2*>(shadow)[i] = s2;
+    }
+    if (ema) {
+      float4 ev = reinterpret_cast<float4*>(ema)[i];
+      ev.x = ev.x * ema_decay + pv.x * (1.f - ema_decay);
+      ev.y = ev.y * ema_decay + pv.y * (1.f - ema_decay);
+      ev.z = ev.z * ema_decay + pv.z * (1.f - ema_decay);
+      ev.w = ev.w * ema_decay + pv.w * (1.f - ema_decay);
+      reinterpret_cast<float4*>(ema)[i] = ev;
+    }
+  }
+  if (blockIdx.x == gridDim.x - 1) {
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      float pi = p[i], mi = m[i], vi = v[i];
+      adamw_one(pi, g[i] * grad_scale, mi, vi, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
+      p[i] = pi; m[i] = mi; v[i] = vi;
+      if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+      if (ema) ema[i] = ema[i] * ema_decay + pi * (1.f - ema_decay);
+    }
   }
 }
 
@@ -374,7 +409,10 @@ DLB_EXPORT int dlb_adamw_step(float* p, const float* g, float* m, float* v, void
   DLB_REQUIRE(n > 0 && step >= 1, DLB_ERR_SHAPE, "adamw_step: bad args");
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
-  adamw_kernel<<<grid_for(n), 256, 0, stream>>>(p, g, m, v, (bf16*)shadow, ema, ema_decay, n, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
+  DLB_REQUIRE(((uintptr_t)p % 16) == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)m % 16) == 0 && ((uintptr_t)v % 16) == 0 &&
+                  ((uintptr_t)shadow % 8) == 0 && ((uintptr_t)ema % 16) == 0,
+              DLB_ERR_ALIGN, "adamw_step: buffers must be 16-byte aligned");
+  adamw_kernel<<<grid_for((n + 3) / 4), 256, 0, stream>>>(p, g, m, v, (bf16*)shadow, ema, ema_decay, n, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
   dlb_count_launch();
   return dlb_check_launch("adamw_step");
 }

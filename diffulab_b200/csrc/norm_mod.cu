@@ -1,22 +1,33 @@
 // Fused LayerNorm + adaLN modulate, gated residual, packed SwiGLU: the bandwidth-bound token-stream kernels.
-// One warp owns one token row (d <= 2048 channels kept in registers as 16-byte bf16x8 vectors); statistics
-// via warp shuffles; every global access is a 128-bit coalesced vector.
 //
 // Reference semantics (bf16 autocast on CUDA):
 //   ln_modulate : modulate(nn.LayerNorm(x), scale, shift)      mmdit.py:257-259,299,305 ; nn.py:539-540
 //   gate_res    : x + branch * gate                            mmdit.py:296-307
 //   swiglu      : silu(x1) * x3 on the packed up-projection    nn.py:478-486
+//
+// Shapes of the kernels (all accesses are 128-bit, coalesced):
+//   row kernels  : one warp owns one token row (d <= 2048); the row is kept PACKED (bf16x8 vectors) in registers so
+//                  the kernels stay at <= 64-80 registers (6-8 CTAs of 4 warps per SM); statistics via warp shuffles.
+//   col kernels  : one thread owns one 8-channel vector and marches down a chunk of rows in batches of 4 rows (8+
+//                  independent 16-byte loads in flight per thread); per-sample sums land in the fp32 adaLN-gradient
+//                  buffer with one low-contention atomic per column per block.
+//   stream kernels: grid-stride over vectors, 2-4 independent vectors per thread per iteration.
 #include "common.cuh"
 
 namespace {
 
 typedef __nv_bfloat16 bf16;
 
+__device__ __forceinline__ void ldf8(const float* p, float* f) {
+  *reinterpret_cast<float4*>(f) = __ldg(reinterpret_cast<const float4*>(p));
+  *reinterpret_cast<float4*>(f + 4) = __ldg(reinterpret_cast<const float4*>(p + 4));
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // LayerNorm (+affine) + modulate forward
 // ---------------------------------------------------------------------------------------------------------
 template <int VPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 6)
 ln_modulate_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                        const bf16* __restrict__ scale, const bf16* __restrict__ shift, int64_t mod_ld,
                        int rows_per_mod, bf16* __restrict__ y, float* __restrict__ mean_out,
@@ -26,15 +37,20 @@ ln_modulate_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, 
   if (row >= R) return;
   const int nv = d >> 3;
   const bf16* xr = x + row * d;
-  float xv[VPL][8];
-  float sum = 0.f;
+  bf16x8 xp[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int v = lane + 32 * i;
-    if (v < nv) {
-      unpack8(ld8(xr + v * 8), xv[i]);
+    if (v < nv) xp[i] = ld8(xr + v * 8);
+  }
+  float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sum += xv[i][j];
+  for (int i = 0; i < VPL; ++i) {
+    if (lane + 32 * i < nv) {
+      float f[8];
+      unpack8(xp[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += f[j];
     }
   }
   const float mean = warp_sum(sum) / d;
@@ -42,8 +58,10 @@ ln_modulate_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, 
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     if (lane + 32 * i < nv) {
+      float f[8];
+      unpack8(xp[i], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float t = xv[i][j] - mean; sq += t * t; }
+      for (int j = 0; j < 8; ++j) { const float t = f[j] - mean; sq += t * t; }
     }
   }
   const float rstd = rsqrtf(warp_sum(sq) / d + eps);
@@ -56,22 +74,20 @@ ln_modulate_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, 
   for (int i = 0; i < VPL; ++i) {
     const int v = lane + 32 * i;
     if (v < nv) {
-      float s[8], t[8], o[8];
+      float f[8], s[8], t[8], o[8];
+      unpack8(xp[i], f);
       unpack8(ld8(sc + v * 8), s);
       unpack8(ld8(sh + v * 8), t);
-      float wv[8], bv[8];
+      // reference: `1 + scale` is evaluated in bf16 before meeting the fp32 LayerNorm output
       if (w) {
-        *reinterpret_cast<float4*>(wv) = __ldg(reinterpret_cast<const float4*>(w + v * 8));
-        *reinterpret_cast<float4*>(wv + 4) = __ldg(reinterpret_cast<const float4*>(w + v * 8 + 4));
-        *reinterpret_cast<float4*>(bv) = __ldg(reinterpret_cast<const float4*>(b + v * 8));
-        *reinterpret_cast<float4*>(bv + 4) = __ldg(reinterpret_cast<const float4*>(b + v * 8 + 4));
-      }
+        float wv[8], bv[8];
+        ldf8(w + v * 8, wv);
+        ldf8(b + v * 8, bv);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float u = (xv[i][j] - mean) * rstd;
-        if (w) u = u * wv[j] + bv[j];
-        // reference: `1 + scale` is evaluated in bf16 before meeting the fp32 LayerNorm output
-        o[j] = u * bf16_round(1.f + s[j]) + t[j];
+        for (int j = 0; j < 8; ++j) o[j] = ((f[j] - mean) * rstd * wv[j] + bv[j]) * bf16_round(1.f + s[j]) + t[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean) * rstd * bf16_round(1.f + s[j]) + t[j];
       }
       st8(yr + v * 8, pack8(o));
     }
@@ -79,16 +95,15 @@ ln_modulate_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// LayerNorm + modulate backward, two bandwidth-shaped kernels:
-//  (1) rows: one warp per token row -> dx (+dres); per-token mode also writes dscale/dshift rows.
-//  (2) cols: one thread per 8-channel vector, marching down a chunk of rows -> two column accumulators
-//        per-sample mode : S1 = sum dy           S2 = sum dy * xhat
-//        per-token  mode : S1 = sum dy*(1+scale) S2 = sum dy*(1+scale)*xhat
-//      which are enough for dshift, dscale, dw and db ("LN backward algebra"); one atomic per column
-//      per block. Keeping the column sums out of kernel (1) keeps it at ~100 registers (2+ CTAs per SM).
+// LayerNorm + modulate backward:
+//  (1) rows kernel: dx (+dres); per-token mode also writes the dscale/dshift rows.
+//  (2) cols kernel: S1 = sum_rows dy, S2 = sum_rows dy * xhat per modulation group (per-token mode: weighted by
+//      (1+scale_row), reduced over all rows straight into db/dw).
+//  (3) finalize kernel (per-sample mode): dshift = S1, dscale = w S2 + b S1, dw += sum_g (1+s_g) S2_g,
+//      db += sum_g (1+s_g) S1_g.            ("LN backward algebra")
 // ---------------------------------------------------------------------------------------------------------
 template <int VPL, bool PER_TOKEN>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 ln_modulate_bwd_rows_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean_in,
                             const float* __restrict__ rstd_in, const float* __restrict__ w, const float* __restrict__ b,
                             const bf16* __restrict__ scale, int64_t mod_ld, int64_t rows_per_mod,
@@ -98,54 +113,70 @@ ln_modulate_bwd_rows_kernel(const bf16* __restrict__ dy, const bf16* __restrict_
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= R) return;
   const int nv = d >> 3;
-  const float mean = mean_in[row], rstd = rstd_in[row];
   const bf16* sc = scale + (row / rows_per_mod) * mod_ld;
-  float xh[VPL][8], gw[VPL][8];
+  bf16x8 xp[VPL], gp[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nv) {
+      xp[i] = ld8(x + row * d + v * 8);
+      gp[i] = ld8(dy + row * d + v * 8);
+    }
+  }
+  const float mean = mean_in[row], rstd = rstd_in[row];
   float m1 = 0.f, m2 = 0.f;
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int v = lane + 32 * i;
     if (v < nv) {
-      float g[8], s[8];
-      unpack8(ld8(x + row * d + v * 8), xh[i]);
-      unpack8(ld8(dy + row * d + v * 8), g);
+      float xf[8], g[8], s[8], wv[8];
+      unpack8(xp[i], xf);
+      unpack8(gp[i], g);
       unpack8(ld8(sc + v * 8), s);
-      float wv[8], bv[8];
-      if (w) {
-        *reinterpret_cast<float4*>(wv) = __ldg(reinterpret_cast<const float4*>(w + v * 8));
-        *reinterpret_cast<float4*>(wv + 4) = __ldg(reinterpret_cast<const float4*>(w + v * 8 + 4));
-        if (PER_TOKEN) {
-          *reinterpret_cast<float4*>(bv) = __ldg(reinterpret_cast<const float4*>(b + v * 8));
-          *reinterpret_cast<float4*>(bv + 4) = __ldg(reinterpret_cast<const float4*>(b + v * 8 + 4));
-        }
-      }
+      if (w) ldf8(w + v * 8, wv);
       float ds_tok[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        xh[i][j] = (xh[i][j] - mean) * rstd;
-        const float gu = g[j] * bf16_round(1.f + s[j]);  // grad wrt the affine LayerNorm output u
-        if (PER_TOKEN) ds_tok[j] = g[j] * (w ? xh[i][j] * wv[j] + bv[j] : xh[i][j]);
-        gw[i][j] = w ? gu * wv[j] : gu;
-        m1 += gw[i][j];
-        m2 += gw[i][j] * xh[i][j];
+        const float xh = (xf[j] - mean) * rstd;
+        float gq = g[j] * bf16_round(1.f + s[j]);  // grad wrt the affine LayerNorm output u
+        if (w) gq *= wv[j];
+        m1 += gq;
+        m2 += gq * xh;
+        if (PER_TOKEN) ds_tok[j] = g[j] * (w ? xh * wv[j] + __ldg(b + v * 8 + j) : xh);
       }
       if (PER_TOKEN) {
         st8(dscale_tok + row * dtok_ld + v * 8, pack8(ds_tok));
-        st8(dshift_tok + row * dtok_ld + v * 8, pack8(g));
+        st8(dshift_tok + row * dtok_ld + v * 8, gp[i]);
       }
+    }
+  }
+  bf16x8 rp[VPL];  // residual-branch gradient: fetched while the row statistics are being reduced
+  if (dres) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nv) rp[i] = ld8(dres + row * d + v * 8);
     }
   }
   m1 = warp_sum(m1) / d;
   m2 = warp_sum(m2) / d;
+  // pass 2 recomputes g_w from the packed registers (scale / w come from L1) instead of keeping 40 more floats live
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int v = lane + 32 * i;
     if (v < nv) {
-      float o[8];
-      if (dres) unpack8(ld8(dres + row * d + v * 8), o);
+      float xf[8], g[8], s[8], wv[8], o[8];
+      unpack8(xp[i], xf);
+      unpack8(gp[i], g);
+      unpack8(ld8(sc + v * 8), s);
+      if (w) ldf8(w + v * 8, wv);
+      if (dres) unpack8(rp[i], o);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float t = rstd * (gw[i][j] - m1 - xh[i][j] * m2);
+        const float xh = (xf[j] - mean) * rstd;
+        float gq = g[j] * bf16_round(1.f + s[j]);
+        if (w) gq *= wv[j];
+        const float t = rstd * (gq - m1 - xh * m2);
         o[j] = dres ? o[j] + t : t;
       }
       st8(dx + row * d + v * 8, pack8(o));
@@ -153,200 +184,328 @@ ln_modulate_bwd_rows_kernel(const bf16* __restrict__ dy, const bf16* __restrict_
   }
 }
 
-// grid (col chunks, row chunks, groups); thread = one 8-channel vector, marching down its row chunk
+// grid (col chunks, row chunks, groups); block = one thread per 8-channel vector
 template <bool PER_TOKEN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 ln_modulate_bwd_cols_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean_in,
-                            const float* __restrict__ rstd_in, const float* __restrict__ w, const float* __restrict__ b,
-                            const bf16* __restrict__ scale, int64_t mod_ld, int64_t rows_per_group,
-                            float* __restrict__ dscale, float* __restrict__ dshift, int64_t dmod_ld,
-                            float* __restrict__ dw, float* __restrict__ db, int d, int rows_per_block) {
+                            const float* __restrict__ rstd_in, const bf16* __restrict__ scale, int64_t mod_ld,
+                            int64_t rows_per_group, float* __restrict__ acc1, float* __restrict__ acc2, int64_t acc_ld,
+                            int d, int rows_per_block) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= (d >> 3)) return;
   const int c = v * 8;
   const int64_t group = blockIdx.z;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r1 = min(r0 + rows_per_block, rows_per_group);
+  const int64_t base = group * rows_per_group;
   float S1[8], S2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { S1[j] = 0.f; S2[j] = 0.f; }
-  const int64_t base = group * rows_per_group;
-#pragma unroll 4
-  for (int64_t rl = r0; rl < r1; ++rl) {
-    const int64_t row = base + rl;
-    float xv[8], g[8];
-    unpack8(ld8(x + row * d + c), xv);
-    unpack8(ld8(dy + row * d + c), g);
-    const float mean = __ldg(mean_in + row), rstd = __ldg(rstd_in + row);
-    if (PER_TOKEN) {
-      float s[8];
-      unpack8(ld8(scale + row * mod_ld + c), s);
+  for (int64_t rb = r0; rb < r1; rb += 4) {
+    bf16x8 xa[4], ga[4], sa[4];
+    float mu[4], rs[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] *= bf16_round(1.f + s[j]);
+    for (int u = 0; u < 4; ++u) {
+      const int64_t row = base + rb + u;
+      if (rb + u < r1) {
+        xa[u] = ld8(x + row * d + c);
+        ga[u] = ld8(dy + row * d + c);
+        if (PER_TOKEN) sa[u] = ld8(scale + row * mod_ld + c);
+        mu[u] = __ldg(mean_in + row);
+        rs[u] = __ldg(rstd_in + row);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      S1[j] += g[j];
-      S2[j] += g[j] * (xv[j] - mean) * rstd;
-    }
-  }
-  if (PER_TOKEN) {
-    if (dw) {
+    for (int u = 0; u < 4; ++u) {
+      if (rb + u < r1) {
+        float xf[8], g[8];
+        unpack8(xa[u], xf);
+        unpack8(ga[u], g);
+        if (PER_TOKEN) {
+          float s[8];
+          unpack8(sa[u], s);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { atomicAdd(dw + c + j, S2[j]); atomicAdd(db + c + j, S1[j]); }
-    }
-  } else {
-    float s[8];
-    unpack8(ld8(scale + group * mod_ld + c), s);
+          for (int j = 0; j < 8; ++j) g[j] *= bf16_round(1.f + s[j]);
+        }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float wc = w ? __ldg(w + c + j) : 1.f, bc = w ? __ldg(b + c + j) : 0.f;
-      atomicAdd(dshift + group * dmod_ld + c + j, S1[j]);
-      atomicAdd(dscale + group * dmod_ld + c + j, wc * S2[j] + bc * S1[j]);
-      if (dw) {
-        const float one_s = bf16_round(1.f + s[j]);
-        atomicAdd(dw + c + j, one_s * S2[j]);
-        atomicAdd(db + c + j, one_s * S1[j]);
+        for (int j = 0; j < 8; ++j) {
+          S1[j] += g[j];
+          S2[j] += g[j] * (xf[j] - mu[u]) * rs[u];
+        }
       }
     }
   }
+  // per-sample: acc1/acc2 = dshift/dscale rows of this group (raw sums, finalised later); per-token: db/dw
+  float* a1 = acc1 + (PER_TOKEN ? 0 : group * acc_ld) + c;
+  float* a2 = acc2 + (PER_TOKEN ? 0 : group * acc_ld) + c;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { atomicAdd(a1 + j, S1[j]); atomicAdd(a2 + j, S2[j]); }
+}
+
+// grid (col blocks, group chunks): thread = one column, loops over a chunk of groups
+__global__ void __launch_bounds__(256)
+ln_modulate_bwd_finalize_kernel(const float* __restrict__ w, const float* __restrict__ b, const bf16* __restrict__ scale,
+                                int64_t mod_ld, float* __restrict__ dscale, float* __restrict__ dshift, int64_t dmod_ld,
+                                float* __restrict__ dw, float* __restrict__ db, int d, int64_t groups, int groups_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  const int64_t g0 = (int64_t)blockIdx.y * groups_per_block;
+  const int64_t g1 = min(g0 + groups_per_block, groups);
+  const float wc = w ? w[c] : 1.f, bc = w ? b[c] : 0.f;
+  float aw = 0.f, ab = 0.f;
+#pragma unroll 4
+  for (int64_t g = g0; g < g1; ++g) {
+    const float s1 = dshift[g * dmod_ld + c], s2 = dscale[g * dmod_ld + c];
+    const float one_s = bf16_round(1.f + __bfloat162float(scale[g * mod_ld + c]));
+    dscale[g * dmod_ld + c] = wc * s2 + bc * s1;
+    aw += one_s * s2;
+    ab += one_s * s1;
+  }
+  if (dw) { atomicAdd(dw + c, aw); atomicAdd(db + c, ab); }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // gated residual: out = x + (a1 [+ a2]) * gate        (bf16 roundings placed where the reference rounds)
 // ---------------------------------------------------------------------------------------------------------
+template <bool TWO>
 __global__ void __launch_bounds__(256)
 gate_residual_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ a1, const bf16* __restrict__ a2,
                          const bf16* __restrict__ gate, int64_t gate_ld, int rows_per_mod, bf16* __restrict__ out,
                          int64_t R, int d) {
   const int nv = d >> 3;
   const int64_t total = R * nv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / nv;
-    const int v = (int)(i - row * nv);
-    float xv[8], av[8], gv[8], o[8];
-    unpack8(ld8(x + row * d + v * 8), xv);
-    unpack8(ld8(a1 + row * d + v * 8), av);
-    if (a2) {
-      float bv[8];
-      unpack8(ld8(a2 + row * d + v * 8), bv);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    bf16x8 xv[4], av[4], bv[4], gv[4];
+    int64_t off[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) av[j] = bf16_round(av[j] + bv[j]);
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < total) {
+        const int64_t row = i / nv;
+        const int v = (int)(i - row * nv);
+        off[u] = row * d + v * 8;
+        xv[u] = ld8(x + off[u]);
+        av[u] = ld8(a1 + off[u]);
+        if (TWO) bv[u] = ld8(a2 + off[u]);
+        gv[u] = ld8(gate + (row / rows_per_mod) * gate_ld + v * 8);
+      }
     }
-    unpack8(ld8(gate + (row / rows_per_mod) * gate_ld + v * 8), gv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = xv[j] + bf16_round(av[j] * gv[j]);
-    st8(out + row * d + v * 8, pack8(o));
-  }
-}
-
-// backward: da = dout * gate ; dgate[group] += sum_rows dout * a      (dx = dout is an alias, no kernel)
-template <int VPL, bool PER_TOKEN>
-__global__ void __launch_bounds__(256)
-gate_residual_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ a1, const bf16* __restrict__ a2,
-                         const bf16* __restrict__ gate, int64_t gate_ld, int64_t rows_per_group,
-                         bf16* __restrict__ da, float* __restrict__ dgate, int64_t dgate_ld,
-                         bf16* __restrict__ dgate_tok, int64_t dtok_ld, int d, int rows_per_warp) {
-  extern __shared__ float red[];  // [warps][d]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int nv = d >> 3;
-  const int64_t group = blockIdx.y;
-  const int64_t r_begin = ((int64_t)blockIdx.x * nwarps + warp) * rows_per_warp;
-  const int64_t r_end = min(r_begin + rows_per_warp, rows_per_group);
-  float S[VPL][8];
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u * stride < total) {
+        float xf[8], a[8], g[8], o[8];
+        unpack8(xv[u], xf);
+        unpack8(av[u], a);
+        unpack8(gv[u], g);
+        if (TWO) {
+          float b2[8];
+          unpack8(bv[u], b2);
 #pragma unroll
-  for (int i = 0; i < VPL; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) S[i][j] = 0.f;
-  for (int64_t rl = r_begin; rl < r_end; ++rl) {
-    const int64_t row = group * rows_per_group + rl;
-    const bf16* gp = gate + (PER_TOKEN ? row : group) * gate_ld;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nv) {
-        float g[8], av[8], gv[8], o[8], dg[8];
-        unpack8(ld8(dout + row * d + v * 8), g);
-        unpack8(ld8(a1 + row * d + v * 8), av);
-        if (a2) {
-          float bv[8];
-          unpack8(ld8(a2 + row * d + v * 8), bv);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) av[j] = bf16_round(av[j] + bv[j]);
+          for (int j = 0; j < 8; ++j) a[j] = bf16_round(a[j] + b2[j]);
         }
-        unpack8(ld8(gp + v * 8), gv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          o[j] = g[j] * gv[j];
-          dg[j] = g[j] * av[j];
-          S[i][j] += dg[j];
-        }
-        st8(da + row * d + v * 8, pack8(o));
-        if (PER_TOKEN) st8(dgate_tok + row * dtok_ld + v * 8, pack8(dg));
+        for (int j = 0; j < 8; ++j) o[j] = xf[j] + bf16_round(a[j] * g[j]);
+        st8(out + off[u], pack8(o));
       }
     }
   }
-  if (PER_TOKEN) return;
+}
+
+// backward part 1 (stream): da = dout * gate  (per-token mode also writes dgate rows = dout * a)
+template <bool TWO, bool PER_TOKEN>
+__global__ void __launch_bounds__(256)
+gate_residual_bwd_stream_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ a1, const bf16* __restrict__ a2,
+                                const bf16* __restrict__ gate, int64_t gate_ld, int64_t rows_per_mod,
+                                bf16* __restrict__ da, bf16* __restrict__ dgate_tok, int64_t dtok_ld, int64_t R, int d) {
+  const int nv = d >> 3;
+  const int64_t total = R * nv;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    bf16x8 gv[4], dv[4], av[4], bv[4];
+    int64_t row[4];
+    int vv[4];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int v = lane + 32 * i;
-    if (v < nv) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) red[(size_t)warp * d + v * 8 + j] = S[i][j];
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < total) {
+        row[u] = i / nv;
+        vv[u] = (int)(i - row[u] * nv);
+        dv[u] = ld8(dout + row[u] * d + vv[u] * 8);
+        gv[u] = ld8(gate + (row[u] / rows_per_mod) * gate_ld + vv[u] * 8);
+        if (PER_TOKEN) {
+          av[u] = ld8(a1 + row[u] * d + vv[u] * 8);
+          if (TWO) bv[u] = ld8(a2 + row[u] * d + vv[u] * 8);
+        }
+      }
     }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float a = 0.f;
-    for (int wi = 0; wi < nwarps; ++wi) a += red[(size_t)wi * d + c];
-    atomicAdd(dgate + group * dgate_ld + c, a);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u * stride < total) {
+        float g[8], dd[8], o[8];
+        unpack8(gv[u], g);
+        unpack8(dv[u], dd);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = dd[j] * g[j];
+        st8(da + row[u] * d + vv[u] * 8, pack8(o));
+        if (PER_TOKEN) {
+          float a[8];
+          unpack8(av[u], a);
+          if (TWO) {
+            float b2[8];
+            unpack8(bv[u], b2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = bf16_round(a[j] + b2[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = dd[j] * a[j];
+          st8(dgate_tok + row[u] * dtok_ld + vv[u] * 8, pack8(o));
+        }
+      }
+    }
   }
 }
 
+// backward part 2 (cols): dgate[group] += sum_rows dout * (a1 [+ a2])
+template <bool TWO>
+__global__ void __launch_bounds__(256, 3)
+gate_residual_bwd_cols_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ a1, const bf16* __restrict__ a2,
+                              int64_t rows_per_group, float* __restrict__ dgate, int64_t dgate_ld, int d, int rows_per_block) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= (d >> 3)) return;
+  const int c = v * 8;
+  const int64_t group = blockIdx.z;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(r0 + rows_per_block, rows_per_group);
+  const int64_t base = group * rows_per_group;
+  float S[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) S[j] = 0.f;
+  for (int64_t rb = r0; rb < r1; rb += 4) {
+    bf16x8 da_[4], aa[4], ba[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t row = base + rb + u;
+      if (rb + u < r1) {
+        da_[u] = ld8(dout + row * d + c);
+        aa[u] = ld8(a1 + row * d + c);
+        if (TWO) ba[u] = ld8(a2 + row * d + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (rb + u < r1) {
+        float g[8], a[8];
+        unpack8(da_[u], g);
+        unpack8(aa[u], a);
+        if (TWO) {
+          float b2[8];
+          unpack8(ba[u], b2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = bf16_round(a[j] + b2[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) S[j] += g[j] * a[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(dgate + group * dgate_ld + c + j, S[j]);
+}
+
 // ---------------------------------------------------------------------------------------------------------
-// packed SwiGLU
+// packed SwiGLU (independent vectors per thread per iteration: loads first, then math, then stores)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 swiglu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ out, int64_t R, int F) {
   const int nv = F >> 3;
   const int64_t total = R * nv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / nv;
-    const int v = (int)(i - row * nv);
-    float a[8], g[8], o[8];
-    unpack8(ld8(h + row * 2 * F + v * 8), a);
-    unpack8(ld8(h + row * 2 * F + F + v * 8), g);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    bf16x8 av[4], gv[4];
+    int64_t oo[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = bf16_round(silu_f(a[j])) * g[j];
-    st8(out + row * F + v * 8, pack8(o));
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < total) {
+        const int64_t row = i / nv;
+        const int v = (int)(i - row * nv);
+        av[u] = ld8(h + row * 2 * F + v * 8);
+        gv[u] = ld8(h + row * 2 * F + F + v * 8);
+        oo[u] = row * F + v * 8;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u * stride < total) {
+        float a[8], g[8], o[8];
+        unpack8(av[u], a);
+        unpack8(gv[u], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = bf16_round(silu_f(a[j])) * g[j];
+        st8(out + oo[u], pack8(o));
+      }
+    }
   }
 }
 __global__ void __launch_bounds__(256)
 swiglu_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ h, bf16* __restrict__ dh, int64_t R, int F) {
   const int nv = F >> 3;
   const int64_t total = R * nv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / nv;
-    const int v = (int)(i - row * nv);
-    float a[8], g[8], go[8], da[8], dg[8];
-    unpack8(ld8(h + row * 2 * F + v * 8), a);
-    unpack8(ld8(h + row * 2 * F + F + v * 8), g);
-    unpack8(ld8(dout + row * F + v * 8), go);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+    bf16x8 av[2], gv[2], dv[2];
+    int64_t ho[2];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      da[j] = go[j] * g[j] * dsilu_f(a[j]);
-      dg[j] = go[j] * silu_f(a[j]);
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < total) {
+        const int64_t row = i / nv;
+        const int v = (int)(i - row * nv);
+        ho[u] = row * 2 * F + v * 8;
+        av[u] = ld8(h + ho[u]);
+        gv[u] = ld8(h + ho[u] + F);
+        dv[u] = ld8(dout + row * F + v * 8);
+      }
     }
-    st8(dh + row * 2 * F + v * 8, pack8(da));
-    st8(dh + row * 2 * F + F + v * 8, pack8(dg));
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (i0 + u * stride < total) {
+        float a[8], g[8], go[8], da[8], dg[8];
+        unpack8(av[u], a);
+        unpack8(gv[u], g);
+        unpack8(dv[u], go);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float sg = 1.f / (1.f + __expf(-a[j]));
+          da[j] = go[j] * g[j] * sg * (1.f + a[j] * (1.f - sg));
+          dg[j] = go[j] * a[j] * sg;
+        }
+        st8(dh + ho[u], pack8(da));
+        st8(dh + ho[u] + F, pack8(dg));
+      }
+    }
   }
 }
 
 int vpl_for(int d) { return (d / 8 + 31) / 32; }
-int ew_grid(int64_t total_vec) {
-  int64_t blocks = (total_vec + 255) / 256;
-  const int64_t cap = (int64_t)dlb_num_sms() * 16;
+int stream_grid(int64_t total_vec, int per_thread) {
+  int64_t blocks = (total_vec + 256 * per_thread - 1) / (256 * per_thread);
+  const int64_t cap = (int64_t)dlb_num_sms() * 8;
   return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+// blocks of `threads` vectors x rows_per_block rows: aim for ~6 blocks per SM, rows per block a multiple of 8
+void cols_grid(int d, int64_t groups, int64_t rows_per_group, int& threads, dim3& grid, int& rpb) {
+  const int nv = d / 8;
+  threads = nv < 256 ? (nv + 31) / 32 * 32 : 256;
+  const int col_chunks = (nv + threads - 1) / threads;
+  int64_t want = (int64_t)dlb_num_sms() * 6 / (col_chunks * groups);
+  if (want < 1) want = 1;
+  int64_t r = (rows_per_group + want - 1) / want;
+  r = (r + 7) / 8 * 8;
+  if (r < 8) r = 8;
+  rpb = (int)r;
+  grid = dim3(col_chunks, (unsigned)((rows_per_group + r - 1) / r), (unsigned)groups);
 }
 
 }  // namespace
@@ -370,7 +529,7 @@ DLB_EXPORT int dlb_ln_modulate_fwd(const void* x, const float* w, const float* b
               (long long)R, d, (long long)mod_ld);
   DLB_REQUIRE((w == nullptr) == (b == nullptr), DLB_ERR_SHAPE, "ln_modulate_fwd: weight and bias must both be set or null");
   DLB_REQUIRE(rows_per_mod >= 1 && (mean == nullptr) == (rstd == nullptr), DLB_ERR_SHAPE, "ln_modulate_fwd: bad args");
-  const int warps = 8;
+  const int warps = 4;
   const int grid = (int)((R + warps - 1) / warps);
   VPL_SWITCH(d, (ln_modulate_fwd_kernel<VPL><<<grid, warps * 32, 0, stream>>>(
                     (const bf16*)x, w, b, (const bf16*)scale, (const bf16*)shift, mod_ld, (int)rows_per_mod, (bf16*)y,
@@ -379,8 +538,10 @@ DLB_EXPORT int dlb_ln_modulate_fwd(const void* x, const float* w, const float* b
   return dlb_check_launch("ln_modulate_fwd");
 }
 
-// groups * rows_per_group rows. per_token != 0: scale is per row, dscale/dshift are written per row (bf16) into
-// dscale_tok/dshift_tok and `groups` must be 1. dres (optional) is added to dx. dw/db optional (non-affine LN).
+// groups * rows_per_group rows. Per-sample mode (per_token == 0): dscale/dshift are fp32 rows (stride dmod_ld), one per
+// group, that MUST BE ZERO on entry and are owned by this call. Per-token mode: scale is per row, dscale/dshift are
+// written per row (bf16) into dscale_tok/dshift_tok and `groups` must be 1. dres (optional) is added to dx.
+// dw/db (fp32 [d], accumulated) optional (must be NULL for the affine-free norm).
 DLB_EXPORT int dlb_ln_modulate_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* w,
                                    const float* b, const void* scale, int64_t mod_ld, int64_t groups,
                                    int64_t rows_per_group, int per_token, const void* dres, void* dx, float* dscale,
@@ -403,27 +564,26 @@ DLB_EXPORT int dlb_ln_modulate_bwd(const void* dy, const void* x, const float* m
                       (const bf16*)dy, (const bf16*)x, mean, rstd, w, b, (const bf16*)scale, mod_ld, rows_per_mod,
                       (const bf16*)dres, (bf16*)dx, nullptr, nullptr, 0, R, d)));
   }
-  if (!per_token || dw != nullptr) {
-    const int nv = d / 8;
-    int threads = nv < 256 ? (nv + 31) / 32 * 32 : 256;
-    const int col_chunks = (nv + threads - 1) / threads;
-    // ~4 blocks per SM in total, at least 16 rows per block so the final atomics stay a small fraction
-    int64_t want_blocks = (int64_t)dlb_num_sms() * 4 / (col_chunks * groups);
-    if (want_blocks < 1) want_blocks = 1;
-    int64_t rpb = (rows_per_group + want_blocks - 1) / want_blocks;
-    if (rpb < 16) rpb = 16;
-    dim3 grid(col_chunks, (unsigned)((rows_per_group + rpb - 1) / rpb), (unsigned)groups);
-    if (per_token)
-      ln_modulate_bwd_cols_kernel<true><<<grid, threads, 0, stream>>>((const bf16*)dy, (const bf16*)x, mean, rstd, w, b,
-                                                                     (const bf16*)scale, mod_ld, rows_per_group, dscale,
-                                                                     dshift, dmod_ld, dw, db, d, (int)rpb);
-    else
-      ln_modulate_bwd_cols_kernel<false><<<grid, threads, 0, stream>>>((const bf16*)dy, (const bf16*)x, mean, rstd, w, b,
-                                                                      (const bf16*)scale, mod_ld, rows_per_group, dscale,
-                                                                      dshift, dmod_ld, dw, db, d, (int)rpb);
-    dlb_count_launch();
-  }
   dlb_count_launch();
+  int threads, rpb;
+  dim3 grid;
+  cols_grid(d, groups, rows_per_group, threads, grid, rpb);
+  if (per_token) {
+    if (dw != nullptr) {
+      ln_modulate_bwd_cols_kernel<true><<<grid, threads, 0, stream>>>((const bf16*)dy, (const bf16*)x, mean, rstd,
+                                                                     (const bf16*)scale, mod_ld, rows_per_group, db, dw, 0, d, rpb);
+      dlb_count_launch();
+    }
+  } else {
+    ln_modulate_bwd_cols_kernel<false><<<grid, threads, 0, stream>>>((const bf16*)dy, (const bf16*)x, mean, rstd,
+                                                                    (const bf16*)scale, mod_ld, rows_per_group, dshift, dscale,
+                                                                    dmod_ld, d, rpb);
+    const int gpb = 16;
+    dim3 fgrid((d + 255) / 256, (unsigned)((groups + gpb - 1) / gpb));
+    ln_modulate_bwd_finalize_kernel<<<fgrid, 256, 0, stream>>>(w, b, (const bf16*)scale, mod_ld, dscale, dshift, dmod_ld, dw, db,
+                                                               d, groups, gpb);
+    dlb_count_launch(2);
+  }
   return dlb_check_launch("ln_modulate_bwd");
 }
 
@@ -431,49 +591,58 @@ DLB_EXPORT int dlb_gate_residual_fwd(const void* x, const void* a1, const void* 
                                      int64_t rows_per_mod, void* out, int64_t R, int d, cudaStream_t stream) {
   DLB_REQUIRE(R > 0 && d > 0 && d % 8 == 0 && gate_ld % 8 == 0 && rows_per_mod >= 1, DLB_ERR_SHAPE,
               "gate_residual_fwd: bad shape R=%lld d=%d", (long long)R, d);
-  gate_residual_fwd_kernel<<<ew_grid(R * (d / 8)), 256, 0, stream>>>((const bf16*)x, (const bf16*)a1, (const bf16*)a2,
-                                                                    (const bf16*)gate, gate_ld, (int)rows_per_mod,
-                                                                    (bf16*)out, R, d);
+  const int g = stream_grid(R * (d / 8), 4);
+  if (a2)
+    gate_residual_fwd_kernel<true><<<g, 256, 0, stream>>>((const bf16*)x, (const bf16*)a1, (const bf16*)a2, (const bf16*)gate,
+                                                         gate_ld, (int)rows_per_mod, (bf16*)out, R, d);
+  else
+    gate_residual_fwd_kernel<false><<<g, 256, 0, stream>>>((const bf16*)x, (const bf16*)a1, nullptr, (const bf16*)gate, gate_ld,
+                                                          (int)rows_per_mod, (bf16*)out, R, d);
   dlb_count_launch();
   return dlb_check_launch("gate_residual_fwd");
 }
 
+// da = dout * gate; per-sample mode: dgate fp32 rows (stride dgate_ld) accumulated; per-token: dgate_tok bf16 rows written
 DLB_EXPORT int dlb_gate_residual_bwd(const void* dout, const void* a1, const void* a2, const void* gate, int64_t gate_ld,
                                      int64_t groups, int64_t rows_per_group, int per_token, void* da, float* dgate,
                                      int64_t dgate_ld, void* dgate_tok, int64_t dtok_ld, int d, cudaStream_t stream) {
   DLB_REQUIRE(groups > 0 && rows_per_group > 0 && d > 0 && d % 8 == 0, DLB_ERR_SHAPE, "gate_residual_bwd: bad shape");
   DLB_REQUIRE(!per_token || groups == 1, DLB_ERR_SHAPE, "gate_residual_bwd: per-token mode takes a single group");
-  const int warps = 8;
-  int64_t rpw = rows_per_group * groups / ((int64_t)dlb_num_sms() * 4 * warps);
-  rpw = rpw < 1 ? 1 : (rpw > 8 ? 8 : rpw);
-  dim3 grid((unsigned)((rows_per_group + warps * rpw - 1) / (warps * rpw)), (unsigned)groups);
-  const size_t smem = (size_t)warps * d * sizeof(float);
-  if (per_token) {
-    VPL_SWITCH(d, (gate_residual_bwd_kernel<VPL, true><<<grid, warps * 32, smem, stream>>>(
-                      (const bf16*)dout, (const bf16*)a1, (const bf16*)a2, (const bf16*)gate, gate_ld, rows_per_group,
-                      (bf16*)da, dgate, dgate_ld, (bf16*)dgate_tok, dtok_ld, d, (int)rpw)));
-  } else {
-    VPL_SWITCH(d, {
-      auto k = gate_residual_bwd_kernel<VPL, false>;
-      if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      k<<<grid, warps * 32, smem, stream>>>((const bf16*)dout, (const bf16*)a1, (const bf16*)a2, (const bf16*)gate,
-                                           gate_ld, rows_per_group, (bf16*)da, dgate, dgate_ld, (bf16*)dgate_tok,
-                                           dtok_ld, d, (int)rpw);
-    });
-  }
+  const int64_t R = groups * rows_per_group;
+  const int64_t rows_per_mod = per_token ? 1 : rows_per_group;
+  const int g = stream_grid(R * (d / 8), 4);
+#define GATE_BWD_STREAM(TWO, PT)                                                                                         \
+  gate_residual_bwd_stream_kernel<TWO, PT><<<g, 256, 0, stream>>>((const bf16*)dout, (const bf16*)a1, (const bf16*)a2,  \
+                                                                  (const bf16*)gate, gate_ld, rows_per_mod, (bf16*)da,   \
+                                                                  (bf16*)dgate_tok, dtok_ld, R, d)
+  if (per_token) { if (a2) GATE_BWD_STREAM(true, true); else GATE_BWD_STREAM(false, true); }
+  else { if (a2) GATE_BWD_STREAM(true, false); else GATE_BWD_STREAM(false, false); }
+#undef GATE_BWD_STREAM
   dlb_count_launch();
+  if (!per_token) {
+    int threads, rpb;
+    dim3 grid;
+    cols_grid(d, groups, rows_per_group, threads, grid, rpb);
+    if (a2)
+      gate_residual_bwd_cols_kernel<true><<<grid, threads, 0, stream>>>((const bf16*)dout, (const bf16*)a1, (const bf16*)a2,
+                                                                       rows_per_group, dgate, dgate_ld, d, rpb);
+    else
+      gate_residual_bwd_cols_kernel<false><<<grid, threads, 0, stream>>>((const bf16*)dout, (const bf16*)a1, nullptr,
+                                                                        rows_per_group, dgate, dgate_ld, d, rpb);
+    dlb_count_launch();
+  }
   return dlb_check_launch("gate_residual_bwd");
 }
 
 DLB_EXPORT int dlb_swiglu_fwd(const void* h, void* out, int64_t R, int F, cudaStream_t stream) {
   DLB_REQUIRE(R > 0 && F > 0 && F % 8 == 0, DLB_ERR_SHAPE, "swiglu_fwd: bad shape R=%lld F=%d", (long long)R, F);
-  swiglu_fwd_kernel<<<ew_grid(R * (F / 8)), 256, 0, stream>>>((const bf16*)h, (bf16*)out, R, F);
+  swiglu_fwd_kernel<<<stream_grid(R * (F / 8), 4), 256, 0, stream>>>((const bf16*)h, (bf16*)out, R, F);
   dlb_count_launch();
   return dlb_check_launch("swiglu_fwd");
 }
 DLB_EXPORT int dlb_swiglu_bwd(const void* dout, const void* h, void* dh, int64_t R, int F, cudaStream_t stream) {
   DLB_REQUIRE(R > 0 && F > 0 && F % 8 == 0, DLB_ERR_SHAPE, "swiglu_bwd: bad shape R=%lld F=%d", (long long)R, F);
-  swiglu_bwd_kernel<<<ew_grid(R * (F / 8)), 256, 0, stream>>>((const bf16*)dout, (const bf16*)h, (bf16*)dh, R, F);
+  swiglu_bwd_kernel<<<stream_grid(R * (F / 8), 2), 256, 0, stream>>>((const bf16*)dout, (const bf16*)h, (bf16*)dh, R, F);
   dlb_count_launch();
   return dlb_check_launch("swiglu_bwd");
 }

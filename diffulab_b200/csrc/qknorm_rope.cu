@@ -24,7 +24,7 @@ __device__ __forceinline__ int rope_pos(const RopeArgs& ra, int64_t row) {
 }
 
 template <int VPL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 6)
 qknorm_rope_fwd_kernel(const bf16* __restrict__ qkv, int64_t ld_in, const float* __restrict__ sq,
                        const float* __restrict__ sk, RopeArgs ra, bf16* __restrict__ out, int64_t ld_out,
                        float* __restrict__ rrms_out, int64_t R, int d, float eps) {
@@ -35,19 +35,26 @@ qknorm_rope_fwd_kernel(const bf16* __restrict__ qkv, int64_t ld_in, const float*
   const int pos = rope_pos(ra, row);
   const float* cr = ra.cos_t + (int64_t)pos * ra.rot_half;
   const float* sr = ra.sin_t + (int64_t)pos * ra.rot_half;
-#pragma unroll 1
-  for (int which = 0; which < 2; ++which) {
-    const bf16* src = qkv + row * ld_in + which * d;
-    const float* sc = which ? sk : sq;
-    float xv[VPL][8];
-    float ss = 0.f;
+  // q and k rows are fetched together (2 * VPL independent 16-byte loads in flight) and kept packed
+  bf16x8 xp[2][VPL];
+#pragma unroll
+  for (int which = 0; which < 2; ++which)
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + 32 * i;
-      if (v < nv) {
-        unpack8(ld8(src + v * 8), xv[i]);
+      if (v < nv) xp[which][i] = ld8(qkv + row * ld_in + which * d + v * 8);
+    }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ss += xv[i][j] * xv[i][j];
+  for (int which = 0; which < 2; ++which) {
+    const float* sc = which ? sk : sq;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (lane + 32 * i < nv) {
+        float f[8];
+        unpack8(xp[which][i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
       }
     }
     const float rrms = rsqrtf(warp_sum(ss) / d + eps);
@@ -59,9 +66,12 @@ qknorm_rope_fwd_kernel(const bf16* __restrict__ qkv, int64_t ld_in, const float*
       if (v < nv) {
         const int c = v * 8;
         const int cl = c % ra.hd;  // channel inside the head; hd % 8 == 0 keeps a vector inside one head
-        float y[8];
+        float y[8], scv[8];
+        unpack8(xp[which][i], y);
+        *reinterpret_cast<float4*>(scv) = __ldg(reinterpret_cast<const float4*>(sc + c));
+        *reinterpret_cast<float4*>(scv + 4) = __ldg(reinterpret_cast<const float4*>(sc + c + 4));
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = bf16_round(bf16_round(xv[i][j] * rrms) * __ldg(sc + c + j));
+        for (int j = 0; j < 8; ++j) y[j] = bf16_round(bf16_round(y[j] * rrms) * scv[j]);
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
           const int pj = (cl + j) >> 1;
@@ -82,7 +92,7 @@ qknorm_rope_fwd_kernel(const bf16* __restrict__ qkv, int64_t ld_in, const float*
 //  rows: dqk (grad wrt normalised+rotated q,k) -> dq, dk written into the packed dqkv buffer (one warp per token);
 //  cols: column-accumulated gradients of the learnable RMS scales (one thread per 8-channel vector).
 template <int VPL>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 qknorm_rope_bwd_rows_kernel(const bf16* __restrict__ dqk, int64_t ld_dqk, const bf16* __restrict__ qkv, int64_t ld_in,
                             const float* __restrict__ sq, const float* __restrict__ sk, RopeArgs ra,
                             const float* __restrict__ rrms_in, bf16* __restrict__ dqkv, int64_t ld_out, int64_t R, int d) {
@@ -99,33 +109,42 @@ qknorm_rope_bwd_rows_kernel(const bf16* __restrict__ dqk, int64_t ld_dqk, const 
     const bf16* src = qkv + row * ld_in + which * d;
     const bf16* gsrc = dqk + row * ld_dqk + which * d;
     const float rrms = rrms_in[row * 2 + which];
-    float xn[VPL][8], gn[VPL][8];
-    float dot = 0.f;
+    bf16x8 xp[VPL], gp[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + 32 * i;
-      if (v < nv) {
-        const int c = v * 8;
-        const int cl = c % ra.hd;
-        float g[8];
-        unpack8(ld8(src + c), xn[i]);
-        unpack8(ld8(gsrc + c), g);
+      if (v < nv) { xp[i] = ld8(src + v * 8); gp[i] = ld8(gsrc + v * 8); }
+    }
+    // grad wrt the normalised value: transpose of the rotation, times the learnable scale
+    auto grad_norm = [&](int i, float* gn) {
+      const int c = (lane + 32 * i) * 8;
+      const int cl = c % ra.hd;
+      float scv[8];
+      unpack8(gp[i], gn);
+      *reinterpret_cast<float4*>(scv) = __ldg(reinterpret_cast<const float4*>(sc + c));
+      *reinterpret_cast<float4*>(scv + 4) = __ldg(reinterpret_cast<const float4*>(sc + c + 4));
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {  // transpose of the rotation
-          const int pj = (cl + j) >> 1;
-          if (pj < ra.rot_half) {
-            const float cs = bf16_round(__ldg(cr + pj)), sn = bf16_round(__ldg(sr + pj));
-            const float ge = g[j], go = g[j + 1];
-            g[j] = ge * cs + go * sn;
-            g[j + 1] = -ge * sn + go * cs;
-          }
+      for (int j = 0; j < 8; j += 2) {
+        const int pj = (cl + j) >> 1;
+        if (pj < ra.rot_half) {
+          const float cs = bf16_round(__ldg(cr + pj)), sn = bf16_round(__ldg(sr + pj));
+          const float ge = gn[j], go = gn[j + 1];
+          gn[j] = ge * cs + go * sn;
+          gn[j + 1] = -ge * sn + go * cs;
         }
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xn[i][j] *= rrms;                     // normalised value (fp32)
-          gn[i][j] = g[j] * __ldg(sc + c + j);  // grad wrt the normalised value
-          dot += gn[i][j] * xn[i][j];
-        }
+      for (int j = 0; j < 8; ++j) gn[j] *= scv[j];
+    };
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      if (lane + 32 * i < nv) {
+        float xn[8], gn[8];
+        unpack8(xp[i], xn);
+        grad_norm(i, gn);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dot += gn[j] * (xn[j] * rrms);
       }
     }
     dot = warp_sum(dot) / d;
@@ -134,17 +153,19 @@ qknorm_rope_bwd_rows_kernel(const bf16* __restrict__ dqk, int64_t ld_dqk, const 
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + 32 * i;
       if (v < nv) {
-        float o[8];
+        float xn[8], gn[8], o[8];
+        unpack8(xp[i], xn);
+        grad_norm(i, gn);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rrms * (gn[i][j] - xn[i][j] * dot);
+        for (int j = 0; j < 8; ++j) o[j] = rrms * (gn[j] - xn[j] * rrms * dot);
         st8(dst + v * 8, pack8(o));
       }
     }
   }
 }
 
-// grid (col chunks, row chunks, 2 = q/k)
-__global__ void __launch_bounds__(256)
+// grid (col chunks, row chunks, 2 = q/k); thread = one 8-channel vector marching down rows in batches of 4
+__global__ void __launch_bounds__(256, 3)
 qknorm_rope_bwd_cols_kernel(const bf16* __restrict__ dqk, int64_t ld_dqk, const bf16* __restrict__ qkv, int64_t ld_in,
                             RopeArgs ra, const float* __restrict__ rrms_in, float* __restrict__ dsq,
                             float* __restrict__ dsk, int64_t R, int d, int rows_per_block) {
@@ -158,27 +179,42 @@ qknorm_rope_bwd_cols_kernel(const bf16* __restrict__ dqk, int64_t ld_dqk, const 
   float S[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) S[j] = 0.f;
-#pragma unroll 4
-  for (int64_t row = r0; row < r1; ++row) {
-    float xq[8], g[8];
-    unpack8(ld8(qkv + row * ld_in + which * d + c), xq);
-    unpack8(ld8(dqk + row * ld_dqk + which * d + c), g);
-    const float rrms = __ldg(rrms_in + row * 2 + which);
-    const int pos = rope_pos(ra, row);
-    const float* cr = ra.cos_t + (int64_t)pos * ra.rot_half;
-    const float* sr = ra.sin_t + (int64_t)pos * ra.rot_half;
+  for (int64_t rb = r0; rb < r1; rb += 4) {
+    bf16x8 xa[4], ga[4];
+    float rr[4];
+    int ps[4];
 #pragma unroll
-    for (int j = 0; j < 8; j += 2) {
-      const int pj = (cl + j) >> 1;
-      if (pj < ra.rot_half) {
-        const float cs = bf16_round(__ldg(cr + pj)), sn = bf16_round(__ldg(sr + pj));
-        const float ge = g[j], go = g[j + 1];
-        g[j] = ge * cs + go * sn;
-        g[j + 1] = -ge * sn + go * cs;
+    for (int u = 0; u < 4; ++u) {
+      const int64_t row = rb + u;
+      if (row < r1) {
+        xa[u] = ld8(qkv + row * ld_in + which * d + c);
+        ga[u] = ld8(dqk + row * ld_dqk + which * d + c);
+        rr[u] = __ldg(rrms_in + row * 2 + which);
+        ps[u] = rope_pos(ra, row);
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) S[j] += g[j] * bf16_round(xq[j] * rrms);  // the reference multiplies the bf16-rounded value
+    for (int u = 0; u < 4; ++u) {
+      if (rb + u < r1) {
+        float xq[8], g[8];
+        unpack8(xa[u], xq);
+        unpack8(ga[u], g);
+        const float* cr = ra.cos_t + (int64_t)ps[u] * ra.rot_half;
+        const float* sr = ra.sin_t + (int64_t)ps[u] * ra.rot_half;
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const int pj = (cl + j) >> 1;
+          if (pj < ra.rot_half) {
+            const float cs = bf16_round(__ldg(cr + pj)), sn = bf16_round(__ldg(sr + pj));
+            const float ge = g[j], go = g[j + 1];
+            g[j] = ge * cs + go * sn;
+            g[j + 1] = -ge * sn + go * cs;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) S[j] += g[j] * bf16_round(xq[j] * rr[u]);  // the reference multiplies the bf16-rounded value
+      }
+    }
   }
   float* dsc = which ? dsk : dsq;
 #pragma unroll
@@ -216,7 +252,7 @@ DLB_EXPORT int dlb_qknorm_rope_fwd(const void* qkv, int64_t ld_in, const float* 
   if (rc) return rc;
   DLB_REQUIRE(R > 0 && ld_in % 8 == 0 && ld_out % 8 == 0, DLB_ERR_SHAPE, "qknorm_rope_fwd: bad strides");
   RopeArgs ra{cos_t, sin_t, pos_idx, rot_half, pos_offset, tokens_per_sample > 0 ? tokens_per_sample : 1, hd};
-  const int warps = 8;
+  const int warps = 4;
   const int grid = (int)((R + warps - 1) / warps);
   VPL_SWITCH(d, (qknorm_rope_fwd_kernel<VPL><<<grid, warps * 32, 0, stream>>>((const bf16*)qkv, ld_in, sq, sk, ra,
                                                                              (bf16*)out, ld_out, rrms, R, d, eps)));
@@ -243,9 +279,10 @@ DLB_EXPORT int dlb_qknorm_rope_bwd(const void* dqk, int64_t ld_dqk, const void* 
     const int nv = d / 8;
     const int threads = nv < 256 ? (nv + 31) / 32 * 32 : 256;
     const int col_chunks = (nv + threads - 1) / threads;
-    int64_t want_blocks = (int64_t)dlb_num_sms() * 4 / (col_chunks * 2);
+    int64_t want_blocks = (int64_t)dlb_num_sms() * 6 / (col_chunks * 2);
     if (want_blocks < 1) want_blocks = 1;
     int64_t rpb = (R + want_blocks - 1) / want_blocks;
+    rpb = (rpb + 3) / 4 * 4;
     if (rpb < 16) rpb = 16;
     dim3 g2(col_chunks, (unsigned)((R + rpb - 1) / rpb), 2);
     qknorm_rope_bwd_cols_kernel<<<g2, threads, 0, stream>>>((const bf16*)dqk, ld_dqk, (const bf16*)qkv, ld_in, ra, rrms, dsq,
