@@ -11,7 +11,8 @@
 //   col kernels  : one thread owns one 8-channel vector and marches down a chunk of rows in batches of 4 rows (8+
 //                  independent 16-byte loads in flight per thread); per-sample sums land in the fp32 adaLN-gradient
 //                  buffer with one low-contention atomic per column per block.
-//   stream kernels: grid-stride over vectors, 2-4 independent vectors per thread per iteration.
+//   stream kernels: grid-stride over vectors, one vector per thread-iteration, <= 42 registers (occupancy beats ILP
+//                  here: measured, profiles/elementwise_microbench_r1.jsonl).
 #include "common.cuh"
 
 namespace {
@@ -268,100 +269,63 @@ ln_modulate_bwd_finalize_kernel(const float* __restrict__ w, const float* __rest
 // gated residual: out = x + (a1 [+ a2]) * gate        (bf16 roundings placed where the reference rounds)
 // ---------------------------------------------------------------------------------------------------------
 template <bool TWO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 gate_residual_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ a1, const bf16* __restrict__ a2,
                          const bf16* __restrict__ gate, int64_t gate_ld, int rows_per_mod, bf16* __restrict__ out,
                          int64_t R, int d) {
   const int nv = d >> 3;
   const int64_t total = R * nv;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
-    bf16x8 xv[4], av[4], bv[4], gv[4];
-    int64_t off[4];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / nv;
+    const int v = (int)(i - row * nv);
+    const int64_t off = row * d + v * 8;
+    const bf16x8 xv = ld8(x + off), av = ld8(a1 + off), gv = ld8(gate + (row / rows_per_mod) * gate_ld + v * 8);
+    float xf[8], a[8], g[8], o[8];
+    unpack8(av, a);
+    if (TWO) {
+      float b2[8];
+      unpack8(ld8(a2 + off), b2);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t i = i0 + u * stride;
-      if (i < total) {
-        const int64_t row = i / nv;
-        const int v = (int)(i - row * nv);
-        off[u] = row * d + v * 8;
-        xv[u] = ld8(x + off[u]);
-        av[u] = ld8(a1 + off[u]);
-        if (TWO) bv[u] = ld8(a2 + off[u]);
-        gv[u] = ld8(gate + (row / rows_per_mod) * gate_ld + v * 8);
-      }
+      for (int j = 0; j < 8; ++j) a[j] = bf16_round(a[j] + b2[j]);
     }
+    unpack8(xv, xf);
+    unpack8(gv, g);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (i0 + u * stride < total) {
-        float xf[8], a[8], g[8], o[8];
-        unpack8(xv[u], xf);
-        unpack8(av[u], a);
-        unpack8(gv[u], g);
-        if (TWO) {
-          float b2[8];
-          unpack8(bv[u], b2);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) a[j] = bf16_round(a[j] + b2[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = xf[j] + bf16_round(a[j] * g[j]);
-        st8(out + off[u], pack8(o));
-      }
-    }
+    for (int j = 0; j < 8; ++j) o[j] = xf[j] + bf16_round(a[j] * g[j]);
+    st8(out + off, pack8(o));
   }
 }
 
 // backward part 1 (stream): da = dout * gate  (per-token mode also writes dgate rows = dout * a)
 template <bool TWO, bool PER_TOKEN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 gate_residual_bwd_stream_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ a1, const bf16* __restrict__ a2,
                                 const bf16* __restrict__ gate, int64_t gate_ld, int64_t rows_per_mod,
                                 bf16* __restrict__ da, bf16* __restrict__ dgate_tok, int64_t dtok_ld, int64_t R, int d) {
   const int nv = d >> 3;
   const int64_t total = R * nv;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
-    bf16x8 gv[4], dv[4], av[4], bv[4];
-    int64_t row[4];
-    int vv[4];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / nv;
+    const int v = (int)(i - row * nv);
+    const int64_t off = row * d + v * 8;
+    float g[8], dd[8], o[8];
+    unpack8(ld8(dout + off), dd);
+    unpack8(ld8(gate + (row / rows_per_mod) * gate_ld + v * 8), g);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t i = i0 + u * stride;
-      if (i < total) {
-        row[u] = i / nv;
-        vv[u] = (int)(i - row[u] * nv);
-        dv[u] = ld8(dout + row[u] * d + vv[u] * 8);
-        gv[u] = ld8(gate + (row[u] / rows_per_mod) * gate_ld + vv[u] * 8);
-        if (PER_TOKEN) {
-          av[u] = ld8(a1 + row[u] * d + vv[u] * 8);
-          if (TWO) bv[u] = ld8(a2 + row[u] * d + vv[u] * 8);
-        }
+    for (int j = 0; j < 8; ++j) o[j] = dd[j] * g[j];
+    st8(da + off, pack8(o));
+    if (PER_TOKEN) {
+      float a[8];
+      unpack8(ld8(a1 + off), a);
+      if (TWO) {
+        float b2[8];
+        unpack8(ld8(a2 + off), b2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = bf16_round(a[j] + b2[j]);
       }
-    }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (i0 + u * stride < total) {
-        float g[8], dd[8], o[8];
-        unpack8(gv[u], g);
-        unpack8(dv[u], dd);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = dd[j] * g[j];
-        st8(da + row[u] * d + vv[u] * 8, pack8(o));
-        if (PER_TOKEN) {
-          float a[8];
-          unpack8(av[u], a);
-          if (TWO) {
-            float b2[8];
-            unpack8(bv[u], b2);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = bf16_round(a[j] + b2[j]);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = dd[j] * a[j];
-          st8(dgate_tok + row[u] * dtok_ld + vv[u] * 8, pack8(o));
-        }
-      }
+      for (int j = 0; j < 8; ++j) o[j] = dd[j] * a[j];
+      st8(dgate_tok + row * dtok_ld + v * 8, pack8(o));
     }
   }
 }
@@ -414,84 +378,52 @@ gate_residual_bwd_cols_kernel(const bf16* __restrict__ dout, const bf16* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// packed SwiGLU (independent vectors per thread per iteration: loads first, then math, then stores)
+// packed SwiGLU (one vector per thread-iteration; <= 40 registers so 6+ CTAs of 256 threads stay resident)
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 swiglu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ out, int64_t R, int F) {
   const int nv = F >> 3;
   const int64_t total = R * nv;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
-    bf16x8 av[4], gv[4];
-    int64_t oo[4];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / nv;
+    const int v = (int)(i - row * nv);
+    const bf16x8 av = ld8(h + row * 2 * F + v * 8), gv = ld8(h + row * 2 * F + F + v * 8);
+    float a[8], g[8], o[8];
+    unpack8(av, a);
+    unpack8(gv, g);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t i = i0 + u * stride;
-      if (i < total) {
-        const int64_t row = i / nv;
-        const int v = (int)(i - row * nv);
-        av[u] = ld8(h + row * 2 * F + v * 8);
-        gv[u] = ld8(h + row * 2 * F + F + v * 8);
-        oo[u] = row * F + v * 8;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (i0 + u * stride < total) {
-        float a[8], g[8], o[8];
-        unpack8(av[u], a);
-        unpack8(gv[u], g);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = bf16_round(silu_f(a[j])) * g[j];
-        st8(out + oo[u], pack8(o));
-      }
-    }
+    for (int j = 0; j < 8; ++j) o[j] = bf16_round(silu_f(a[j])) * g[j];
+    st8(out + row * F + v * 8, pack8(o));
   }
 }
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 swiglu_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ h, bf16* __restrict__ dh, int64_t R, int F) {
   const int nv = F >> 3;
   const int64_t total = R * nv;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
-    bf16x8 av[2], gv[2], dv[2];
-    int64_t ho[2];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / nv;
+    const int v = (int)(i - row * nv);
+    const int64_t ho = row * 2 * F + v * 8;
+    const bf16x8 av = ld8(h + ho), gv = ld8(h + ho + F), dv = ld8(dout + row * F + v * 8);
+    float a[8], g[8], go[8], da[8], dg[8];
+    unpack8(av, a);
+    unpack8(gv, g);
+    unpack8(dv, go);
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int64_t i = i0 + u * stride;
-      if (i < total) {
-        const int64_t row = i / nv;
-        const int v = (int)(i - row * nv);
-        ho[u] = row * 2 * F + v * 8;
-        av[u] = ld8(h + ho[u]);
-        gv[u] = ld8(h + ho[u] + F);
-        dv[u] = ld8(dout + row * F + v * 8);
-      }
+    for (int j = 0; j < 8; ++j) {
+      const float sg = 1.f / (1.f + __expf(-a[j]));
+      da[j] = go[j] * g[j] * sg * (1.f + a[j] * (1.f - sg));
+      dg[j] = go[j] * a[j] * sg;
     }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (i0 + u * stride < total) {
-        float a[8], g[8], go[8], da[8], dg[8];
-        unpack8(av[u], a);
-        unpack8(gv[u], g);
-        unpack8(dv[u], go);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float sg = 1.f / (1.f + __expf(-a[j]));
-          da[j] = go[j] * g[j] * sg * (1.f + a[j] * (1.f - sg));
-          dg[j] = go[j] * a[j] * sg;
-        }
-        st8(dh + ho[u], pack8(da));
-        st8(dh + ho[u] + F, pack8(dg));
-      }
-    }
+    st8(dh + ho, pack8(da));
+    st8(dh + ho + F, pack8(dg));
   }
 }
 
 int vpl_for(int d) { return (d / 8 + 31) / 32; }
 int stream_grid(int64_t total_vec, int per_thread) {
   int64_t blocks = (total_vec + 256 * per_thread - 1) / (256 * per_thread);
-  const int64_t cap = (int64_t)dlb_num_sms() * 8;
+  const int64_t cap = (int64_t)dlb_num_sms() * 24;
   return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 // blocks of `threads` vectors x rows_per_block rows: aim for ~6 blocks per SM, rows per block a multiple of 8
@@ -591,7 +523,7 @@ DLB_EXPORT int dlb_gate_residual_fwd(const void* x, const void* a1, const void* 
                                      int64_t rows_per_mod, void* out, int64_t R, int d, cudaStream_t stream) {
   DLB_REQUIRE(R > 0 && d > 0 && d % 8 == 0 && gate_ld % 8 == 0 && rows_per_mod >= 1, DLB_ERR_SHAPE,
               "gate_residual_fwd: bad shape R=%lld d=%d", (long long)R, d);
-  const int g = stream_grid(R * (d / 8), 4);
+  const int g = stream_grid(R * (d / 8), 1);
   if (a2)
     gate_residual_fwd_kernel<true><<<g, 256, 0, stream>>>((const bf16*)x, (const bf16*)a1, (const bf16*)a2, (const bf16*)gate,
                                                          gate_ld, (int)rows_per_mod, (bf16*)out, R, d);
@@ -610,7 +542,7 @@ DLB_EXPORT int dlb_gate_residual_bwd(const void* dout, const void* a1, const voi
   DLB_REQUIRE(!per_token || groups == 1, DLB_ERR_SHAPE, "gate_residual_bwd: per-token mode takes a single group");
   const int64_t R = groups * rows_per_group;
   const int64_t rows_per_mod = per_token ? 1 : rows_per_group;
-  const int g = stream_grid(R * (d / 8), 4);
+  const int g = stream_grid(R * (d / 8), 1);
 #define GATE_BWD_STREAM(TWO, PT)                                                                                         \
   gate_residual_bwd_stream_kernel<TWO, PT><<<g, 256, 0, stream>>>((const bf16*)dout, (const bf16*)a1, (const bf16*)a2,  \
                                                                   (const bf16*)gate, gate_ld, rows_per_mod, (bf16*)da,   \
@@ -636,13 +568,13 @@ DLB_EXPORT int dlb_gate_residual_bwd(const void* dout, const void* a1, const voi
 
 DLB_EXPORT int dlb_swiglu_fwd(const void* h, void* out, int64_t R, int F, cudaStream_t stream) {
   DLB_REQUIRE(R > 0 && F > 0 && F % 8 == 0, DLB_ERR_SHAPE, "swiglu_fwd: bad shape R=%lld F=%d", (long long)R, F);
-  swiglu_fwd_kernel<<<stream_grid(R * (F / 8), 4), 256, 0, stream>>>((const bf16*)h, (bf16*)out, R, F);
+  swiglu_fwd_kernel<<<stream_grid(R * (F / 8), 1), 256, 0, stream>>>((const bf16*)h, (bf16*)out, R, F);
   dlb_count_launch();
   return dlb_check_launch("swiglu_fwd");
 }
 DLB_EXPORT int dlb_swiglu_bwd(const void* dout, const void* h, void* dh, int64_t R, int F, cudaStream_t stream) {
   DLB_REQUIRE(R > 0 && F > 0 && F % 8 == 0, DLB_ERR_SHAPE, "swiglu_bwd: bad shape R=%lld F=%d", (long long)R, F);
-  swiglu_bwd_kernel<<<stream_grid(R * (F / 8), 2), 256, 0, stream>>>((const bf16*)dout, (const bf16*)h, (bf16*)dh, R, F);
+  swiglu_bwd_kernel<<<stream_grid(R * (F / 8), 1), 256, 0, stream>>>((const bf16*)dout, (const bf16*)h, (bf16*)dh, R, F);
   dlb_count_launch();
   return dlb_check_launch("swiglu_bwd");
 }
