@@ -38,12 +38,12 @@ _SIGNATURES: dict[str, list] = {
     "dlb_gate_residual_bwd": [p, p, p, p, i64, i64, i64, i32, p, p, i64, p, i64, i32, p],
     "dlb_swiglu_fwd": [p, p, i64, i32, p],
     "dlb_swiglu_bwd": [p, p, p, i64, i32, p],
-    # qkv, ld_in, sq, sk, cos, sin, rot_half, pos_idx, pos_offset, tokens_per_sample, hd, out, ld_out, rrms, R, d, eps, stream
-    "dlb_qknorm_rope_fwd": [p, i64, p, p, p, p, i32, p, i32, i32, i32, p, i64, p, i64, i32, f32, p],
-    # dqk, ld_dqk, qkv, ld_in, sq, sk, cos, sin, rot_half, pos_idx, pos_offset, tps, hd, rrms, dqkv, ld_out, dsq, dsk, R, d, stream
-    "dlb_qknorm_rope_bwd": [p, i64, p, i64, p, p, p, p, i32, p, i32, i32, i32, p, p, i64, p, p, i64, i32, p],
-    # pos, n_axes, axis_of_pair, local_of_pair, axis_dim, base, cos, sin, P, rot_half, stream
-    "dlb_rope_table": [p, i32, p, p, p, C.c_double, p, p, i64, i32, p],
+    # qkv, ld_in, sq, sk, cs, rot_half, pos_idx, pos_offset, tokens_per_sample, hd, out, ld_out, rrms, R, d, eps, stream
+    "dlb_qknorm_rope_fwd": [p, i64, p, p, p, i32, p, i32, i32, i32, p, i64, p, i64, i32, f32, p],
+    # dqk, ld_dqk, qkv, ld_in, sq, sk, cs, rot_half, pos_idx, pos_offset, tps, hd, rrms, dqkv, ld_out, dsq, dsk, R, d, stream
+    "dlb_qknorm_rope_bwd": [p, i64, p, i64, p, p, p, i32, p, i32, i32, i32, p, p, i64, p, p, i64, i32, p],
+    # pos, n_axes, axis_of_pair, local_of_pair, axis_dim, base, cos, sin, cs, P, rot_half, stream
+    "dlb_rope_table": [p, i32, p, p, p, C.c_double, p, p, p, i64, i32, p],
     # segs, nseg, lse, kmask, mask_len, B, H, hd, scale, stream
     "dlb_attn_fwd": [p, i32, p, p, i32, i32, i32, i32, f32, p],
     "dlb_attn_fwd_tc": [p, i32, p, p, i32, i32, i32, i32, f32, p],

@@ -218,11 +218,7 @@ class PatchEmbedFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------------------
 # attention sub-layer over 1 or 2 streams (qkv GEMM -> QK-norm + RoPE -> joint attention -> out proj)
 # ---------------------------------------------------------------------------------------------------------
-class RopeCtx:
-    """RoPE tables for one forward: cos/sin [P, R/2] fp32 on device, plus how stream rows map to table rows."""
-
-    def __init__(self, cos: Tensor, sin: Tensor):
-        self.cos, self.sin = cos, sin
+RopeCtx = ops.RopeTable  # RoPE tables for one forward (fp32 cos / sin + the packed bf16x2 table the kernels read)
 
 
 class StreamSpec:
@@ -241,7 +237,7 @@ def attn_fwd(hs: list[Tensor], streams: list[StreamSpec], rope: RopeCtx, B: int,
     qkvs, qks, rrmss, specs = [], [], [], []
     for h, s in zip(hs, streams):
         qkv = ops.gemm(h, wb(s.w_qkv))
-        qk, rrms = ops.qknorm_rope_fwd(qkv, s.sq.detach(), s.sk.detach(), rope.cos, rope.sin, hd, tokens_per_sample=s.len,
+        qk, rrms = ops.qknorm_rope_fwd(qkv, s.sq.detach(), s.sk.detach(), rope, hd, tokens_per_sample=s.len,
                                        pos_offset=s.pos_offset, pos_idx=s.pos_idx)
         qkvs.append(qkv)
         qks.append(qk)
@@ -269,7 +265,7 @@ def attn_bwd(dprojs: list[Tensor | None], streams: list[StreamSpec], rope: RopeC
     dqks = ops.attn_bwd(specs, save["outs"], douts, save["lse"], B, H, hd, hd**-0.5, dqkvs, kmask)
     dhs = []
     for dqk, dqkv, qkv, rrms, h, s in zip(dqks, dqkvs, save["qkvs"], save["rrmss"], save["hs"], streams):
-        ops.qknorm_rope_bwd(dqk, qkv, rrms, s.sq.detach(), s.sk.detach(), rope.cos, rope.sin, hd, dqkv, vgrad(s.sq), vgrad(s.sk),
+        ops.qknorm_rope_bwd(dqk, qkv, rrms, s.sq.detach(), s.sk.detach(), rope, hd, dqkv, vgrad(s.sq), vgrad(s.sk),
                             tokens_per_sample=s.len, pos_offset=s.pos_offset, pos_idx=s.pos_idx)
         _ready(s.sq)
         _ready(s.sk)

@@ -34,9 +34,9 @@ ln_modulate_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, 
                        int rows_per_mod, bf16* __restrict__ y, float* __restrict__ mean_out,
                        float* __restrict__ rstd_out, int64_t R, int d, float eps) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= R) return;
   const int nv = d >> 3;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < R; row += nwarps) {
   const bf16* xr = x + row * d;
   bf16x8 xp[VPL];
 #pragma unroll
@@ -93,6 +93,7 @@ ln_modulate_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, 
       st8(yr + v * 8, pack8(o));
     }
   }
+  }  // row loop
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -111,9 +112,9 @@ ln_modulate_bwd_rows_kernel(const bf16* __restrict__ dy, const bf16* __restrict_
                             const bf16* __restrict__ dres, bf16* __restrict__ dx, bf16* __restrict__ dscale_tok,
                             bf16* __restrict__ dshift_tok, int64_t dtok_ld, int64_t R, int d) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= R) return;
   const int nv = d >> 3;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < R; row += nwarps) {
   const bf16* sc = scale + (row / rows_per_mod) * mod_ld;
   bf16x8 xp[VPL], gp[VPL];
 #pragma unroll
@@ -183,6 +184,7 @@ ln_modulate_bwd_rows_kernel(const bf16* __restrict__ dy, const bf16* __restrict_
       st8(dx + row * d + v * 8, pack8(o));
     }
   }
+  }  // row loop
 }
 
 // grid (col chunks, row chunks, groups); block = one thread per 8-channel vector
@@ -462,7 +464,8 @@ DLB_EXPORT int dlb_ln_modulate_fwd(const void* x, const float* w, const float* b
   DLB_REQUIRE((w == nullptr) == (b == nullptr), DLB_ERR_SHAPE, "ln_modulate_fwd: weight and bias must both be set or null");
   DLB_REQUIRE(rows_per_mod >= 1 && (mean == nullptr) == (rstd == nullptr), DLB_ERR_SHAPE, "ln_modulate_fwd: bad args");
   const int warps = 4;
-  const int grid = (int)((R + warps - 1) / warps);
+  const int64_t grid64 = (R + warps - 1) / warps;
+  const int grid = (int)(grid64 < (int64_t)dlb_num_sms() * 6 ? grid64 : (int64_t)dlb_num_sms() * 6);
   VPL_SWITCH(d, (ln_modulate_fwd_kernel<VPL><<<grid, warps * 32, 0, stream>>>(
                     (const bf16*)x, w, b, (const bf16*)scale, (const bf16*)shift, mod_ld, (int)rows_per_mod, (bf16*)y,
                     mean, rstd, R, d, eps)));
@@ -486,7 +489,8 @@ DLB_EXPORT int dlb_ln_modulate_bwd(const void* dy, const void* x, const float* m
   const int64_t R = groups * rows_per_group;
   const int64_t rows_per_mod = per_token ? 1 : rows_per_group;
   const int warps = 4;
-  const int grid_rows = (int)((R + warps - 1) / warps);
+  const int64_t grid64 = (R + warps - 1) / warps;
+  const int grid_rows = (int)(grid64 < (int64_t)dlb_num_sms() * 5 ? grid64 : (int64_t)dlb_num_sms() * 5);
   if (per_token) {
     VPL_SWITCH(d, (ln_modulate_bwd_rows_kernel<VPL, true><<<grid_rows, warps * 32, 0, stream>>>(
                       (const bf16*)dy, (const bf16*)x, mean, rstd, w, b, (const bf16*)scale, mod_ld, rows_per_mod,

@@ -10,8 +10,8 @@ namespace {
 typedef __nv_bfloat16 bf16;
 
 struct RopeArgs {
-  const float* cos_t;   // [positions, rot_half]
-  const float* sin_t;
+  const uint32_t* cs_t;  // [positions, rot_half] packed bf16x2: low half = cos, high half = sin (the reference casts the
+                         // fp32 tables to the activation dtype before rotating, nn.py:378-379)
   const int32_t* pos_idx;  // optional [R]: table row per token (SPRINT-gathered sequences); else offset + row % tps
   int rot_half;            // rotary pairs per head
   int pos_offset;
@@ -23,66 +23,77 @@ __device__ __forceinline__ int rope_pos(const RopeArgs& ra, int64_t row) {
   return ra.pos_idx ? ra.pos_idx[row] : ra.pos_offset + (int)(row % ra.tokens_per_sample);
 }
 
+__device__ __forceinline__ float2 cs_unpack(uint32_t cs) {  // (cos, sin) as fp32 (exactly the bf16 values)
+  return make_float2(__uint_as_float(cs << 16), __uint_as_float(cs & 0xffff0000u));
+}
+
 template <int VPL>
 __global__ void __launch_bounds__(128, 6)
 qknorm_rope_fwd_kernel(const bf16* __restrict__ qkv, int64_t ld_in, const float* __restrict__ sq,
                        const float* __restrict__ sk, RopeArgs ra, bf16* __restrict__ out, int64_t ld_out,
                        float* __restrict__ rrms_out, int64_t R, int d, float eps) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= R) return;
   const int nv = d >> 3;
-  const int pos = rope_pos(ra, row);
-  const float* cr = ra.cos_t + (int64_t)pos * ra.rot_half;
-  const float* sr = ra.sin_t + (int64_t)pos * ra.rot_half;
-  // q and k rows are fetched together (2 * VPL independent 16-byte loads in flight) and kept packed
-  bf16x8 xp[2][VPL];
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < R; row += nwarps) {
+    const uint32_t* csr = ra.cs_t + (int64_t)rope_pos(ra, row) * ra.rot_half;
+    // q and k rows are fetched together (2 * VPL independent 16-byte loads in flight) and kept packed
+    bf16x8 xp[2][VPL];
 #pragma unroll
-  for (int which = 0; which < 2; ++which)
+    for (int which = 0; which < 2; ++which)
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nv) xp[which][i] = ld8(qkv + row * ld_in + which * d + v * 8);
-    }
-#pragma unroll
-  for (int which = 0; which < 2; ++which) {
-    const float* sc = which ? sk : sq;
-    float ss = 0.f;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      if (lane + 32 * i < nv) {
-        float f[8];
-        unpack8(xp[which][i], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nv) xp[which][i] = ld8(qkv + row * ld_in + which * d + v * 8);
       }
-    }
-    const float rrms = rsqrtf(warp_sum(ss) / d + eps);
-    if (lane == 0 && rrms_out) rrms_out[row * 2 + which] = rrms;
-    bf16* dst = out + row * ld_out + which * d;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nv) {
-        const int c = v * 8;
-        const int cl = c % ra.hd;  // channel inside the head; hd % 8 == 0 keeps a vector inside one head
-        float y[8], scv[8];
-        unpack8(xp[which][i], y);
-        *reinterpret_cast<float4*>(scv) = __ldg(reinterpret_cast<const float4*>(sc + c));
-        *reinterpret_cast<float4*>(scv + 4) = __ldg(reinterpret_cast<const float4*>(sc + c + 4));
+    for (int which = 0; which < 2; ++which) {
+      const float* sc = which ? sk : sq;
+      float ss = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) y[j] = bf16_round(bf16_round(y[j] * rrms) * scv[j]);
+      for (int i = 0; i < VPL; ++i) {
+        if (lane + 32 * i < nv) {
+          float f[8];
+          unpack8(xp[which][i], f);
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) {
-          const int pj = (cl + j) >> 1;
-          if (pj < ra.rot_half) {
-            const float cs = bf16_round(__ldg(cr + pj)), sn = bf16_round(__ldg(sr + pj));
-            const float e = y[j], o = y[j + 1];
-            y[j] = bf16_round(e * cs) - bf16_round(o * sn);
-            y[j + 1] = bf16_round(e * sn) + bf16_round(o * cs);
-          }
+          for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
         }
-        st8(dst + c, pack8(y));
+      }
+      const float rrms = rsqrtf(warp_sum(ss) / d + eps);
+      if (lane == 0 && rrms_out) rrms_out[row * 2 + which] = rrms;
+      bf16* dst = out + row * ld_out + which * d;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nv) {
+          const int c = v * 8;
+          const int cl = c % ra.hd;  // channel inside the head; hd % 8 == 0 keeps a vector inside one head
+          float y[8], scv[8];
+          unpack8(xp[which][i], y);
+          *reinterpret_cast<float4*>(scv) = __ldg(reinterpret_cast<const float4*>(sc + c));
+          *reinterpret_cast<float4*>(scv + 4) = __ldg(reinterpret_cast<const float4*>(sc + c + 4));
+          bf16x8 o;
+#pragma unroll
+          for (int j = 0; j < 8; j += 2) {
+            // bf16(bf16(x * rrms) * scale) on a pair, then the rotation in native bf16x2 arithmetic: every product
+            // and the final add/sub round to bf16 exactly like the reference's bf16 tensor ops
+            float2 xn = unpack_bf16x2(pack_bf16x2(y[j] * rrms, y[j + 1] * rrms));
+            uint32_t yp = pack_bf16x2(xn.x * scv[j], xn.y * scv[j + 1]);
+            const int pj = (cl + j) >> 1;
+            if (pj < ra.rot_half) {
+              const uint32_t cs = __ldg(csr + pj);
+              const uint32_t cc = __byte_perm(cs, cs, 0x1010), sn = __byte_perm(cs, cs, 0x3232);  // (c,c) (s,s)
+              const uint32_t ysw = __byte_perm(yp, yp, 0x1032);                                   // (o, e)
+              __nv_bfloat162 t1 = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&yp), *reinterpret_cast<const __nv_bfloat162*>(&cc));
+              __nv_bfloat162 t2 = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&ysw), *reinterpret_cast<const __nv_bfloat162*>(&sn));
+              uint32_t t2n = *reinterpret_cast<uint32_t*>(&t2) ^ 0x00008000u;  // (-o*s, e*s)
+              __nv_bfloat162 r = __hadd2(t1, *reinterpret_cast<__nv_bfloat162*>(&t2n));
+              yp = *reinterpret_cast<uint32_t*>(&r);
+            }
+            o.u[j >> 1] = yp;
+          }
+          st8(dst + c, o);
+        }
       }
     }
   }
@@ -97,68 +108,67 @@ qknorm_rope_bwd_rows_kernel(const bf16* __restrict__ dqk, int64_t ld_dqk, const 
                             const float* __restrict__ sq, const float* __restrict__ sk, RopeArgs ra,
                             const float* __restrict__ rrms_in, bf16* __restrict__ dqkv, int64_t ld_out, int64_t R, int d) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= R) return;
   const int nv = d >> 3;
-  const int pos = rope_pos(ra, row);
-  const float* cr = ra.cos_t + (int64_t)pos * ra.rot_half;
-  const float* sr = ra.sin_t + (int64_t)pos * ra.rot_half;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < R; row += nwarps) {
+    const uint32_t* csr = ra.cs_t + (int64_t)rope_pos(ra, row) * ra.rot_half;
 #pragma unroll 1
-  for (int which = 0; which < 2; ++which) {
-    const float* sc = which ? sk : sq;
-    const bf16* src = qkv + row * ld_in + which * d;
-    const bf16* gsrc = dqk + row * ld_dqk + which * d;
-    const float rrms = rrms_in[row * 2 + which];
-    bf16x8 xp[VPL], gp[VPL];
+    for (int which = 0; which < 2; ++which) {
+      const float* sc = which ? sk : sq;
+      const bf16* src = qkv + row * ld_in + which * d;
+      const bf16* gsrc = dqk + row * ld_dqk + which * d;
+      const float rrms = rrms_in[row * 2 + which];
+      bf16x8 xp[VPL], gp[VPL];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nv) { xp[i] = ld8(src + v * 8); gp[i] = ld8(gsrc + v * 8); }
-    }
-    // grad wrt the normalised value: transpose of the rotation, times the learnable scale
-    auto grad_norm = [&](int i, float* gn) {
-      const int c = (lane + 32 * i) * 8;
-      const int cl = c % ra.hd;
-      float scv[8];
-      unpack8(gp[i], gn);
-      *reinterpret_cast<float4*>(scv) = __ldg(reinterpret_cast<const float4*>(sc + c));
-      *reinterpret_cast<float4*>(scv + 4) = __ldg(reinterpret_cast<const float4*>(sc + c + 4));
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nv) { xp[i] = ld8(src + v * 8); gp[i] = ld8(gsrc + v * 8); }
+      }
+      // grad wrt the normalised value: transpose of the rotation, times the learnable scale
+      auto grad_norm = [&](int i, float* gn) {
+        const int c = (lane + 32 * i) * 8;
+        const int cl = c % ra.hd;
+        float scv[8];
+        unpack8(gp[i], gn);
+        *reinterpret_cast<float4*>(scv) = __ldg(reinterpret_cast<const float4*>(sc + c));
+        *reinterpret_cast<float4*>(scv + 4) = __ldg(reinterpret_cast<const float4*>(sc + c + 4));
 #pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        const int pj = (cl + j) >> 1;
-        if (pj < ra.rot_half) {
-          const float cs = bf16_round(__ldg(cr + pj)), sn = bf16_round(__ldg(sr + pj));
-          const float ge = gn[j], go = gn[j + 1];
-          gn[j] = ge * cs + go * sn;
-          gn[j + 1] = -ge * sn + go * cs;
+        for (int j = 0; j < 8; j += 2) {
+          const int pj = (cl + j) >> 1;
+          if (pj < ra.rot_half) {
+            const float2 cs = cs_unpack(__ldg(csr + pj));
+            const float ge = gn[j], go = gn[j + 1];
+            gn[j] = ge * cs.x + go * cs.y;
+            gn[j + 1] = go * cs.x - ge * cs.y;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gn[j] *= scv[j];
+      };
+      float dot = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        if (lane + 32 * i < nv) {
+          float xn[8], gn[8];
+          unpack8(xp[i], xn);
+          grad_norm(i, gn);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dot += gn[j] * (xn[j] * rrms);
         }
       }
+      dot = warp_sum(dot) / d;
+      bf16* dst = dqkv + row * ld_out + which * d;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) gn[j] *= scv[j];
-    };
-    float dot = 0.f;
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nv) {
+          float xn[8], gn[8], o[8];
+          unpack8(xp[i], xn);
+          grad_norm(i, gn);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      if (lane + 32 * i < nv) {
-        float xn[8], gn[8];
-        unpack8(xp[i], xn);
-        grad_norm(i, gn);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dot += gn[j] * (xn[j] * rrms);
-      }
-    }
-    dot = warp_sum(dot) / d;
-    bf16* dst = dqkv + row * ld_out + which * d;
-#pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nv) {
-        float xn[8], gn[8], o[8];
-        unpack8(xp[i], xn);
-        grad_norm(i, gn);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rrms * (gn[j] - xn[j] * rrms * dot);
-        st8(dst + v * 8, pack8(o));
+          for (int j = 0; j < 8; ++j) o[j] = rrms * (gn[j] - xn[j] * rrms * dot);
+          st8(dst + v * 8, pack8(o));
+        }
       }
     }
   }
@@ -199,16 +209,15 @@ qknorm_rope_bwd_cols_kernel(const bf16* __restrict__ dqk, int64_t ld_dqk, const 
         float xq[8], g[8];
         unpack8(xa[u], xq);
         unpack8(ga[u], g);
-        const float* cr = ra.cos_t + (int64_t)ps[u] * ra.rot_half;
-        const float* sr = ra.sin_t + (int64_t)ps[u] * ra.rot_half;
+        const uint32_t* csr = ra.cs_t + (int64_t)ps[u] * ra.rot_half;
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
           const int pj = (cl + j) >> 1;
           if (pj < ra.rot_half) {
-            const float cs = bf16_round(__ldg(cr + pj)), sn = bf16_round(__ldg(sr + pj));
+            const float2 cs = cs_unpack(__ldg(csr + pj));
             const float ge = g[j], go = g[j + 1];
-            g[j] = ge * cs + go * sn;
-            g[j + 1] = -ge * sn + go * cs;
+            g[j] = ge * cs.x + go * cs.y;
+            g[j + 1] = go * cs.x - ge * cs.y;
           }
         }
 #pragma unroll
@@ -244,16 +253,17 @@ static int check_rope(const char* who, int d, int hd, int rot_half, int tokens_p
 }
 
 // qkv: [R, >=2d] packed (q | k | ...) with row stride ld_in; out: [R, 2d] rotated (q | k) with row stride ld_out.
-DLB_EXPORT int dlb_qknorm_rope_fwd(const void* qkv, int64_t ld_in, const float* sq, const float* sk, const float* cos_t,
-                                   const float* sin_t, int rot_half, const int32_t* pos_idx, int pos_offset,
+DLB_EXPORT int dlb_qknorm_rope_fwd(const void* qkv, int64_t ld_in, const float* sq, const float* sk, const uint32_t* cs_t,
+                                   int rot_half, const int32_t* pos_idx, int pos_offset,
                                    int tokens_per_sample, int hd, void* out, int64_t ld_out, float* rrms, int64_t R,
                                    int d, float eps, cudaStream_t stream) {
   int rc = check_rope("qknorm_rope_fwd", d, hd, rot_half, tokens_per_sample, pos_idx);
   if (rc) return rc;
   DLB_REQUIRE(R > 0 && ld_in % 8 == 0 && ld_out % 8 == 0, DLB_ERR_SHAPE, "qknorm_rope_fwd: bad strides");
-  RopeArgs ra{cos_t, sin_t, pos_idx, rot_half, pos_offset, tokens_per_sample > 0 ? tokens_per_sample : 1, hd};
+  RopeArgs ra{cs_t, pos_idx, rot_half, pos_offset, tokens_per_sample > 0 ? tokens_per_sample : 1, hd};
   const int warps = 4;
-  const int grid = (int)((R + warps - 1) / warps);
+  int64_t grid64 = (R + warps - 1) / warps;
+  const int grid = (int)(grid64 < (int64_t)dlb_num_sms() * 6 ? grid64 : (int64_t)dlb_num_sms() * 6);
   VPL_SWITCH(d, (qknorm_rope_fwd_kernel<VPL><<<grid, warps * 32, 0, stream>>>((const bf16*)qkv, ld_in, sq, sk, ra,
                                                                              (bf16*)out, ld_out, rrms, R, d, eps)));
   dlb_count_launch();
@@ -261,7 +271,7 @@ DLB_EXPORT int dlb_qknorm_rope_fwd(const void* qkv, int64_t ld_in, const float* 
 }
 
 DLB_EXPORT int dlb_qknorm_rope_bwd(const void* dqk, int64_t ld_dqk, const void* qkv, int64_t ld_in, const float* sq,
-                                   const float* sk, const float* cos_t, const float* sin_t, int rot_half,
+                                   const float* sk, const uint32_t* cs_t, int rot_half,
                                    const int32_t* pos_idx, int pos_offset, int tokens_per_sample, int hd,
                                    const float* rrms, void* dqkv, int64_t ld_out, float* dsq, float* dsk, int64_t R,
                                    int d, cudaStream_t stream) {
@@ -269,9 +279,10 @@ DLB_EXPORT int dlb_qknorm_rope_bwd(const void* dqk, int64_t ld_dqk, const void* 
   if (rc) return rc;
   DLB_REQUIRE(R > 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && ld_dqk % 8 == 0, DLB_ERR_SHAPE, "qknorm_rope_bwd: bad strides");
   DLB_REQUIRE(rrms != nullptr, DLB_ERR_SHAPE, "qknorm_rope_bwd: the rrms buffer saved by the forward pass is required");
-  RopeArgs ra{cos_t, sin_t, pos_idx, rot_half, pos_offset, tokens_per_sample > 0 ? tokens_per_sample : 1, hd};
+  RopeArgs ra{cs_t, pos_idx, rot_half, pos_offset, tokens_per_sample > 0 ? tokens_per_sample : 1, hd};
   const int warps = 4;
-  const int grid = (int)((R + warps - 1) / warps);
+  int64_t grid64 = (R + warps - 1) / warps;
+  const int grid = (int)(grid64 < (int64_t)dlb_num_sms() * 5 ? grid64 : (int64_t)dlb_num_sms() * 5);
   VPL_SWITCH(d, (qknorm_rope_bwd_rows_kernel<VPL><<<grid, warps * 32, 0, stream>>>(
                     (const bf16*)dqk, ld_dqk, (const bf16*)qkv, ld_in, sq, sk, ra, rrms, (bf16*)dqkv, ld_out, R, d)));
   dlb_count_launch();
@@ -295,8 +306,8 @@ DLB_EXPORT int dlb_qknorm_rope_bwd(const void* dqk, int64_t ld_dqk, const void* 
 // cos/sin table of get_cos_sin_ndim_grid (nn.py:262-307): fp64 angles, stored fp32. pos: [P, n_axes] int32.
 __global__ void rope_table_kernel(const int32_t* __restrict__ pos, int n_axes, const int32_t* __restrict__ axis_of_pair,
                                   const int32_t* __restrict__ local_of_pair, const int32_t* __restrict__ axis_dim,
-                                  double base, float* __restrict__ cos_t, float* __restrict__ sin_t, int64_t P,
-                                  int rot_half) {
+                                  double base, float* __restrict__ cos_t, float* __restrict__ sin_t,
+                                  uint32_t* __restrict__ cs_t, int64_t P, int rot_half) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P * rot_half) return;
   const int64_t p = i / rot_half;
@@ -304,17 +315,18 @@ __global__ void rope_table_kernel(const int32_t* __restrict__ pos, int n_axes, c
   const int ax = axis_of_pair[j];
   const double freq = 1.0 / pow(base, (double)(2 * local_of_pair[j]) / (double)axis_dim[ax]);
   const double ang = (double)pos[p * n_axes + ax] * freq;
-  cos_t[i] = (float)cos(ang);
-  sin_t[i] = (float)sin(ang);
+  const float c = (float)cos(ang), sn = (float)sin(ang);
+  if (cos_t) { cos_t[i] = c; sin_t[i] = sn; }
+  if (cs_t) cs_t[i] = pack_bf16x2(c, sn);
 }
 
 DLB_EXPORT int dlb_rope_table(const int32_t* pos, int n_axes, const int32_t* axis_of_pair, const int32_t* local_of_pair,
-                              const int32_t* axis_dim, double base, float* cos_t, float* sin_t, int64_t P, int rot_half,
-                              cudaStream_t stream) {
+                              const int32_t* axis_dim, double base, float* cos_t, float* sin_t, uint32_t* cs_t, int64_t P,
+                              int rot_half, cudaStream_t stream) {
   DLB_REQUIRE(P > 0 && rot_half > 0 && n_axes > 0, DLB_ERR_SHAPE, "rope_table: bad shape");
   const int64_t total = P * rot_half;
   rope_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(pos, n_axes, axis_of_pair, local_of_pair,
-                                                                        axis_dim, base, cos_t, sin_t, P, rot_half);
+                                                                        axis_dim, base, cos_t, sin_t, cs_t, P, rot_half);
   dlb_count_launch();
   return dlb_check_launch("rope_table");
 }

@@ -228,7 +228,6 @@ def rope_for(device: torch.device, L_text: int, hp: int, wp: int, axes_dim: list
             pos = torch.cat([text, img], 0)
         else:
             pos = torch.stack([hh.reshape(-1), ww.reshape(-1)], -1)
-        cos, sin = ops.rope_table(pos.to(torch.int32).to(device).contiguous(), list(axes_dim), float(base))
-        ctx = K.RopeCtx(cos, sin)
+        ctx = ops.rope_table(pos.to(torch.int32).to(device).contiguous(), list(axes_dim), float(base))
         _rope_cache[key] = ctx
     return ctx

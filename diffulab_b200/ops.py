@@ -272,8 +272,18 @@ def swiglu_bwd(dout: Tensor, h: Tensor) -> Tensor:
 # ---------------------------------------------------------------------------------------------------------
 # RoPE table, QK-norm + RoPE
 # ---------------------------------------------------------------------------------------------------------
-def rope_table(pos_ids: Tensor, axes_dim: list[int], base: float) -> tuple[Tensor, Tensor]:
-    """pos_ids: int32 [P, n_axes] on device -> cos, sin fp32 [P, sum(axes)/2] (nn.py:262-307)."""
+class RopeTable:
+    """cos / sin fp32 [P, R/2] (get_cos_sin_ndim_grid, nn.py:262-307) + the packed bf16x2 table the kernels read."""
+
+    def __init__(self, cos: Tensor, sin: Tensor, cs: Tensor):
+        self.cos, self.sin, self.cs = cos, sin, cs
+
+    def rows(self, idx: Tensor) -> "RopeTable":
+        return RopeTable(self.cos[idx].contiguous(), self.sin[idx].contiguous(), self.cs[idx].contiguous())
+
+
+def rope_table(pos_ids: Tensor, axes_dim: list[int], base: float) -> RopeTable:
+    """pos_ids: int32 [P, n_axes] on device."""
     _req(pos_ids, torch.int32, "pos_ids")
     P, n_axes = pos_ids.shape
     axis_of, local_of = [], []
@@ -288,12 +298,13 @@ def rope_table(pos_ids: Tensor, axes_dim: list[int], base: float) -> tuple[Tenso
     ad = torch.tensor(axes_dim, dtype=torch.int32, device=dev)
     cos = torch.empty(P, rot_half, device=dev, dtype=F32)
     sin = torch.empty(P, rot_half, device=dev, dtype=F32)
+    cs = torch.empty(P, rot_half, device=dev, dtype=torch.int32)
     _lib_call("dlb_rope_table", pos_ids.data_ptr(), n_axes, ax.data_ptr(), lo.data_ptr(), ad.data_ptr(), float(base),
-              cos.data_ptr(), sin.data_ptr(), P, rot_half, _stream())
-    return cos, sin
+              cos.data_ptr(), sin.data_ptr(), cs.data_ptr(), P, rot_half, _stream())
+    return RopeTable(cos, sin, cs)
 
 
-def qknorm_rope_fwd(qkv: Tensor, sq: Tensor, sk: Tensor, cos: Tensor, sin: Tensor, hd: int, *, tokens_per_sample: int,
+def qknorm_rope_fwd(qkv: Tensor, sq: Tensor, sk: Tensor, rope: RopeTable, hd: int, *, tokens_per_sample: int,
                     pos_offset: int = 0, pos_idx: Tensor | None = None, eps: float = 1e-6) -> tuple[Tensor, Tensor]:
     """qkv: [R, 3d] packed projection -> ([R, 2d] normalised + rotated (q | k), rrms fp32 [R, 2] for the backward)."""
     _req(qkv, BF16, "qkv")
@@ -301,20 +312,20 @@ def qknorm_rope_fwd(qkv: Tensor, sq: Tensor, sk: Tensor, cos: Tensor, sin: Tenso
     d = qkv.shape[-1] // 3
     out = torch.empty(R, 2 * d, device=qkv.device, dtype=BF16)
     rrms = torch.empty(R, 2, device=qkv.device, dtype=F32)
-    _lib_call("dlb_qknorm_rope_fwd", qkv.data_ptr(), 3 * d, sq.data_ptr(), sk.data_ptr(), cos.data_ptr(), sin.data_ptr(),
-              cos.shape[-1], _ptr(pos_idx), pos_offset, tokens_per_sample, hd, out.data_ptr(), 2 * d, rrms.data_ptr(), R, d, eps,
+    _lib_call("dlb_qknorm_rope_fwd", qkv.data_ptr(), 3 * d, sq.data_ptr(), sk.data_ptr(), rope.cs.data_ptr(),
+              rope.cs.shape[-1], _ptr(pos_idx), pos_offset, tokens_per_sample, hd, out.data_ptr(), 2 * d, rrms.data_ptr(), R, d, eps,
               _stream())
     return out, rrms
 
 
-def qknorm_rope_bwd(dqk: Tensor, qkv: Tensor, rrms: Tensor, sq: Tensor, sk: Tensor, cos: Tensor, sin: Tensor, hd: int,
+def qknorm_rope_bwd(dqk: Tensor, qkv: Tensor, rrms: Tensor, sq: Tensor, sk: Tensor, rope: RopeTable, hd: int,
                     dqkv: Tensor, dsq: Tensor | None, dsk: Tensor | None, *, tokens_per_sample: int, pos_offset: int = 0,
                     pos_idx: Tensor | None = None) -> None:
     """Writes dq, dk into dqkv[:, :2d] (dv at [:, 2d:] is produced by attention bwd); accumulates dsq/dsk (fp32)."""
     R = _rows(qkv)
     d = qkv.shape[-1] // 3
     _lib_call("dlb_qknorm_rope_bwd", dqk.data_ptr(), 2 * d, qkv.data_ptr(), 3 * d, sq.data_ptr(), sk.data_ptr(),
-              cos.data_ptr(), sin.data_ptr(), cos.shape[-1], _ptr(pos_idx), pos_offset, tokens_per_sample, hd,
+              rope.cs.data_ptr(), rope.cs.shape[-1], _ptr(pos_idx), pos_offset, tokens_per_sample, hd,
               rrms.data_ptr(), dqkv.data_ptr(), 3 * d, _ptr(dsq), _ptr(dsk), R, d, _stream())
 
 

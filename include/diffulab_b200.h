@@ -83,21 +83,24 @@ int dlb_swiglu_bwd(const void* dout, const void* h, void* dh, int64_t R, int F, 
 
 /* ---- QK-RMSNorm over the full inner dim + N-D interleaved-pair RoPE (nn.py:262-307, 331-400, 423-475) ------
  * qkv bf16 [R, >=2d] packed (q | k | ...), out bf16 [R, 2d] (q | k) normalised, scaled and rotated.
- * cos/sin fp32 [P, rot_half]; table row of token r = pos_idx[r] if given else pos_offset + r % tokens_per_sample.
+ * cs_t uint32 [P, rot_half]: packed bf16x2 (low = cos, high = sin) written by dlb_rope_table (the reference casts
+ * its fp32 tables to the activation dtype); table row of token r = pos_idx[r] if given else
+ * pos_offset + r % tokens_per_sample.
  * rrms fp32 [R,2] (reciprocal RMS of q and k rows) is written by the forward and consumed by the backward;
  * dsq/dsk (fp32 [d], accumulated) may both be NULL when the scales are frozen. */
-int dlb_qknorm_rope_fwd(const void* qkv, int64_t ld_in, const float* sq, const float* sk, const float* cos_t,
-                        const float* sin_t, int rot_half, const int32_t* pos_idx, int pos_offset,
+int dlb_qknorm_rope_fwd(const void* qkv, int64_t ld_in, const float* sq, const float* sk, const uint32_t* cs_t,
+                        int rot_half, const int32_t* pos_idx, int pos_offset,
                         int tokens_per_sample, int hd, void* out, int64_t ld_out, float* rrms, int64_t R, int d,
                         float eps, dlb_stream_t stream);
 int dlb_qknorm_rope_bwd(const void* dqk, int64_t ld_dqk, const void* qkv, int64_t ld_in, const float* sq,
-                        const float* sk, const float* cos_t, const float* sin_t, int rot_half, const int32_t* pos_idx,
+                        const float* sk, const uint32_t* cs_t, int rot_half, const int32_t* pos_idx,
                         int pos_offset, int tokens_per_sample, int hd, const float* rrms, void* dqkv, int64_t ld_out,
                         float* dsq, float* dsk, int64_t R, int d, dlb_stream_t stream);
-/* cos/sin tables of get_cos_sin_ndim_grid (fp64 angles -> fp32). pos int32 [P, n_axes]. */
+/* cos/sin tables of get_cos_sin_ndim_grid (fp64 angles -> fp32) and/or the packed bf16x2 table; each output optional
+ * (cos_t and sin_t together). pos int32 [P, n_axes]. */
 int dlb_rope_table(const int32_t* pos, int n_axes, const int32_t* axis_of_pair, const int32_t* local_of_pair,
-                   const int32_t* axis_dim, double base, float* cos_t, float* sin_t, int64_t P, int rot_half,
-                   dlb_stream_t stream);
+                   const int32_t* axis_dim, double base, float* cos_t, float* sin_t, uint32_t* cs_t, int64_t P,
+                   int rot_half, dlb_stream_t stream);
 
 /* ---- joint attention over 1 or 2 segments (text rows first, then image rows) ------------------------------
  * softmax(q k^T * scale + key_padding_mask) v per (sample, head); replaces F.scaled_dot_product_attention and the

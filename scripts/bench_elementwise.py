@@ -45,9 +45,9 @@ dmod = torch.zeros(B, 6 * d, device="cuda")
 dw, db = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
 qkv = rnd(R, 3 * d)
 pos = torch.stack([torch.arange(N) // 16, torch.arange(N) % 16], -1).int().cuda()
-cos, sin = ops.rope_table(pos, [36, 36], 10000.0)
+rope = ops.rope_table(pos, [36, 36], 10000.0)
 sq, sk = torch.ones(d, device="cuda"), torch.ones(d, device="cuda")
-qk, rrms = ops.qknorm_rope_fwd(qkv, sq, sk, cos, sin, hd, tokens_per_sample=N)
+qk, rrms = ops.qknorm_rope_fwd(qkv, sq, sk, rope, hd, tokens_per_sample=N)
 dqk, dqkv = rnd(R, 2 * d), torch.empty(R, 3 * d, device="cuda", dtype=BF)
 u, ds = rnd(R, 8 * d), rnd(R, 4 * d)
 n_par = 823_400_000 // 8  # an eighth of the model is enough to saturate
@@ -62,8 +62,8 @@ cases = [
     ("gate_residual_bwd", 4 * T * 2, lambda: ops.gate_residual_bwd(dy, x, None, mod[:, 2 * d:3 * d], dmod[:, 2 * d:3 * d])),
     ("swiglu_fwd", 12 * T * 2, lambda: ops.swiglu_fwd(u)),
     ("swiglu_bwd", 20 * T * 2, lambda: ops.swiglu_bwd(ds, u)),
-    ("qknorm_rope_fwd", 4 * T * 2, lambda: ops.qknorm_rope_fwd(qkv, sq, sk, cos, sin, hd, tokens_per_sample=N)),
-    ("qknorm_rope_bwd", 10 * T * 2, lambda: ops.qknorm_rope_bwd(dqk, qkv, rrms, sq, sk, cos, sin, hd, dqkv, dw, db, tokens_per_sample=N)),
+    ("qknorm_rope_fwd", 4 * T * 2, lambda: ops.qknorm_rope_fwd(qkv, sq, sk, rope, hd, tokens_per_sample=N)),
+    ("qknorm_rope_bwd", 10 * T * 2, lambda: ops.qknorm_rope_bwd(dqk, qkv, rrms, sq, sk, rope, hd, dqkv, dw, db, tokens_per_sample=N)),
     ("adamw_step", 30 * n_par, lambda: ops.adamw_step(p32, g32, m32, v32, shadow, lr=1e-4, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.01, step=3)),
 ]
 for name, nbytes, fn in cases:

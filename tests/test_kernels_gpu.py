@@ -169,13 +169,15 @@ def test_qknorm_rope(gen, B, S, H, hd, axes):
     d = H * hd
     n_ax = len(axes)
     pos = torch.stack([torch.randint(0, 17, (S,), device="cuda", generator=gen) for _ in range(n_ax)], -1).int()
-    cos, sin = ops.rope_table(pos, axes, 10000.0)
+    rope = ops.rope_table(pos, axes, 10000.0)
     cr, sr_ = ref_rope_tables(pos, axes, 10000.0)
-    assert (cos - cr).abs().max().item() < 2e-6 and (sin - sr_).abs().max().item() < 2e-6
+    assert (rope.cos - cr).abs().max().item() < 2e-6 and (rope.sin - sr_).abs().max().item() < 2e-6
+    packed = torch.stack([rope.cos.to(BF), rope.sin.to(BF)], -1).view(torch.int32).squeeze(-1)
+    assert torch.equal(rope.cs, packed)
     qkv = mk(gen, B * S, 3 * d)
     sq = 1 + 0.2 * torch.randn(d, device="cuda", generator=gen)
     sk = 1 + 0.2 * torch.randn(d, device="cuda", generator=gen)
-    out, rrms = ops.qknorm_rope_fwd(qkv, sq, sk, cos, sin, hd, tokens_per_sample=S)
+    out, rrms = ops.qknorm_rope_fwd(qkv, sq, sk, rope, hd, tokens_per_sample=S)
     x = qkv.float().view(B, S, 3 * d).requires_grad_(True)
     sqr, skr = sq.clone().requires_grad_(True), sk.clone().requires_grad_(True)
     cb, sb = cr.to(BF).float(), sr_.to(BF).float()  # the reference casts cos/sin to the activation dtype
@@ -187,7 +189,7 @@ def test_qknorm_rope(gen, B, S, H, hd, axes):
     ref.backward(dqk.float())
     dqkv = torch.zeros(B * S, 3 * d, device="cuda", dtype=BF)
     dsq, dsk = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
-    ops.qknorm_rope_bwd(dqk, qkv, rrms, sq, sk, cos, sin, hd, dqkv, dsq, dsk, tokens_per_sample=S)
+    ops.qknorm_rope_bwd(dqk, qkv, rrms, sq, sk, rope, hd, dqkv, dsq, dsk, tokens_per_sample=S)
     g = x.grad.view(B * S, 3 * d)
     assert rel_l2(dqkv[:, : 2 * d], g[:, : 2 * d]) < 1e-2
     assert dqkv[:, 2 * d :].abs().max().item() == 0.0
@@ -201,14 +203,13 @@ def test_qknorm_rope_pos_idx(gen):
     B, S, H, hd, k = 2, 32, 4, 32, 8
     d = H * hd
     pos = torch.stack([torch.arange(S, device="cuda") // 8, torch.arange(S, device="cuda") % 8], -1).int()
-    cos, sin = ops.rope_table(pos, [16, 16], 10000.0)
+    rope = ops.rope_table(pos, [16, 16], 10000.0)
     kept = torch.stack([torch.randperm(S, device="cuda", generator=gen)[:k].sort().values for _ in range(B)]).int()
     qkv = mk(gen, B * k, 3 * d)
     ones = torch.ones(d, device="cuda")
-    a, _ = ops.qknorm_rope_fwd(qkv, ones, ones, cos, sin, hd, tokens_per_sample=k, pos_idx=kept.reshape(-1).contiguous())
+    a, _ = ops.qknorm_rope_fwd(qkv, ones, ones, rope, hd, tokens_per_sample=k, pos_idx=kept.reshape(-1).contiguous())
     for b in range(B):
-        cb, sb = cos[kept[b].long()], sin[kept[b].long()]
-        single, _ = ops.qknorm_rope_fwd(qkv[b * k : (b + 1) * k].contiguous(), ones, ones, cb.contiguous(), sb.contiguous(), hd, tokens_per_sample=k)
+        single, _ = ops.qknorm_rope_fwd(qkv[b * k : (b + 1) * k].contiguous(), ones, ones, rope.rows(kept[b].long()), hd, tokens_per_sample=k)
         assert torch.equal(a[b * k : (b + 1) * k], single)
 
 
