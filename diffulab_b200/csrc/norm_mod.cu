@@ -27,70 +27,70 @@ __device__ __forceinline__ void ldf8(const float* p, float* f) {
 // ---------------------------------------------------------------------------------------------------------
 // LayerNorm (+affine) + modulate forward
 // ---------------------------------------------------------------------------------------------------------
-// (1 + scale) evaluated in bf16 like the reference (`1 + scale` on a bf16 tensor), two channels per HADD2
-__device__ __forceinline__ float2 one_plus_bf16x2(uint32_t s2) {
-  const uint32_t one2 = 0x3f803f80u;
-  __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&s2), *reinterpret_cast<const __nv_bfloat162*>(&one2));
-  return unpack_bf16x2(*reinterpret_cast<uint32_t*>(&r));
-}
-
 template <int VPL>
-__global__ void __launch_bounds__(128, 5)
+__global__ void __launch_bounds__(128, 6)
 ln_modulate_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                        const bf16* __restrict__ scale, const bf16* __restrict__ shift, int64_t mod_ld,
                        int rows_per_mod, bf16* __restrict__ y, float* __restrict__ mean_out,
                        float* __restrict__ rstd_out, int64_t R, int d, float eps) {
   const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
   const int nv = d >> 3;
-  const float inv_d = 1.f / d;
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < R; row += nwarps) {
-    const bf16* xr = x + row * d;
-    float xf[VPL][8];
-    float sum = 0.f;
+  const bf16* xr = x + row * d;
+  bf16x8 xp[VPL];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nv) {
-        unpack8(ld8(xr + v * 8), xf[i]);
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nv) xp[i] = ld8(xr + v * 8);
+  }
+  float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sum += xf[i][j];
-      }
+  for (int i = 0; i < VPL; ++i) {
+    if (lane + 32 * i < nv) {
+      float f[8];
+      unpack8(xp[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += f[j];
     }
-    const float mean = warp_sum(sum) * inv_d;
-    float sq = 0.f;
+  }
+  const float mean = warp_sum(sum) / d;
+  float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      if (lane + 32 * i < nv) {
+  for (int i = 0; i < VPL; ++i) {
+    if (lane + 32 * i < nv) {
+      float f[8];
+      unpack8(xp[i], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const float t = xf[i][j] - mean; sq = fmaf(t, t, sq); }
-      }
+      for (int j = 0; j < 8; ++j) { const float t = f[j] - mean; sq += t * t; }
     }
-    const float rstd = rsqrtf(warp_sum(sq) * inv_d + eps);
-    const float nmr = -mean * rstd;
-    if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
-    const int64_t mrow = row / rows_per_mod;
-    const bf16* sc = scale + mrow * mod_ld;
-    const bf16* sh = shift + mrow * mod_ld;
-    bf16* yr = y + row * d;
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / d + eps);
+  if (lane == 0 && mean_out) { mean_out[row] = mean; rstd_out[row] = rstd; }
+  const int64_t mrow = row / rows_per_mod;
+  const bf16* sc = scale + mrow * mod_ld;
+  const bf16* sh = shift + mrow * mod_ld;
+  bf16* yr = y + row * d;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nv) {
-        const bf16x8 sp = ld8(sc + v * 8), tp = ld8(sh + v * 8);
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nv) {
+      float f[8], s[8], t[8], o[8];
+      unpack8(xp[i], f);
+      unpack8(ld8(sc + v * 8), s);
+      unpack8(ld8(sh + v * 8), t);
+      // reference: `1 + scale` is evaluated in bf16 before meeting the fp32 LayerNorm output
+      if (w) {
         float wv[8], bv[8];
-        if (w) { ldf8(w + v * 8, wv); ldf8(b + v * 8, bv); }
-        bf16x8 o;
+        ldf8(w + v * 8, wv);
+        ldf8(b + v * 8, bv);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 os = one_plus_bf16x2(sp.u[j]);
-          const float2 tt = unpack_bf16x2(tp.u[j]);
-          float u0 = fmaf(xf[i][2 * j], rstd, nmr), u1 = fmaf(xf[i][2 * j + 1], rstd, nmr);
-          if (w) { u0 = fmaf(u0, wv[2 * j], bv[2 * j]); u1 = fmaf(u1, wv[2 * j + 1], bv[2 * j + 1]); }
-          o.u[j] = pack_bf16x2(fmaf(u0, os.x, tt.x), fmaf(u1, os.y, tt.y));
-        }
-        st8(yr + v * 8, o);
+        for (int j = 0; j < 8; ++j) o[j] = ((f[j] - mean) * rstd * wv[j] + bv[j]) * bf16_round(1.f + s[j]) + t[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean) * rstd * bf16_round(1.f + s[j]) + t[j];
       }
+      st8(yr + v * 8, pack8(o));
     }
   }
 }
@@ -104,80 +104,83 @@ ln_modulate_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, 
 //      db += sum_g (1+s_g) S1_g.            ("LN backward algebra")
 // ---------------------------------------------------------------------------------------------------------
 template <int VPL, bool PER_TOKEN>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, 5)
 ln_modulate_bwd_rows_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean_in,
                             const float* __restrict__ rstd_in, const float* __restrict__ w, const float* __restrict__ b,
                             const bf16* __restrict__ scale, int64_t mod_ld, int64_t rows_per_mod,
                             const bf16* __restrict__ dres, bf16* __restrict__ dx, bf16* __restrict__ dscale_tok,
                             bf16* __restrict__ dshift_tok, int64_t dtok_ld, int64_t R, int d) {
   const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= R) return;
   const int nv = d >> 3;
-  const float inv_d = 1.f / d;
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < R; row += nwarps) {
-    const bf16* sc = scale + (row / rows_per_mod) * mod_ld;
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    const float nmr = -mean * rstd;
-    float xh[VPL][8], gq[VPL][8];  // normalised input, gradient wrt it (before the mean corrections)
-    float m1 = 0.f, m2 = 0.f;
+  const bf16* sc = scale + (row / rows_per_mod) * mod_ld;
+  bf16x8 xp[VPL], gp[VPL];
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nv) {
-        const bf16x8 gp = ld8(dy + row * d + v * 8), sp = ld8(sc + v * 8);
-        unpack8(ld8(x + row * d + v * 8), xh[i]);
-        float wv[8];
-        if (w) ldf8(w + v * 8, wv);
-        float ds_tok[8];
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nv) {
+      xp[i] = ld8(x + row * d + v * 8);
+      gp[i] = ld8(dy + row * d + v * 8);
+    }
+  }
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 os = one_plus_bf16x2(sp.u[j]);
-          const float2 g2 = unpack_bf16x2(gp.u[j]);
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nv) {
+      float xf[8], g[8], s[8], wv[8];
+      unpack8(xp[i], xf);
+      unpack8(gp[i], g);
+      unpack8(ld8(sc + v * 8), s);
+      if (w) ldf8(w + v * 8, wv);
+      float ds_tok[8];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int e = 2 * j + h;
-            const float g = h ? g2.y : g2.x;
-            xh[i][e] = fmaf(xh[i][e], rstd, nmr);
-            float q = g * (h ? os.y : os.x);
-            if (w) q *= wv[e];
-            gq[i][e] = q;
-            m1 += q;
-            m2 = fmaf(q, xh[i][e], m2);
-            if (PER_TOKEN) ds_tok[e] = g * (w ? fmaf(xh[i][e], wv[e], __ldg(b + v * 8 + e)) : xh[i][e]);
-          }
-        }
-        if (PER_TOKEN) {
-          st8(dscale_tok + row * dtok_ld + v * 8, pack8(ds_tok));
-          st8(dshift_tok + row * dtok_ld + v * 8, gp);
-        }
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xf[j] - mean) * rstd;
+        float gq = g[j] * bf16_round(1.f + s[j]);  // grad wrt the affine LayerNorm output u
+        if (w) gq *= wv[j];
+        m1 += gq;
+        m2 += gq * xh;
+        if (PER_TOKEN) ds_tok[j] = g[j] * (w ? xh * wv[j] + __ldg(b + v * 8 + j) : xh);
+      }
+      if (PER_TOKEN) {
+        st8(dscale_tok + row * dtok_ld + v * 8, pack8(ds_tok));
+        st8(dshift_tok + row * dtok_ld + v * 8, gp[i]);
       }
     }
-    const float m1r = warp_sum(m1) * inv_d * rstd;
-    const float m2r = warp_sum(m2) * inv_d * rstd;
+  }
+  bf16x8 rp[VPL];  // residual-branch gradient: fetched while the row statistics are being reduced
+  if (dres) {
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const int v = lane + 32 * i;
-      if (v < nv) {
-        bf16x8 o;
-        if (dres) {
-          const bf16x8 rp = ld8(dres + row * d + v * 8);
+      if (v < nv) rp[i] = ld8(dres + row * d + v * 8);
+    }
+  }
+  m1 = warp_sum(m1) / d;
+  m2 = warp_sum(m2) / d;
+  // pass 2 recomputes g_w from the packed registers (scale / w come from L1) instead of keeping 40 more floats live
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 r2 = unpack_bf16x2(rp.u[j]);
-            const float t0 = fmaf(xh[i][2 * j], -m2r, fmaf(gq[i][2 * j], rstd, -m1r));
-            const float t1 = fmaf(xh[i][2 * j + 1], -m2r, fmaf(gq[i][2 * j + 1], rstd, -m1r));
-            o.u[j] = pack_bf16x2(r2.x + t0, r2.y + t1);
-          }
-        } else {
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nv) {
+      float xf[8], g[8], s[8], wv[8], o[8];
+      unpack8(xp[i], xf);
+      unpack8(gp[i], g);
+      unpack8(ld8(sc + v * 8), s);
+      if (w) ldf8(w + v * 8, wv);
+      if (dres) unpack8(rp[i], o);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float t0 = fmaf(xh[i][2 * j], -m2r, fmaf(gq[i][2 * j], rstd, -m1r));
-            const float t1 = fmaf(xh[i][2 * j + 1], -m2r, fmaf(gq[i][2 * j + 1], rstd, -m1r));
-            o.u[j] = pack_bf16x2(t0, t1);
-          }
-        }
-        st8(dx + row * d + v * 8, o);
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xf[j] - mean) * rstd;
+        float gq = g[j] * bf16_round(1.f + s[j]);
+        if (w) gq *= wv[j];
+        const float t = rstd * (gq - m1 - xh * m2);
+        o[j] = dres ? o[j] + t : t;
       }
+      st8(dx + row * d + v * 8, pack8(o));
     }
   }
 }
@@ -459,8 +462,7 @@ DLB_EXPORT int dlb_ln_modulate_fwd(const void* x, const float* w, const float* b
   DLB_REQUIRE((w == nullptr) == (b == nullptr), DLB_ERR_SHAPE, "ln_modulate_fwd: weight and bias must both be set or null");
   DLB_REQUIRE(rows_per_mod >= 1 && (mean == nullptr) == (rstd == nullptr), DLB_ERR_SHAPE, "ln_modulate_fwd: bad args");
   const int warps = 4;
-  const int64_t grid64 = (R + warps - 1) / warps;
-  const int grid = (int)(grid64 < (int64_t)dlb_num_sms() * 6 ? grid64 : (int64_t)dlb_num_sms() * 6);
+  const int grid = (int)((R + warps - 1) / warps);
   VPL_SWITCH(d, (ln_modulate_fwd_kernel<VPL><<<grid, warps * 32, 0, stream>>>(
                     (const bf16*)x, w, b, (const bf16*)scale, (const bf16*)shift, mod_ld, (int)rows_per_mod, (bf16*)y,
                     mean, rstd, R, d, eps)));
@@ -484,8 +486,7 @@ DLB_EXPORT int dlb_ln_modulate_bwd(const void* dy, const void* x, const float* m
   const int64_t R = groups * rows_per_group;
   const int64_t rows_per_mod = per_token ? 1 : rows_per_group;
   const int warps = 4;
-  const int64_t grid64 = (R + warps - 1) / warps;
-  const int grid_rows = (int)(grid64 < (int64_t)dlb_num_sms() * 5 ? grid64 : (int64_t)dlb_num_sms() * 5);
+  const int grid_rows = (int)((R + warps - 1) / warps);
   if (per_token) {
     VPL_SWITCH(d, (ln_modulate_bwd_rows_kernel<VPL, true><<<grid_rows, warps * 32, 0, stream>>>(
                       (const bf16*)dy, (const bf16*)x, mean, rstd, w, b, (const bf16*)scale, mod_ld, rows_per_mod,
