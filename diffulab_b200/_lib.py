@@ -49,6 +49,7 @@ _SIGNATURES: dict[str, list] = {
     "dlb_attn_fwd_tc": [p, i32, p, p, i32, i32, i32, i32, f32, p],
     # segs, nseg, lse, dsum, kmask, mask_len, B, H, hd, scale, stream
     "dlb_attn_bwd": [p, i32, p, p, p, i32, i32, i32, i32, f32, p],
+    "dlb_attn_bwd_tc": [p, i32, p, p, p, i32, i32, i32, i32, f32, p],
     "dlb_cast_f32_bf16": [p, p, i64, i64, i64, p],
     "dlb_cast_bf16_f32": [p, p, i64, p],
     "dlb_umma_probe": [p, p, p, i32, i32, i32, i32, i32, p],

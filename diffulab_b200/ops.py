@@ -382,8 +382,11 @@ def attn_fwd(specs: list[AttnSegSpec], B: int, H: int, hd: int, scale: float, km
     return outs, lse
 
 
+ATTN_BWD_IMPL = "dlb_attn_bwd_tc"  # tcgen05 backward; "dlb_attn_bwd" is the mma.sync kernel pair (comparison tests)
+
+
 def attn_bwd(specs: list[AttnSegSpec], outs: list[Tensor], douts: list[Tensor], lse: Tensor, B: int, H: int, hd: int,
-             scale: float, dqkvs: list[Tensor], kmask: Tensor | None = None) -> list[Tensor]:
+             scale: float, dqkvs: list[Tensor], kmask: Tensor | None = None, impl: str | None = None) -> list[Tensor]:
     """Returns dqk (grad wrt rotated q|k) per segment; writes dv into dqkvs[i][:, 2d:]."""
     dev = specs[0].qk.device
     dqks = [torch.empty(B * s.len, 2 * s.d, device=dev, dtype=BF16) for s in specs]
@@ -391,7 +394,7 @@ def attn_bwd(specs: list[AttnSegSpec], outs: list[Tensor], douts: list[Tensor], 
     arr = _seg_array(specs, outs, douts, dqks, dqkvs)
     mask_len = kmask.shape[1] if kmask is not None else 0
     import ctypes as C
-    _lib_call("dlb_attn_bwd", C.cast(arr, C.c_void_p), len(specs), lse.data_ptr(), dsum.data_ptr(), _ptr(kmask), mask_len,
+    _lib_call(impl or ATTN_BWD_IMPL, C.cast(arr, C.c_void_p), len(specs), lse.data_ptr(), dsum.data_ptr(), _ptr(kmask), mask_len,
               B, H, hd, scale, _stream())
     return dqks
 

@@ -121,6 +121,10 @@ int dlb_attn_fwd_tc(const dlb_attn_seg* segs, int nseg, float* lse, const uint8_
 int dlb_attn_bwd(const dlb_attn_seg* segs, int nseg, const float* lse, float* dsum, const uint8_t* kmask,
                  int mask_len, int B, int H, int hd, float scale, dlb_stream_t stream);
 
+/* tcgen05 / TMEM implementation of dlb_attn_bwd (same contract; head_dim <= 128) */
+int dlb_attn_bwd_tc(const dlb_attn_seg* segs, int nseg, const float* lse, float* dsum, const uint8_t* kmask,
+                    int mask_len, int B, int H, int hd, float scale, dlb_stream_t stream);
+
 /* development probe: D[128,N] = A*B^T from thread-staged non-swizzled UMMA operands (pins LBO/SBO semantics) */
 int dlb_umma_probe(const void* A, const void* B, float* D, int N, int K, int a_mn, int b_mn, int swap_lbo_sbo,
                    dlb_stream_t stream);

@@ -38,7 +38,8 @@ for name, B, H, hd, L, N in [("dit_xl2", 128, 16, 72, 0, 256), ("sprint_mm", 64,
     outs, lse = ops.attn_fwd(specs, B, H, hd, hd ** -0.5, None)
     douts = [torch.randn_like(o) for o in outs]
     dqkvs = [torch.empty_like(q) for q in qkvs]
-    ms = timeit(lambda: ops.attn_bwd(specs, outs, douts, lse, B, H, hd, hd ** -0.5, dqkvs, None))
-    row["bwd_ms"] = round(ms, 4)
-    row["bwd_tflops"] = round(2.5 * flops / ms / 1e9, 1)
+    for impl in ("dlb_attn_bwd_tc", "dlb_attn_bwd"):
+        ms = timeit(lambda: ops.attn_bwd(specs, outs, douts, lse, B, H, hd, hd ** -0.5, dqkvs, None, impl=impl))
+        row[impl + "_ms"] = round(ms, 4)
+        row[impl + "_tflops"] = round(2.5 * flops / ms / 1e9, 1)
     print(json.dumps(row), flush=True)

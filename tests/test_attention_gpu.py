@@ -36,8 +36,9 @@ CASES = [
 
 
 @pytest.mark.parametrize("impl", ["dlb_attn_fwd_tc", "dlb_attn_fwd"])
+@pytest.mark.parametrize("bwd_impl", ["dlb_attn_bwd_tc", "dlb_attn_bwd"])
 @pytest.mark.parametrize("B,H,hd,L,N,masked", CASES)
-def test_attention_fwd_bwd(cuda_device, B, H, hd, L, N, masked, impl):
+def test_attention_fwd_bwd(cuda_device, B, H, hd, L, N, masked, impl, bwd_impl):
     from diffulab_b200 import ops
 
     g = torch.Generator(device="cuda").manual_seed(B * 100 + H * 10 + hd + L)
@@ -71,7 +72,7 @@ def test_attention_fwd_bwd(cuda_device, B, H, hd, L, N, masked, impl):
     dref = torch.cat([o.view(B, l, d) for o, l in zip(douts, segs_len)], 1).float().view(B, S, H, hd)
     ref.backward(dref)
     dqkvs = [torch.zeros(B * l, 3 * d, device="cuda", dtype=BF) for l in segs_len]
-    dqks = ops.attn_bwd(specs, outs, douts, lse, B, H, hd, scale, dqkvs, kmask)
+    dqks = ops.attn_bwd(specs, outs, douts, lse, B, H, hd, scale, dqkvs, kmask, impl=bwd_impl)
     dq = torch.cat([x.view(B, l, 2 * d)[..., :d] for x, l in zip(dqks, segs_len)], 1)
     dk = torch.cat([x.view(B, l, 2 * d)[..., d:] for x, l in zip(dqks, segs_len)], 1)
     dv = torch.cat([x.view(B, l, 3 * d)[..., 2 * d :] for x, l in zip(dqkvs, segs_len)], 1)
