@@ -304,7 +304,8 @@ def run_gpu_arm(args) -> None:
                 "launches": int(g_calls), "gemm_ms_per_step": round(g_ms / args.steps, 3),
                 "gemm_share_of_kernel_time": round(g_ms / all_ms, 4) if all_ms else None,
                 "step_model_flops_frac": round(value / world * TRAIN_GFLOP_PER_IMG * 1e9 / (peak * 1e12), 4)}
-    breakdown = {k: {"calls_per_step": v["calls"] / args.steps, "ms_per_step": round(v["ms"] / args.steps, 3)}
+    breakdown = {k: {"calls_per_step": v["calls"] / args.steps, "ms_per_step": round(v["ms"] / args.steps, 3),
+                     **({"tflops": round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1)} if v["work"] > 0 and v["ms"] > 0 else {})}
                  for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
 
     # ---- 50-step Euler sampling sweep (sharded batch, no collective) --------------------------------------

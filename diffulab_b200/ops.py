@@ -118,7 +118,7 @@ def gemm(
     if bias is not None and (bias.dtype != F32 or bias.numel() != N or not bias.is_contiguous()):
         raise ValueError("gemm: bias must be a contiguous fp32 vector of length N")
     kind = "gemm_wgrad" if (a_mn and b_mn) else ("gemm_dgrad" if b_mn else "gemm_fwd")
-    with _Timed(kind, 2.0 * M * N * K):
+    with _Timed(f"{kind} {M}x{N}x{K}" if _prof is not None else kind, 2.0 * M * N * K):
         rc = _lib.load().dlb_gemm_bf16(
             a.data_ptr(), b.data_ptr(), out.data_ptr(), _ptr(bias), M, N, K,
             a.stride(0), b.stride(0), out.stride(0), int(a_mn), int(b_mn), mode, split_k, tile_n, _stream(),
