@@ -22,7 +22,9 @@ def timeit(fn, iters=10):
     return e0.elapsed_time(e1) / iters
 
 
-for name, B, H, hd, L, N in [("dit_xl2", 128, 16, 72, 0, 256), ("sprint_mm", 64, 12, 64, 128, 256), ("hd128", 32, 8, 128, 0, 1024)]:
+CASES = [("dit_xl2", 128, 16, 72, 0, 256), ("sprint_mm", 64, 12, 64, 128, 256), ("hd128", 32, 8, 128, 0, 1024)]
+ONLY = sys.argv[1:]  # optional case names
+for name, B, H, hd, L, N in [c for c in CASES if not ONLY or c[0] in ONLY]:
     d = H * hd
     lens = [L, N] if L else [N]
     qks = [torch.randn(B * l, 2 * d, device="cuda").bfloat16() for l in lens]
