@@ -71,7 +71,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler (role dispatch + uniform MMA issue)
   const int mb = (M + BM - 1) / BM, nb = (N + BN - 1) / BN;
   const int kb_total = (K + BK - 1) / BK;
   const int kb_per = (kb_total + split_k - 1) / split_k;
@@ -100,39 +101,46 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp loops on uniform values, one elected lane issues) =====================
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(t, mb, nb, kb_total, kb_per);
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full[stage], C::STAGE_BYTES);
-          uint8_t* a = sA + stage * A_TILE_BYTES;
-          uint8_t* b = sB + stage * C::B_TILE_BYTES;
-          if constexpr (!A_MN) {
-            ptx::tma_load_2d(a, &tmA, &full[stage], kb * BK, tc.m_blk * BM);
-          } else {
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(&full[stage], C::STAGE_BYTES);
+            uint8_t* a = sA + stage * A_TILE_BYTES;
+            uint8_t* b = sB + stage * C::B_TILE_BYTES;
+            if constexpr (!A_MN) {
+              ptx::tma_load_2d(a, &tmA, &full[stage], kb * BK, tc.m_blk * BM);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i)
-              ptx::tma_load_2d(a + i * MN_BLOCK_BYTES, &tmA, &full[stage], tc.m_blk * BM + i * 64, kb * BK);
-          }
-          if constexpr (!B_MN) {
-            ptx::tma_load_2d(b, &tmB, &full[stage], kb * BK, tc.n_blk * BN);
-          } else {
+              for (int i = 0; i < BM / 64; ++i)
+                ptx::tma_load_2d(a + i * MN_BLOCK_BYTES, &tmA, &full[stage], tc.m_blk * BM + i * 64, kb * BK);
+            }
+            if constexpr (!B_MN) {
+              ptx::tma_load_2d(b, &tmB, &full[stage], kb * BK, tc.n_blk * BN);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              ptx::tma_load_2d(b + i * MN_BLOCK_BYTES, &tmB, &full[stage], tc.n_blk * BN + i * 64, kb * BK);
+              for (int i = 0; i < BN / 64; ++i)
+                ptx::tma_load_2d(b + i * MN_BLOCK_BYTES, &tmB, &full[stage], tc.n_blk * BN + i * 64, kb * BK);
+            }
           }
+          __syncwarp();
           if (++stage == NST) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp, warp-uniform code; one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN, B_MN);
+      // K-major: a k-step is 16 elements (32 B) inside the swizzle atom. MN-major: 16 k-rows (2 KB). In 16-byte units:
+      constexpr uint64_t A_KSTEP = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4, B_KSTEP = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t a_base = ptx::smem_u32(sA), b_base = ptx::smem_u32(sB);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -141,25 +149,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const TileCoord tc = decode_tile(t, mb, nb, kb_total, kb_per);
         ptx::mbar_wait(&tempty[as], aphase ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = tmem_u + as * BN;
         for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
           ptx::mbar_wait(&full[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(sA + stage * A_TILE_BYTES);
-          const uint32_t b_addr = ptx::smem_u32(sB + stage * C::B_TILE_BYTES);
+          const uint32_t a_addr = a_base + stage * A_TILE_BYTES;
+          const uint32_t b_addr = b_base + stage * C::B_TILE_BYTES;
+          const uint64_t adesc0 = A_MN ? ptx::make_smem_desc_sw128(a_addr, MN_BLOCK_BYTES, 1024) : ptx::make_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t bdesc0 = B_MN ? ptx::make_smem_desc_sw128(b_addr, MN_BLOCK_BYTES, 1024) : ptx::make_smem_desc_sw128(b_addr, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // K-major: step 16 elements (32 B) inside the swizzle atom. MN-major: step 16 k-rows (2 KB).
-            const uint64_t adesc = A_MN ? ptx::make_smem_desc_sw128(a_addr + k * (UMMA_K * 128), MN_BLOCK_BYTES, 1024)
-                                        : ptx::make_smem_desc_sw128(a_addr + k * (UMMA_K * 2), 16, 1024);
-            const uint64_t bdesc = B_MN ? ptx::make_smem_desc_sw128(b_addr + k * (UMMA_K * 128), MN_BLOCK_BYTES, 1024)
-                                        : ptx::make_smem_desc_sw128(b_addr + k * (UMMA_K * 2), 16, 1024);
-            ptx::umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
-          }
-          ptx::umma_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            ptx::umma_bf16_elect(d_tmem, adesc0 + k * A_KSTEP, bdesc0 + k * B_KSTEP, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
+          ptx::umma_commit_elect(&empty[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == NST) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tfull[as]);  // accumulator complete -> epilogue
+        ptx::umma_commit_elect(&tfull[as]);  // accumulator complete -> epilogue
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
@@ -303,15 +307,16 @@ int dispatch_major(int a_mn, int b_mn, int out_mode, const CUtensorMap& ta, cons
   return dispatch_out<BN, true, true>(out_mode, ta, tb, tc, bias, M, N, K, split_k, s);
 }
 
-// Cost model fitted to B200 measurements (profiles/gemm_microbench_r1.md): one k-block of a 128 x BN tile costs
-// ~(BN + 364) units, the epilogue ~8*BN; a launch costs waves * per-tile cost. Used to pick BN and split-K.
+// Cost model fitted to B200 measurements (profiles/gemm_microbench_r1.jsonl): one k-block of a 128 x BN tile costs
+// ~(BN + 100) units, the epilogue ~8*BN; a launch costs waves * per-tile cost. Used to pick BN and split-K.
+// (The constant was 364 while the MMA warp issued from an `if (lane == 0)` region: ~95 cycles per tcgen05.mma.)
 double tile_cost(int M, int N, int kb_total, int bn, int split_k) {
   const int sms = dlb_num_sms();
   const int kb_per = (kb_total + split_k - 1) / split_k;
   const int splits = (kb_total + kb_per - 1) / kb_per;
   const long tiles = (long)((M + BM - 1) / BM) * ((N + bn - 1) / bn) * splits;
   const long waves = (tiles + sms - 1) / sms;
-  return (double)waves * ((double)kb_per * (bn + 364.0) + 8.0 * bn);
+  return (double)waves * ((double)kb_per * (bn + 100.0) + 8.0 * bn);
 }
 
 void pick_config(int M, int N, int K, bool allow_split, int& tile_n, int& split_k) {

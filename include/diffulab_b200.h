@@ -125,6 +125,10 @@ int dlb_attn_bwd(const dlb_attn_seg* segs, int nseg, const float* lse, float* ds
 int dlb_attn_bwd_tc(const dlb_attn_seg* segs, int nseg, const float* lse, float* dsum, const uint8_t* kmask,
                     int mask_len, int B, int H, int hd, float scale, dlb_stream_t stream);
 
+/* development aid: dev_buf = device buffer of 3 x 64 int64 receiving one CTA's SM-clock timeline per tcgen05 attention
+ * kernel (slots 0..63 forward, 64..127 dq, 128..191 dkv); NULL switches tracing off (the default) */
+int dlb_attn_set_trace(long long* dev_buf);
+
 /* development probe: D[128,N] = A*B^T from thread-staged non-swizzled UMMA operands (pins LBO/SBO semantics) */
 int dlb_umma_probe(const void* A, const void* B, float* D, int N, int K, int a_mn, int b_mn, int swap_lbo_sbo,
                    dlb_stream_t stream);
