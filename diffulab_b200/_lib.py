@@ -54,6 +54,8 @@ _SIGNATURES: dict[str, list] = {
     "dlb_cast_bf16_f32": [p, p, i64, p],
     "dlb_umma_probe": [p, p, p, i32, i32, i32, i32, i32, p],
     "dlb_attn_set_trace": [p],
+    # base, rows, ld, H, hd, grid, tiles_per_cta, dump, stream
+    "dlb_tma_gather_probe": [p, i64, i64, i32, i32, i32, i32, p, p],
     "dlb_add_bf16": [p, p, p, i64, p],
     "dlb_bias_silu_fwd": [p, p, p, i64, i64, i32, p],
     "dlb_bias_silu_bwd": [p, p, p, p, p, i64, i64, i32, p],

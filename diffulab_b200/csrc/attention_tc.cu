@@ -32,8 +32,9 @@
 namespace attn_tc {
 typedef __nv_bfloat16 bf16;
 
-constexpr int NC = 256;      // compute threads
-constexpr int NT = NC + 32;  // + the MMA-issue warp
+constexpr int NC = 256;      // compute threads (forward: the whole CTA)
+constexpr int NPW = 2;       // backward: producer (cp.async) warps
+constexpr int NT = NC + 32 + NPW * 32;  // backward CTA: compute warps 0-7, MMA-issue warp 8, producer warps 9..
 constexpr int KT = 64;       // rows of a streamed tile
 constexpr float LOG2E = 1.4426950408889634f;
 
@@ -71,9 +72,14 @@ __device__ __forceinline__ void cp_async16_zfill(void* dst, const void* src, boo
   const int sz = valid ? 16 : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(src), "r"(sz));
 }
-__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+__device__ __forceinline__ void cp_async4_zfill(void* dst, const void* src, bool valid) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(src));
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(src), "r"(sz));
+}
+// this thread arrives on the mbarrier (without raising its pending count) once all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(ptx::smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -99,16 +105,16 @@ __device__ __forceinline__ const bf16* row_ptr(const Params& p, int which, int b
   return base + (int64_t)h * p.hd;
 }
 
-// The 8 compute warps stage a ROWS-row tile into layout L1(ROWS). One warp instruction covers 8 rows x 4 chunks: 64
+// NW loader warps stage a ROWS-row tile into layout L1(ROWS). One warp instruction covers 8 rows x 4 chunks: 64
 // contiguous bytes of each row on the global side, and 4 conflict-free 128-byte wavefronts on the shared side.
-template <int HDP, int WHICH, int ROWS>
+template <int HDP, int WHICH, int ROWS, int NW = 8>
 __device__ __forceinline__ void load_tile(uint8_t* sm, const Params& p, int b, int h, int s0, int warp, int lane) {
   constexpr int CPR = HDP / 8;
   const int nvalid = p.hd >> 3;
   const int cl = lane & 3;
 #pragma unroll
-  for (int rg = 0; rg < ROWS / 64; ++rg) {
-    const int r = (rg * 8 + warp) * 8 + (lane >> 2);
+  for (int rg = 0; rg < ROWS / (8 * NW); ++rg) {
+    const int r = (rg * NW + warp) * 8 + (lane >> 2);
     const int s = s0 + r;
     const bool rv = s < p.S;
     const bf16* src = row_ptr(p, WHICH, b, h, rv ? s : 0);
@@ -125,8 +131,9 @@ __device__ __forceinline__ void load_tile(uint8_t* sm, const Params& p, int b, i
 template <int HDP, int WHICH>
 __device__ __forceinline__ void store_tile(const bf16* stage, const Params& p, int b, int h, int s0, int tid) {
   const int cpr = p.hd >> 3;
-  for (int idx = tid; idx < 128 * cpr; idx += NC) {
-    const int r = idx / cpr, c = idx - r * cpr;
+  const int dq = NC / cpr, dm = NC - dq * cpr;  // idx += NC  <=>  (r, c) += (dq, dm) with carry
+  int r = tid / cpr, c = tid - r * cpr;
+  while (r < 128) {
     const int s = s0 + r;
     if (s < p.S) {
       int sg;
@@ -137,22 +144,29 @@ __device__ __forceinline__ void store_tile(const bf16* stage, const Params& p, i
                  : WHICH == O_DK ? g.dk + row * g.lddk : g.dv + row * g.lddv;
       *reinterpret_cast<uint4*>(base + (int64_t)h * p.hd + c * 8) = *reinterpret_cast<const uint4*>(stage + r * HDP + c * 8);
     }
+    r += dq;
+    c += dm;
+    if (c >= cpr) { c -= cpr; ++r; }
   }
 }
 
 // this thread's half of a finished fp32 TMEM tile (HDP columns) -> scaled bf16 in the row-major staging tile
 template <int HDP>
 __device__ __forceinline__ void tmem_half_to_stage(uint32_t taddr, bf16* stage, int r, int half, float mul) {
+  constexpr int HH = HDP / 2;  // 32, 40, 48 or 64 columns: all loads are issued before the single wait
+  uint32_t v[HH];
+  const uint32_t a = taddr + half * HH;
+  ptx::tmem_ld32(a, v);
+  if constexpr (HH == 40) ptx::tmem_ld8(a + 32, v + 32);
+  if constexpr (HH == 48) ptx::tmem_ld16(a + 32, v + 32);
+  if constexpr (HH == 64) ptx::tmem_ld32(a + 32, v + 32);
+  ptx::tmem_ld_wait();
 #pragma unroll
-  for (int c8 = 0; c8 < HDP / 16; ++c8) {
-    const int c = half * (HDP / 2) + c8 * 8;
-    uint32_t v[8];
-    ptx::tmem_ld8(taddr + c, v);
-    ptx::tmem_ld_wait();
+  for (int c = 0; c < HH; c += 8) {
     float t[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) t[j] = __uint_as_float(v[j]) * mul;
-    st8(stage + r * HDP + c, pack8(t));
+    for (int j = 0; j < 8; ++j) t[j] = __uint_as_float(v[c + j]) * mul;
+    st8(stage + r * HDP + half * HH + c, pack8(t));
   }
 }
 
@@ -343,48 +357,141 @@ __global__ void __launch_bounds__(NC, 2) attn_fwd_tc_kernel(const Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// backward kernels: persistent CTAs (one per SM) walk a list of work items (128-row tile x, head h, sample b).
+// Warp roles: 0-7 compute, 8 MMA issue, 9.. producers. The producers run the cp.async ring NST-1 streamed tiles ahead
+// ACROSS item boundaries (resident tiles are double-buffered, RES = 2) and are the only threads that ever block on
+// load-store-unit backpressure; each producer thread arrives on full[stage] asynchronously when its copies have landed
+// (cp.async.mbarrier.arrive.noinc). The MMA warp likewise issues the next item's first score products during the
+// current item's epilogue. RES = 1 (large head dims, or fewer than NST streamed tiles per item) = one item per CTA.
+//   empty[s] (tcgen05.commit) accumulating products that read stage s are done        MMA warp -> producers
+// ---------------------------------------------------------------------------------------------------------
+// TMA fast path (every segment length a multiple of 128): 4-D tensor maps {8 elements, rows, 16-byte chunks of a head,
+// heads} whose boxes land directly in layout L1(64) / L1(128) (pinned by scripts/probe_tma_gather.py); one elected
+// producer lane issues them. Otherwise the producer warps use cp.async (ragged tiles, arbitrary segment lengths).
+enum { M_Q64 = 0, M_Q128, M_K64, M_K128, M_V64, M_V128, M_DO64, M_DO128, M_O128, M_COUNT };
+struct BwdMaps { CUtensorMap m[2][M_COUNT]; };
+__device__ __forceinline__ void tma_tile(void* dst, const BwdMaps& maps, int which, const Params& p, int b, int h, int s0, uint64_t* bar) {
+  const int sg = s0 < p.seg[0].len ? 0 : 1;
+  const int row = b * p.seg[sg].len + (sg ? s0 - p.seg[0].len : s0);
+  ptx::tma_load_4d(dst, &maps.m[sg][which], bar, 0, row, 0, h);
+}
+
+struct Item { int x, h, b; };
+__device__ __forceinline__ Item decode_item(const Params& p, int w, int nx) {
+  Item it;
+  it.x = w % nx;
+  const int t = w / nx;
+  it.h = t % p.H;
+  it.b = t / p.H;
+  return it;
+}
+#define MMA_TRACE(KIND, item, i)                                                                   \
+  do {                                                                                             \
+    if (p.trace != nullptr && lane == 0 && blockIdx.x == gridDim.x / 2 && (item) == (n_my > 1 ? 1 : 0) && (i) < 56) p.trace[(KIND) * 64 + (i)] = clock64(); \
+  } while (0)
+#define BWD_TRACE(KIND, i)                                                                         \
+  do {                                                                                             \
+    if (p.trace != nullptr && tid == 0 && blockIdx.x == gridDim.x / 2 && k == trace_item) p.trace[(KIND) * 64 + (i)] = clock64(); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
 // backward: dQ (and D = rowsum(dO o O))
 // ---------------------------------------------------------------------------------------------------------
-template <int HDP>
-__global__ void __launch_bounds__(NT, 1) attn_bwd_dq_tc_kernel(const Params p) {
-  constexpr int NST = 4;
+template <int HDP, int RES, int NST, bool TMA>
+__global__ void __launch_bounds__(NT, 1) attn_bwd_dq_tc_kernel(const Params p, const __grid_constant__ BwdMaps maps) {
   constexpr int TQ = 128 * HDP * 2, TK = KT * HDP * 2;
   constexpr int CPR = HDP / 8;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sDO = sQ + TQ;
-  uint8_t* sKV = sDO + TQ;                                 // NST stages of {K tile, V tile}
+  uint8_t* sRes = smem;                                    // RES x {Q, dO, O} resident tiles, layout L1(128)
+  uint8_t* sKV = sRes + RES * 3 * TQ;                      // NST stages of {K tile, V tile}
   uint8_t* sDS = sKV + NST * 2 * TK;                       // [128 q][64 keys] bf16, layout L1(128), 16 KB
-  float* sBias = reinterpret_cast<float*>(sDS + 16384);    // [NST][64] key biases
-  float* sDrow = sBias + NST * KT;                         // [128] D
-  __shared__ uint64_t full[NST], bar1[2], ps_full, bar2;
+  float* sLrow = reinterpret_cast<float*>(sDS + 16384);    // [RES][128] lse rows (natural log)
+  float* sX = sLrow + RES * 128;                           // [2][2][128] pair exchange
+  __shared__ uint64_t full[NST], empty[NST], bar1[2], ps_full, bar2;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int T = (p.S + KT - 1) / KT;
-  ATTN_TRACE(1, 0);
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const int T = (p.S + KT - 1) / KT, nx = (p.S + 127) / 128;
+  const int nitems = nx * p.H * p.B;
+  const int n_my = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int G = n_my * T;  // streamed tiles this CTA processes
   if (tid == 0) {
-    for (int i = 0; i < NST; ++i) ptx::mbar_init(&full[i], NC);
+    for (int i = 0; i < NST; ++i) { ptx::mbar_init(&full[i], TMA ? 1 : NPW * 32); ptx::mbar_init(&empty[i], 1); }
     ptx::mbar_init(&bar1[0], 1); ptx::mbar_init(&bar1[1], 1); ptx::mbar_init(&ps_full, NC); ptx::mbar_init(&bar2, 1);
     ptx::fence_mbar_init();
   }
-  if (warp == 8) ptx::tmem_alloc<512>(&tmem_slot);
+  if (warp_u == 8) ptx::tmem_alloc<512>(&tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
   constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, KT, false, false);
   constexpr uint32_t idesc_dq = ptx::make_idesc_bf16(128, HDP, false, true);
 
-  if (warp == 8) {
+  if (warp_u > 8) {
+    // ---------------- producer warps ----------------
+    const int pw = warp_u - 9;
+    int uk = 0, uj = 0;
+    for (int u = 0; u < G; ++u) {
+      if (u >= NST) ptx::mbar_wait(&empty[u % NST], ((u / NST) - 1) & 1);
+      const Item it = decode_item(p, blockIdx.x + uk * gridDim.x, nx);
+      uint8_t* st = sKV + (u % NST) * 2 * TK;
+      uint8_t* res = sRes + (uk % RES) * 3 * TQ;
+      if constexpr (TMA) {
+        if (pw == 0 && ptx::elect_one()) {
+          uint64_t* bar = &full[u % NST];
+          ptx::mbar_expect_tx(bar, 2 * TK + (uj == 0 ? 3 * TQ + 512 : 0));
+          if (uj == 0) {
+            tma_tile(res, maps, M_Q128, p, it.b, it.h, it.x * 128, bar);
+            tma_tile(res + TQ, maps, M_DO128, p, it.b, it.h, it.x * 128, bar);
+            tma_tile(res + 2 * TQ, maps, M_O128, p, it.b, it.h, it.x * 128, bar);
+            ptx::bulk_load_1d(sLrow + (uk % RES) * 128, p.lse + ((int64_t)it.b * p.H + it.h) * p.S + it.x * 128, 512, bar);
+          }
+          tma_tile(st, maps, M_K64, p, it.b, it.h, uj * KT, bar);
+          tma_tile(st + TK, maps, M_V64, p, it.b, it.h, uj * KT, bar);
+        }
+        __syncwarp();
+        if (++uj == T) { uj = 0; ++uk; }
+        continue;
+      }
+      if (uj == 0) {
+        load_tile<HDP, T_Q, 128, NPW>(res, p, it.b, it.h, it.x * 128, pw, lane);
+        load_tile<HDP, T_DO, 128, NPW>(res + TQ, p, it.b, it.h, it.x * 128, pw, lane);
+        load_tile<HDP, T_O, 128, NPW>(res + 2 * TQ, p, it.b, it.h, it.x * 128, pw, lane);
+#pragma unroll
+        for (int i = pw * 32 + lane; i < 128; i += NPW * 32) {
+          const int row = it.x * 128 + i;
+          const bool v = row < p.S;
+          cp_async4_zfill(sLrow + (uk % RES) * 128 + i, p.lse + ((int64_t)it.b * p.H + it.h) * p.S + (v ? row : 0), v);
+        }
+      }
+      load_tile<HDP, T_K, KT, NPW>(st, p, it.b, it.h, uj * KT, pw, lane);
+      load_tile<HDP, T_V, KT, NPW>(st + TK, p, it.b, it.h, uj * KT, pw, lane);
+      cp_async_arrive_noinc(&full[u % NST]);
+      if (++uj == T) { uj = 0; ++uk; }
+    }
+    cp_async_wait<0>();
+  } else if (warp_u == 8) {
     // ---------------- MMA-issue warp ----------------
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
-    const uint64_t dq0 = desc_k128(ptx::smem_u32(sQ)), dd0 = desc_k128(ptx::smem_u32(sDO)), ds0 = desc_k128(ptx::smem_u32(sDS));
-    const uint32_t kva = ptx::smem_u32(sKV);
-    for (int j = -1; j < T; ++j) {
-      if (j + 1 < T) {  // S(t) = Q K_t^T, dP(t) = dO V_t^T into TMEM buffer t & 1
-        const int t = j + 1;
+    const uint32_t resa = ptx::smem_u32(sRes), kva = ptx::smem_u32(sKV);
+    const uint64_t ds0 = desc_k128(ptx::smem_u32(sDS));
+    int tk = 0, tj = 0;  // item / tile-in-item of tile t = g + 1
+    int gj = 0;          // tile-in-item of tile g
+    for (int g = -1; g < G; ++g) {
+      // Scores of tile g+1 go first (their operands are normally resident long before the dS of tile g is written) —
+      // unless that tile has not landed yet (item boundary, load-bound phase): then the accumulation of tile g goes first.
+      const bool next_ready = g + 1 < G && (g < 0 || __shfl_sync(0xffffffffu, (int)ptx::mbar_test_wait(&full[(g + 1) % NST], ((g + 1) / NST) & 1), 0) != 0);
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+      if ((pass == 0) == next_ready && g + 1 < G) {  // S(t) = Q K_t^T, dP(t) = dO V_t^T into TMEM buffer t & 1
+        const int t = g + 1;
+        MMA_TRACE(1, tk, 32 + tj * 4);
         ptx::mbar_wait(&full[t % NST], (t / NST) & 1);
+        MMA_TRACE(1, tk, 33 + tj * 4);
+        ptx::fence_proxy_async_smem();
         ptx::tc_fence_after();
+        const uint32_t ra = resa + (tk % RES) * 3 * TQ;
+        const uint64_t dq0 = desc_k128(ra), dd0 = desc_k128(ra + TQ);
         const uint64_t dk = desc_k64(kva + (t % NST) * 2 * TK), dv = desc_k64(kva + (t % NST) * 2 * TK + TK);
         const uint32_t ts = tmem + (t & 1) * 128;
 #pragma unroll
@@ -393,196 +500,204 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dq_tc_kernel(const Params p) {
           ptx::umma_bf16_elect(ts + KT, dd0 + ks * KSTEP_K128, dv + ks * KSTEP_K64, idesc_s, ks > 0);
         }
         ptx::umma_commit_elect(&bar1[t & 1]);
+        if (++tj == T) { tj = 0; ++tk; }
       }
-      if (j >= 0) {  // dQ += dS K_j : A K-major over keys, B = K tile read MN-major (N = hd, K = keys)
-        ptx::mbar_wait(&ps_full, j & 1);
+      if (pass == 0 && g >= 0) {  // dQ += dS K_g : A K-major over keys, B = K tile read MN-major (N = hd, K = keys)
+        MMA_TRACE(1, g / T, 34 + gj * 4);
+        ptx::mbar_wait(&ps_full, g & 1);
+        MMA_TRACE(1, g / T, 35 + gj * 4);
         ptx::tc_fence_after();
-        const uint64_t dk = desc_mn64(kva + (j % NST) * 2 * TK);
+        const uint64_t dk = desc_mn64(kva + (g % NST) * 2 * TK);
 #pragma unroll
-        for (int ks = 0; ks < KT / 16; ++ks) ptx::umma_bf16_elect(tmem + 256, ds0 + ks * KSTEP_K128, dk + ks * KSTEP_MN64, idesc_dq, (j > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < KT / 16; ++ks) ptx::umma_bf16_elect(tmem + 256, ds0 + ks * KSTEP_K128, dk + ks * KSTEP_MN64, idesc_dq, (gj > 0 || ks > 0) ? 1u : 0u);
+        ptx::umma_commit_elect(&empty[g % NST]);
         ptx::umma_commit_elect(&bar2);
+        if (++gj == T) gj = 0;
+      }
       }
     }
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tmem_dealloc<512>(tmem);
-    return;
-  }
+  } else {
+    // ---------------- compute warps ----------------
+    const int r = tid & 127, half = tid >> 7;
+    const int trace_item = n_my > 1 ? 1 : 0;
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tDQ = tmem + 256 + lane_off;
+    int k = 0, j = 0;
+    Item it = decode_item(p, blockIdx.x, nx);
+    float Lrow = 0.f, Drow = 0.f;
 
-  // ---------------- compute warps ----------------
-  const int r = tid & 127, half = tid >> 7;
-  auto issue_tile = [&](int t) {
-    if (t < T) {
-      uint8_t* st = sKV + (t % NST) * 2 * TK;
-      load_tile<HDP, T_K, KT>(st, p, b, h, t * KT, warp, lane);
-      load_tile<HDP, T_V, KT>(st + TK, p, b, h, t * KT, warp, lane);
-      if (tid < KT && tile_may_be_masked(p, t * KT)) sBias[(t % NST) * KT + tid] = key_bias(p, b, t * KT + tid);
-    }
-    cp_async_commit();
-  };
-  // dO tile: staged through registers (same 8 rows x 4 chunks mapping) so that D = rowsum(dO o O) comes for free.
-  // All global loads are issued first, ahead of the cp.async traffic they would otherwise queue behind.
-  constexpr int NCG = (CPR + 3) / 4;
-  bf16x8 dreg[2][NCG], oreg[2][NCG];
-  {
-    const int nvalid = p.hd >> 3;
-    const int cl = lane & 3;
+    for (int g = 0; g < G; ++g) {
+      if (j == 0) {  // per-item setup: D = rowsum(dO o O) from the resident tiles, lse row
+        BWD_TRACE(1, 0);
+        it = decode_item(p, blockIdx.x + k * gridDim.x, nx);
+        ptx::mbar_wait(&full[g % NST], (g / NST) & 1);  // resident tiles (and streamed tile 0) of this item have landed
+        const uint8_t* sdo = sRes + (k % RES) * 3 * TQ + TQ + r * 16;
+        float dpart = 0.f;
 #pragma unroll
-    for (int rg = 0; rg < 2; ++rg) {
-      const int rr = (rg * 8 + warp) * 8 + (lane >> 2);
-      const int s = q0 + rr;
-      const bool rv = s < p.S;
-      const bf16* dsrc = row_ptr(p, T_DO, b, h, rv ? s : 0);
-      const bf16* osrc = row_ptr(p, T_O, b, h, rv ? s : 0);
-#pragma unroll
-      for (int g = 0; g < NCG; ++g) {
-        const int c = g * 4 + cl;
-        dreg[rg][g].u[0] = dreg[rg][g].u[1] = dreg[rg][g].u[2] = dreg[rg][g].u[3] = 0u;
-        oreg[rg][g] = dreg[rg][g];
-        if (rv && c < nvalid) { dreg[rg][g] = ld8(dsrc + c * 8); oreg[rg][g] = ld8(osrc + c * 8); }
-      }
-    }
-  }
-  load_tile<HDP, T_Q, 128>(sQ, p, b, h, q0, warp, lane);
-#pragma unroll
-  for (int t = 0; t < NST; ++t) issue_tile(t);
-  ATTN_TRACE(1, 1);
-  {
-    const int cl = lane & 3;
-#pragma unroll
-    for (int rg = 0; rg < 2; ++rg) {
-      const int rr = (rg * 8 + warp) * 8 + (lane >> 2);
-      const int s = q0 + rr;
-      uint8_t* dst = sDO + rr * 16;
-      float dpart = 0.f;
-#pragma unroll
-      for (int g = 0; g < NCG; ++g) {
-        const int c = g * 4 + cl;
-        if (g * 4 + 3 < CPR || c < CPR) {
+        for (int c = half; c < CPR; c += 2) {
           float df[8], of[8];
-          unpack8(dreg[rg][g], df); unpack8(oreg[rg][g], of);
+          unpack8(*reinterpret_cast<const bf16x8*>(sdo + c * 2048), df);
+          unpack8(*reinterpret_cast<const bf16x8*>(sdo + TQ + c * 2048), of);
 #pragma unroll
           for (int i = 0; i < 8; ++i) dpart += df[i] * of[i];
-          *reinterpret_cast<bf16x8*>(dst + c * 2048) = dreg[rg][g];
         }
+        float* sx = sX + (k & 1) * 256;  // double-buffered by item parity: one barrier is enough
+        sx[half * 128 + r] = dpart;
+        pair_barrier(1 + (warp & 3));
+        Drow = sx[r] + sx[128 + r];
+        const int myrow = it.x * 128 + r;
+        Lrow = myrow < p.S ? sLrow[(k % RES) * 128 + r] * LOG2E : INFINITY;
+        if (half == 0 && myrow < p.S) p.dsum[((int64_t)it.b * p.H + it.h) * p.S + myrow] = Drow;
+        BWD_TRACE(1, 1);
       }
-      dpart += __shfl_xor_sync(0xffffffffu, dpart, 1);
-      dpart += __shfl_xor_sync(0xffffffffu, dpart, 2);
-      if (cl == 0) {
-        sDrow[rr] = dpart;
-        if (s < p.S) p.dsum[((int64_t)b * p.H + h) * p.S + s] = dpart;
+      if (j < 8) BWD_TRACE(1, 4 + j * 6);
+      ptx::mbar_wait(&bar1[g & 1], (g >> 1) & 1);
+      ptx::tc_fence_after();
+      if (j < 8) BWD_TRACE(1, 5 + j * 6);
+      if (g >= 1) ptx::mbar_wait(&bar2, (g - 1) & 1);  // dQ += dS K_{g-1} finished: sDS is free
+      if (j < 8) BWD_TRACE(1, 6 + j * 6);
+      {
+        const uint32_t ts = tmem + lane_off + (g & 1) * 128 + half * 32;
+        uint32_t vs[32], vd[32];
+        ptx::tmem_ld32(ts, vs);
+        ptx::tmem_ld32(ts + KT, vd);
+        ptx::tmem_ld_wait();
+        float ds[32];
+        if (tile_may_be_masked(p, j * KT)) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            ds[i] = ex2((__uint_as_float(vs[i]) + key_bias(p, it.b, j * KT + half * 32 + i)) * p.scale_log2 - Lrow) * (__uint_as_float(vd[i]) - Drow);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ds[i] = ex2(__uint_as_float(vs[i]) * p.scale_log2 - Lrow) * (__uint_as_float(vd[i]) - Drow);
+        }
+        store_bf16x32(sDS + r * 16, half * 32, ds);
       }
-    }
-  }
-  const int myrow = q0 + r;
-  const float Lrow = myrow < p.S ? p.lse[((int64_t)b * p.H + h) * p.S + myrow] * LOG2E : INFINITY;
-  ATTN_TRACE(1, 2);
-  cp_async_wait<NST - 1>();  // Q and tile 0
-  ptx::fence_proxy_async_smem();
-  ptx::mbar_arrive(&full[0]);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  ATTN_TRACE(1, 3);
-  const float Drow = sDrow[r];
-  const uint32_t tmem = tmem_slot;
-  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-  const uint32_t tDQ = tmem + 256 + lane_off;
-
-  for (int j = 0; j < T; ++j) {
-    if (j + 1 < T) {
-      cp_async_wait<NST - 3>();  // my part of tile j+1 has landed
       ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&full[(j + 1) % NST]);
-    }
-    if (j < 8) ATTN_TRACE(1, 4 + j * 6);
-    ptx::mbar_wait(&bar1[j & 1], (j >> 1) & 1);
-    ptx::tc_fence_after();
-    if (j < 8) ATTN_TRACE(1, 5 + j * 6);
-    if (j >= 1) {
-      ptx::mbar_wait(&bar2, (j - 1) & 1);  // dQ += dS K_{j-1} finished: its stage and sDS are free
-      issue_tile(j + NST - 1);
-    }
-    if (j < 8) ATTN_TRACE(1, 6 + j * 6);
-    {
-      const uint32_t ts = tmem + lane_off + (j & 1) * 128 + half * 32;
-      uint32_t vs[32], vd[32];
-      ptx::tmem_ld32(ts, vs);
-      ptx::tmem_ld32(ts + KT, vd);
-      ptx::tmem_ld_wait();
-      float ds[32];
-      if (tile_may_be_masked(p, j * KT)) {
-        const float* bias = sBias + (j % NST) * KT + half * 32;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) ds[i] = ex2((__uint_as_float(vs[i]) + bias[i]) * p.scale_log2 - Lrow) * (__uint_as_float(vd[i]) - Drow);
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&ps_full);
+      if (j < 8) BWD_TRACE(1, 7 + j * 6);
+      if (j == T - 1) {  // item epilogue: dQ tile -> bf16 -> global
+        BWD_TRACE(1, 56);
+        ptx::mbar_wait(&bar2, g & 1);
+        ptx::tc_fence_after();
+        BWD_TRACE(1, 57);
+        bf16* stage = reinterpret_cast<bf16*>(sRes + (k % RES) * 3 * TQ + 2 * TQ);  // this item's (now dead) O buffer
+        tmem_half_to_stage<HDP>(tDQ, stage, r, half, p.scale);
+        ptx::tc_fence_before();
+        compute_barrier();
+        store_tile<HDP, O_DQ>(stage, p, it.b, it.h, it.x * 128, tid);
+        BWD_TRACE(1, 59);
+        j = 0;
+        ++k;
       } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) ds[i] = ex2(__uint_as_float(vs[i]) * p.scale_log2 - Lrow) * (__uint_as_float(vd[i]) - Drow);
+        ++j;
       }
-      store_bf16x32(sDS + r * 16, half * 32, ds);
     }
-    ptx::fence_proxy_async_smem();
-    ptx::tc_fence_before();
-    ptx::mbar_arrive(&ps_full);
-    if (j < 8) ATTN_TRACE(1, 7 + j * 6);
   }
-  ATTN_TRACE(1, 56);
-  ptx::mbar_wait(&bar2, (T - 1) & 1);
-  ptx::tc_fence_after();
-  ATTN_TRACE(1, 57);
-  bf16* stage = reinterpret_cast<bf16*>(sKV);
-  tmem_half_to_stage<HDP>(tDQ, stage, r, half, p.scale);
-  compute_barrier();
-  store_tile<HDP, O_DQ>(stage, p, b, h, q0, tid);
-  ATTN_TRACE(1, 59);
   ptx::tc_fence_before();
   __syncthreads();
+  if (warp_u == 8) ptx::tmem_dealloc<512>(__shfl_sync(0xffffffffu, tmem_slot, 0));
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // backward: dK, dV
 // ---------------------------------------------------------------------------------------------------------
-template <int HDP>
-__global__ void __launch_bounds__(NT, 1) attn_bwd_dkv_tc_kernel(const Params p) {
-  constexpr int NST = 4;
+template <int HDP, int RES, int NST, bool TMA>
+__global__ void __launch_bounds__(NT, 1) attn_bwd_dkv_tc_kernel(const Params p, const __grid_constant__ BwdMaps maps) {
   constexpr int TQ = 128 * HDP * 2, TK = KT * HDP * 2;
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* sK = smem;
-  uint8_t* sV = sK + TQ;
-  uint8_t* sQD = sV + TQ;                                  // NST stages of {Q tile, dO tile}
+  uint8_t* sRes = smem;                                    // RES x {K, V} resident tiles, layout L1(128)
+  uint8_t* sQD = sRes + RES * 2 * TQ;                      // NST stages of {Q tile, dO tile}
   uint8_t* sPT = sQD + NST * 2 * TK;                       // P^T  [128 keys][64 queries] bf16, layout L1(128)
   uint8_t* sDST = sPT + 16384;                             // dS^T
-  float* sL = reinterpret_cast<float*>(sDST + 16384);      // [NST][64] lse (natural log; +inf for rows >= S)
+  float* sL = reinterpret_cast<float*>(sDST + 16384);      // [NST][64] lse (natural log)
   float* sD = sL + NST * KT;                               // [NST][64] D
-  __shared__ uint64_t full[NST], bar1[2], ps_full, bar2;
+  __shared__ uint64_t full[NST], empty[NST], bar1[2], ps_full, bar2;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int T = (p.S + KT - 1) / KT;
-  ATTN_TRACE(2, 0);
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const int T = (p.S + KT - 1) / KT, nx = (p.S + 127) / 128;
+  const int nitems = nx * p.H * p.B;
+  const int n_my = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int G = n_my * T;
   if (tid == 0) {
-    for (int i = 0; i < NST; ++i) ptx::mbar_init(&full[i], NC);
+    for (int i = 0; i < NST; ++i) { ptx::mbar_init(&full[i], TMA ? 1 : NPW * 32); ptx::mbar_init(&empty[i], 1); }
     ptx::mbar_init(&bar1[0], 1); ptx::mbar_init(&bar1[1], 1); ptx::mbar_init(&ps_full, NC); ptx::mbar_init(&bar2, 1);
     ptx::fence_mbar_init();
   }
-  if (warp == 8) ptx::tmem_alloc<512>(&tmem_slot);
+  if (warp_u == 8) ptx::tmem_alloc<512>(&tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
   constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, KT, false, false);
   constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, HDP, false, true);
 
-  if (warp == 8) {
+  if (warp_u > 8) {
+    // ---------------- producer warps ----------------
+    const int pw = warp_u - 9;
+    int uk = 0, uj = 0;
+    for (int u = 0; u < G; ++u) {
+      if (u >= NST) ptx::mbar_wait(&empty[u % NST], ((u / NST) - 1) & 1);
+      const Item it = decode_item(p, blockIdx.x + uk * gridDim.x, nx);
+      uint8_t* st = sQD + (u % NST) * 2 * TK;
+      uint8_t* res = sRes + (uk % RES) * 2 * TQ;
+      const int64_t base = ((int64_t)it.b * p.H + it.h) * p.S;
+      if constexpr (TMA) {
+        if (pw == 0 && ptx::elect_one()) {
+          uint64_t* bar = &full[u % NST];
+          ptx::mbar_expect_tx(bar, 2 * TK + 2 * KT * 4 + (uj == 0 ? 2 * TQ : 0));
+          if (uj == 0) {
+            tma_tile(res, maps, M_K128, p, it.b, it.h, it.x * 128, bar);
+            tma_tile(res + TQ, maps, M_V128, p, it.b, it.h, it.x * 128, bar);
+          }
+          tma_tile(st, maps, M_Q64, p, it.b, it.h, uj * KT, bar);
+          tma_tile(st + TK, maps, M_DO64, p, it.b, it.h, uj * KT, bar);
+          ptx::bulk_load_1d(sL + (u % NST) * KT, p.lse + base + uj * KT, KT * 4, bar);
+          ptx::bulk_load_1d(sD + (u % NST) * KT, p.dsum + base + uj * KT, KT * 4, bar);
+        }
+        __syncwarp();
+        if (++uj == T) { uj = 0; ++uk; }
+        continue;
+      }
+      if (uj == 0) {
+        load_tile<HDP, T_K, 128, NPW>(res, p, it.b, it.h, it.x * 128, pw, lane);
+        load_tile<HDP, T_V, 128, NPW>(res + TQ, p, it.b, it.h, it.x * 128, pw, lane);
+      }
+      load_tile<HDP, T_Q, KT, NPW>(st, p, it.b, it.h, uj * KT, pw, lane);
+      load_tile<HDP, T_DO, KT, NPW>(st + TK, p, it.b, it.h, uj * KT, pw, lane);
+      {
+#pragma unroll
+        for (int i = pw * 32 + lane; i < 2 * KT; i += NPW * 32) {
+          const int q = i & (KT - 1), s2 = uj * KT + q;
+          const bool v = s2 < p.S;
+          cp_async4_zfill((i < KT ? sL : sD) + (u % NST) * KT + q, (i < KT ? p.lse : p.dsum) + base + (v ? s2 : 0), v);
+        }
+      }
+      cp_async_arrive_noinc(&full[u % NST]);
+      if (++uj == T) { uj = 0; ++uk; }
+    }
+    cp_async_wait<0>();
+  } else if (warp_u == 8) {
     // ---------------- MMA-issue warp ----------------
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
     const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
-    const uint64_t dk0 = desc_k128(ptx::smem_u32(sK)), dv0 = desc_k128(ptx::smem_u32(sV));
+    const uint32_t resa = ptx::smem_u32(sRes), qda = ptx::smem_u32(sQD);
     const uint64_t dp0 = desc_k128(ptx::smem_u32(sPT)), ds0 = desc_k128(ptx::smem_u32(sDST));
-    const uint32_t qda = ptx::smem_u32(sQD);
-    for (int j = -1; j < T; ++j) {
-      if (j + 1 < T) {  // S^T(t) = K Q_t^T, dP^T(t) = V dO_t^T into TMEM buffer t & 1
-        const int t = j + 1;
+    int tk = 0, tj = 0, gj = 0;
+    for (int g = -1; g < G; ++g) {
+      const bool next_ready = g + 1 < G && (g < 0 || __shfl_sync(0xffffffffu, (int)ptx::mbar_test_wait(&full[(g + 1) % NST], ((g + 1) / NST) & 1), 0) != 0);
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+      if ((pass == 0) == next_ready && g + 1 < G) {  // S^T(t) = K Q_t^T, dP^T(t) = V dO_t^T into TMEM buffer t & 1
+        const int t = g + 1;
+        MMA_TRACE(2, tk, 32 + tj * 4);
         ptx::mbar_wait(&full[t % NST], (t / NST) & 1);
+        MMA_TRACE(2, tk, 33 + tj * 4);
+        ptx::fence_proxy_async_smem();
         ptx::tc_fence_after();
+        const uint32_t ra = resa + (tk % RES) * 2 * TQ;
+        const uint64_t dk0 = desc_k128(ra), dv0 = desc_k128(ra + TQ);
         const uint64_t dq = desc_k64(qda + (t % NST) * 2 * TK), dd = desc_k64(qda + (t % NST) * 2 * TK + TK);
         const uint32_t ts = tmem + (t & 1) * 128;
 #pragma unroll
@@ -591,114 +706,98 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dkv_tc_kernel(const Params p) 
           ptx::umma_bf16_elect(ts + KT, dv0 + ks * KSTEP_K128, dd + ks * KSTEP_K64, idesc_s, ks > 0);
         }
         ptx::umma_commit_elect(&bar1[t & 1]);
+        if (++tj == T) { tj = 0; ++tk; }
       }
-      if (j >= 0) {  // dV += P^T dO_j, dK += dS^T Q_j: contraction over the 64 queries; Q / dO tiles read MN-major (N = hd)
-        ptx::mbar_wait(&ps_full, j & 1);
+      if (pass == 0 && g >= 0) {  // dV += P^T dO_g, dK += dS^T Q_g: contraction over the 64 queries; Q / dO tiles read MN-major (N = hd)
+        MMA_TRACE(2, g / T, 34 + gj * 4);
+        ptx::mbar_wait(&ps_full, g & 1);
+        MMA_TRACE(2, g / T, 35 + gj * 4);
         ptx::tc_fence_after();
-        const uint64_t dq = desc_mn64(qda + (j % NST) * 2 * TK), dd = desc_mn64(qda + (j % NST) * 2 * TK + TK);
+        const uint64_t dq = desc_mn64(qda + (g % NST) * 2 * TK), dd = desc_mn64(qda + (g % NST) * 2 * TK + TK);
 #pragma unroll
         for (int ks = 0; ks < KT / 16; ++ks) {
-          const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+          const uint32_t acc = (gj > 0 || ks > 0) ? 1u : 0u;
           ptx::umma_bf16_elect(tmem + 256 + HDP, dp0 + ks * KSTEP_K128, dd + ks * KSTEP_MN64, idesc_o, acc);
           ptx::umma_bf16_elect(tmem + 256, ds0 + ks * KSTEP_K128, dq + ks * KSTEP_MN64, idesc_o, acc);
         }
+        ptx::umma_commit_elect(&empty[g % NST]);
         ptx::umma_commit_elect(&bar2);
+        if (++gj == T) gj = 0;
+      }
       }
     }
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tmem_dealloc<512>(tmem);
-    return;
-  }
+  } else {
+    // ---------------- compute warps ----------------
+    const int r = tid & 127, half = tid >> 7;
+    const int trace_item = n_my > 1 ? 1 : 0;
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tDK = tmem + 256 + lane_off, tDV = tmem + 256 + HDP + lane_off;
+    int k = 0, j = 0;
+    Item it = decode_item(p, blockIdx.x, nx);
+    float kbias = 0.f;
 
-  // ---------------- compute warps ----------------
-  const int r = tid & 127, half = tid >> 7;
-  const float* lse = p.lse + ((int64_t)b * p.H + h) * p.S;
-  const float* dsm = p.dsum + ((int64_t)b * p.H + h) * p.S;
-  auto issue_tile = [&](int t) {
-    if (t < T) {
-      uint8_t* st = sQD + (t % NST) * 2 * TK;
-      load_tile<HDP, T_Q, KT>(st, p, b, h, t * KT, warp, lane);
-      load_tile<HDP, T_DO, KT>(st + TK, p, b, h, t * KT, warp, lane);
-      if (tid < 2 * KT) {
-        const int i = tid & (KT - 1), s = t * KT + i;
-        float* dst = (tid < KT ? sL : sD) + (t % NST) * KT + i;
-        if (s < p.S) cp_async4(dst, (tid < KT ? lse : dsm) + s);
-        else *dst = tid < KT ? INFINITY : 0.f;
+    for (int g = 0; g < G; ++g) {
+      if (j == 0) {
+        BWD_TRACE(2, 0);
+        it = decode_item(p, blockIdx.x + k * gridDim.x, nx);
+        kbias = (it.x * 128 + 128 > p.S || (p.kmask != nullptr && it.x * 128 < p.mask_len)) ? key_bias(p, it.b, it.x * 128 + r) : 0.f;
       }
-    }
-    cp_async_commit();
-  };
-  load_tile<HDP, T_K, 128>(sK, p, b, h, kv0, warp, lane);
-  load_tile<HDP, T_V, 128>(sV, p, b, h, kv0, warp, lane);
+      if (j < 8) BWD_TRACE(2, 4 + j * 6);
+      ptx::mbar_wait(&bar1[g & 1], (g >> 1) & 1);
+      ptx::tc_fence_after();
+      if (j < 8) BWD_TRACE(2, 5 + j * 6);
+      if (g >= 1) ptx::mbar_wait(&bar2, (g - 1) & 1);  // dV / dK accumulation of tile g-1 finished: sPT and sDST are free
+      if (j < 8) BWD_TRACE(2, 6 + j * 6);
+      {
+        const float* Lq = sL + (g % NST) * KT + half * 32;
+        const float* Dq = sD + (g % NST) * KT + half * 32;
+        const uint32_t ts = tmem + lane_off + (g & 1) * 128 + half * 32;
+        uint32_t vs[32], vd[32];
+        ptx::tmem_ld32(ts, vs);
+        ptx::tmem_ld32(ts + KT, vd);
+        ptx::tmem_ld_wait();
+        float pv[32], ds[32];
+        const int nq = p.S - (j * KT + half * 32);  // queries of my 32 columns that exist
 #pragma unroll
-  for (int t = 0; t < NST; ++t) issue_tile(t);
-  ATTN_TRACE(2, 1);
-  const float kbias = key_bias(p, b, kv0 + r);
-  ATTN_TRACE(2, 2);
-  cp_async_wait<NST - 1>();  // K, V and tile 0
-  ptx::fence_proxy_async_smem();
-  ptx::mbar_arrive(&full[0]);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  ATTN_TRACE(2, 3);
-  const uint32_t tmem = tmem_slot;
-  const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-  const uint32_t tDK = tmem + 256 + lane_off, tDV = tmem + 256 + HDP + lane_off;
-
-  for (int j = 0; j < T; ++j) {
-    if (j + 1 < T) {
-      cp_async_wait<NST - 3>();  // my part of tile j+1 has landed
+        for (int i = 0; i < 32; ++i) {
+          pv[i] = ex2(fmaf(Lq[i], -LOG2E, (__uint_as_float(vs[i]) + kbias) * p.scale_log2));
+          if (i >= nq) pv[i] = 0.f;
+          ds[i] = pv[i] * (__uint_as_float(vd[i]) - Dq[i]);
+        }
+        store_bf16x32(sPT + r * 16, half * 32, pv);
+        store_bf16x32(sDST + r * 16, half * 32, ds);
+      }
       ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&full[(j + 1) % NST]);
-    }
-    if (j < 8) ATTN_TRACE(2, 4 + j * 6);
-    ptx::mbar_wait(&bar1[j & 1], (j >> 1) & 1);
-    ptx::tc_fence_after();
-    if (j < 8) ATTN_TRACE(2, 5 + j * 6);
-    if (j >= 1) {
-      ptx::mbar_wait(&bar2, (j - 1) & 1);  // dV / dK accumulation of tile j-1 finished: its stage, sPT and sDST are free
-      issue_tile(j + NST - 1);
-    }
-    if (j < 8) ATTN_TRACE(2, 6 + j * 6);
-    {
-      const float* Lq = sL + (j % NST) * KT + half * 32;
-      const float* Dq = sD + (j % NST) * KT + half * 32;
-      const uint32_t ts = tmem + lane_off + (j & 1) * 128 + half * 32;
-      uint32_t vs[32], vd[32];
-      ptx::tmem_ld32(ts, vs);
-      ptx::tmem_ld32(ts + KT, vd);
-      ptx::tmem_ld_wait();
-      float pv[32], ds[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        pv[i] = ex2(fmaf(Lq[i], -LOG2E, (__uint_as_float(vs[i]) + kbias) * p.scale_log2));
-        ds[i] = pv[i] * (__uint_as_float(vd[i]) - Dq[i]);
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&ps_full);
+      if (j < 8) BWD_TRACE(2, 7 + j * 6);
+      if (j == T - 1) {  // item epilogue: dK, dV tiles -> bf16 -> global
+        BWD_TRACE(2, 56);
+        ptx::mbar_wait(&bar2, g & 1);
+        ptx::tc_fence_after();
+        BWD_TRACE(2, 57);
+        bf16* stage = reinterpret_cast<bf16*>(sPT);  // the (now idle) P^T / dS^T tiles
+        tmem_half_to_stage<HDP>(tDK, stage, r, half, p.scale);
+        compute_barrier();
+        store_tile<HDP, O_DK>(stage, p, it.b, it.h, it.x * 128, tid);
+        compute_barrier();
+        tmem_half_to_stage<HDP>(tDV, stage, r, half, 1.f);
+        ptx::tc_fence_before();
+        compute_barrier();
+        store_tile<HDP, O_DV>(stage, p, it.b, it.h, it.x * 128, tid);
+        compute_barrier();  // the staging tile becomes P^T / dS^T again
+        BWD_TRACE(2, 59);
+        j = 0;
+        ++k;
+      } else {
+        ++j;
       }
-      store_bf16x32(sPT + r * 16, half * 32, pv);
-      store_bf16x32(sDST + r * 16, half * 32, ds);
     }
-    ptx::fence_proxy_async_smem();
-    ptx::tc_fence_before();
-    ptx::mbar_arrive(&ps_full);
-    if (j < 8) ATTN_TRACE(2, 7 + j * 6);
   }
-  ATTN_TRACE(2, 56);
-  ptx::mbar_wait(&bar2, (T - 1) & 1);
-  ptx::tc_fence_after();
-  ATTN_TRACE(2, 57);
-  bf16* stage = reinterpret_cast<bf16*>(sQD);
-  tmem_half_to_stage<HDP>(tDK, stage, r, half, p.scale);
-  compute_barrier();
-  store_tile<HDP, O_DK>(stage, p, b, h, kv0, tid);
-  compute_barrier();
-  tmem_half_to_stage<HDP>(tDV, stage, r, half, 1.f);
-  compute_barrier();
-  store_tile<HDP, O_DV>(stage, p, b, h, kv0, tid);
-  ATTN_TRACE(2, 59);
   ptx::tc_fence_before();
   __syncthreads();
+  if (warp_u == 8) ptx::tmem_dealloc<512>(__shfl_sync(0xffffffffu, tmem_slot, 0));
 }
 
 }  // namespace attn_tc
@@ -712,6 +811,51 @@ struct dlb_attn_seg {
   int64_t ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
   int32_t len;
 };
+
+#include <cudaTypedefs.h>
+#include <unordered_map>
+
+namespace {
+struct MapKey {
+  const void* ptr; int64_t rows, ld; int H, hd, box_rows, cprb;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && ld == o.ld && H == o.H && hd == o.hd && box_rows == o.box_rows && cprb == o.cprb;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    for (int64_t v : {k.rows, k.ld, (int64_t)k.H, (int64_t)k.hd, (int64_t)k.box_rows, (int64_t)k.cprb}) h = h * 1000003u ^ std::hash<int64_t>()(v);
+    return h;
+  }
+};
+// head-slice tensor map of a packed bf16 [rows, ld] activation (cached: the training loop reuses its buffers)
+int head_map(CUtensorMap* out, const void* base, int64_t rows, int64_t ld, int H, int hd, int box_rows, int cprb) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+  const MapKey key{base, rows, ld, H, hd, box_rows, cprb};
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return DLB_OK; }
+  if (!enc) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    const bool ok = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess;
+    DLB_REQUIRE(ok, DLB_ERR_DRIVER, "attn_bwd_tc: cuTensorMapEncodeTiled unavailable");
+    enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fp);
+  }
+  cuuint64_t dims[4] = {8, (cuuint64_t)rows, (cuuint64_t)(hd / 8), (cuuint64_t)H};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, 16, (cuuint64_t)hd * 2};
+  cuuint32_t box[4] = {8, (cuuint32_t)box_rows, (cuuint32_t)cprb, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DLB_REQUIRE(r == CUDA_SUCCESS, DLB_ERR_DRIVER, "attn_bwd_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
+  return DLB_OK;
+}
+}  // namespace
 
 static long long* g_attn_trace = nullptr;
 // Development aid: device buffer of 3 x 64 int64 that receives one CTA's SM-clock timeline per kernel (null = off).
@@ -778,15 +922,49 @@ DLB_EXPORT int dlb_attn_bwd_tc(const dlb_attn_seg* segs, int nseg, const float* 
   Params p{};
   int rc = fill_tc_params(p, "attn_bwd_tc", segs, nseg, const_cast<float*>(lse), dsum, kmask, mask_len, B, H, hd, scale, true);
   if (rc) return rc;
-  dim3 grid((p.S + 127) / 128, H, B);
+  const int nitems = ((p.S + 127) / 128) * H * B, T = (p.S + 63) / 64;
+  const int sms = dlb_num_sms();
+  bool use_tma = true;  // TMA producer: every tile lies inside one segment and lse / dsum rows are 16-byte aligned
+  for (int i = 0; i < nseg; ++i) use_tma = use_tma && segs[i].len > 0 && segs[i].len % 128 == 0;
   HDP_SWITCH_TC(hd, {
-    const size_t sm_dq = (size_t)2 * 128 * HDPV * 2 + 4 * 2 * 64 * HDPV * 2 + 16384 + 4 * 64 * 4 + 128 * 4;
-    const size_t sm_dkv = (size_t)2 * 128 * HDPV * 2 + 4 * 2 * 64 * HDPV * 2 + 32768 + 2 * 4 * 64 * 4;
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<HDPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dq);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<HDPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dkv);
+    // resident double-buffering (persistent CTAs) where shared memory allows; otherwise one item per CTA
+    constexpr int RES_DQ = HDPV <= 80 ? 2 : 1, NST_DQ = HDPV <= 96 ? 4 : 3;
+    constexpr int RES_DKV = HDPV <= 96 ? 2 : 1, NST_DKV = 4;
+    const size_t sm_dq = (size_t)RES_DQ * 3 * 128 * HDPV * 2 + (size_t)NST_DQ * 2 * 64 * HDPV * 2 + 16384 + RES_DQ * 128 * 4 + 512 * 4;
+    const size_t sm_dkv = (size_t)RES_DKV * 2 * 128 * HDPV * 2 + (size_t)NST_DKV * 2 * 64 * HDPV * 2 + 32768 + 2 * NST_DKV * 64 * 4;
+    const int grid_dq = (RES_DQ == 2 && T >= NST_DQ && nitems > sms) ? sms : nitems;
+    const int grid_dkv = (RES_DKV == 2 && T >= NST_DKV && nitems > sms) ? sms : nitems;
+    static BwdMaps maps;  // by-value kernel parameter; contents only read on the TMA path
+    if (use_tma) {
+      for (int i = 0; i < nseg; ++i) {
+        const dlb_attn_seg& g = segs[i];
+        const int64_t rows = (int64_t)B * g.len;
+        const struct { int idx; const void* ptr; int64_t ld; int box; } want[M_COUNT] = {
+            {M_Q64, g.q, g.ldq, 64}, {M_Q128, g.q, g.ldq, 128}, {M_K64, g.k, g.ldk, 64}, {M_K128, g.k, g.ldk, 128},
+            {M_V64, g.v, g.ldv, 64}, {M_V128, g.v, g.ldv, 128}, {M_DO64, g.dout, g.lddo, 64}, {M_DO128, g.dout, g.lddo, 128},
+            {M_O128, g.o, g.ldo, 128}};
+        for (const auto& w : want) {
+          rc = head_map(&maps.m[i][w.idx], w.ptr, rows, w.ld, H, hd, w.box, HDPV / 8);
+          if (rc) return rc;
+        }
+      }
+    }
+    cudaError_t e = cudaSuccess;
+    if (use_tma) {
+      e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<HDPV, RES_DQ, NST_DQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dq);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<HDPV, RES_DKV, NST_DKV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dkv);
+    } else {
+      e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<HDPV, RES_DQ, NST_DQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dq);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<HDPV, RES_DKV, NST_DKV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dkv);
+    }
     DLB_REQUIRE(e == cudaSuccess, (int)e, "attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attn_bwd_dq_tc_kernel<HDPV><<<grid, NT, sm_dq, stream>>>(p);
-    attn_bwd_dkv_tc_kernel<HDPV><<<grid, NT, sm_dkv, stream>>>(p);
+    if (use_tma) {
+      attn_bwd_dq_tc_kernel<HDPV, RES_DQ, NST_DQ, true><<<grid_dq, NT, sm_dq, stream>>>(p, maps);
+      attn_bwd_dkv_tc_kernel<HDPV, RES_DKV, NST_DKV, true><<<grid_dkv, NT, sm_dkv, stream>>>(p, maps);
+    } else {
+      attn_bwd_dq_tc_kernel<HDPV, RES_DQ, NST_DQ, false><<<grid_dq, NT, sm_dq, stream>>>(p, maps);
+      attn_bwd_dkv_tc_kernel<HDPV, RES_DKV, NST_DKV, false><<<grid_dkv, NT, sm_dkv, stream>>>(p, maps);
+    }
   });
   dlb_count_launch(2);
   return dlb_check_launch("attn_bwd_tc");

@@ -27,10 +27,11 @@ torch.cuda.synchronize()
 lib.dlb_attn_set_trace(None)
 t = trace.cpu().tolist()
 for k, name in enumerate(("fwd", "dq", "dkv")):
-    pts = [(i, v) for i, v in enumerate(t[k * 64:(k + 1) * 64]) if v]
-    t0 = pts[0][1]
-    print(name, "total cycles", pts[-1][1] - t0)
+    pts = sorted([(v, i) for i, v in enumerate(t[k * 64:(k + 1) * 64]) if v])
+    t0 = pts[0][0]
+    print(name, "total cycles", pts[-1][0] - t0, "(slots 32-55: MMA warp; others: compute thread 0)")
     prev = t0
-    for i, v in pts:
-        print(f"   slot {i:2d}  +{v - prev:6d}   @{v - t0:7d}")
+    for v, i in pts:
+        who = "mma " if 32 <= i < 56 else "cmp "
+        print(f"   {who} slot {i:2d}  +{v - prev:6d}   @{v - t0:7d}")
         prev = v

@@ -32,6 +32,9 @@ CASES = [
     (1, 2, 128, 0, 100, False),
     (2, 2, 32, 5, 20, True),
     (2, 4, 72, 100, 300, True),   # S = 400: four 128-key tiles, ragged tail
+    (11, 8, 72, 0, 256, False),   # 176 work items > 148 SMs: persistent backward CTAs, uneven items per CTA
+    (7, 6, 64, 40, 300, True),    # 126 items x ragged S = 340 (6 streamed tiles): one item per CTA, long ring
+    (10, 6, 64, 72, 256, True),   # 180 items, S = 328: persistent + mask + partial tiles
 ]
 
 
