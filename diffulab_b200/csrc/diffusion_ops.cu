@@ -252,6 +252,54 @@ __global__ void euler_step_kernel(const float* __restrict__ x, const TV* __restr
   }
 }
 
+// One reverse step of the Gaussian samplers (reference samplers/gaussian_diffusion/ddpm.py `step`, ddim.py `step`):
+// x0 from the model output (epsilon / xstart / xprev parameterisation, optional clamp), posterior mean, x_{t-1} =
+// mean + mask * std * noise and the per-element log-probability, in one pass. All schedule-dependent scalars come
+// from a per-timestep fp32 table built on the host from the float64 schedule exactly as `extract_into_tensor` yields
+// them (GS_* columns); arithmetic keeps the reference's operation order (no FMA contraction) so results agree to ~1 ulp.
+enum { GS_RSAB = 0, GS_CEPS, GS_RC1, GS_C2C1, GS_C1, GS_C2, GS_VAR, GS_STD, GS_MASK, GS_EDEN, GS_SABP, GS_SA, GS_SB, GS_ABP, GS_COLS = 16 };
+template <typename TP>
+__global__ void gaussian_step_kernel(const TP* __restrict__ pred, const float* __restrict__ xt, const float* __restrict__ noise,
+                                     const float* __restrict__ table, const int* __restrict__ t, int sampler, int mean_type,
+                                     int clamp, float eta, int64_t per_sample, float* __restrict__ x_prev,
+                                     float* __restrict__ x0_out, float* __restrict__ mean_out, float* __restrict__ logprob) {
+  const int b = blockIdx.y;
+  const float* c = table + (int64_t)t[b] * GS_COLS;
+  const float r_sab = c[GS_RSAB], c_eps = c[GS_CEPS], r_c1 = c[GS_RC1], c2c1 = c[GS_C2C1], c1 = c[GS_C1], c2 = c[GS_C2];
+  const float var = c[GS_VAR], stdv = c[GS_STD], mask = c[GS_MASK], e_den = c[GS_EDEN], sabp = c[GS_SABP], abp = c[GS_ABP];
+  const float sigma = __fmul_rn(__fmul_rn(eta, c[GS_SA]), c[GS_SB]);
+  const float dir = sqrtf(__fsub_rn(__fsub_rn(1.f, abp), __fmul_rn(sigma, sigma)));
+  const float vs = fmaxf(var, 1e-20f);
+  const float two_vs = __fmul_rn(2.f, vs), lconst = __fmul_rn(logf(__fmul_rn(6.283185307179586f, vs)), 0.5f);
+  const float two_s2 = __fmul_rn(2.f, __fmul_rn(sigma, sigma)), lsig = logf(sigma), lhalf = __fmul_rn(0.5f, logf(6.283185307179586f));
+  const int64_t base = (int64_t)b * per_sample;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_sample; i += (int64_t)gridDim.x * blockDim.x) {
+    const float p = (float)pred[base + i], x = xt[base + i], nz = noise[base + i];
+    float x0;
+    if (mean_type == 0) x0 = __fsub_rn(__fmul_rn(r_sab, x), __fmul_rn(c_eps, p));
+    else if (mean_type == 1) x0 = p;
+    else x0 = __fsub_rn(__fmul_rn(r_c1, p), __fmul_rn(c2c1, x));
+    if (clamp && x0 == x0) x0 = fminf(fmaxf(x0, -1.f), 1.f);  // NaN propagates, like torch.clamp
+    float mean, xp, lp;
+    if (sampler == 0) {
+      mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, x));
+      xp = __fadd_rn(mean, __fmul_rn(__fmul_rn(mask, nz), stdv));
+      const float d = __fsub_rn(xp, mean);
+      lp = __fmul_rn(__fsub_rn(__fdiv_rn(-__fmul_rn(d, d), two_vs), lconst), mask);
+    } else {
+      const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(r_sab, x), x0), e_den);
+      mean = __fadd_rn(__fmul_rn(x0, sabp), __fmul_rn(dir, eps));
+      xp = __fadd_rn(mean, __fmul_rn(__fmul_rn(mask, sigma), nz));
+      const float d = __fsub_rn(xp, mean);
+      lp = -__fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(d, d), two_s2), lsig), lhalf);
+    }
+    x_prev[base + i] = xp;
+    x0_out[base + i] = x0;
+    mean_out[base + i] = mean;
+    if (logprob) logprob[base + i] = lp;
+  }
+}
+
 // torch.optim.AdamW (no amsgrad, no maximize): p *= 1 - lr*wd; m,v update; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).
 // Also refreshes the bf16 shadow copy used by the GEMMs and (optionally) the EMA copy.
 __device__ __forceinline__ void adamw_one(float& pi, float gi, float& mi, float& vi, float lr, float beta1, float beta2,
@@ -401,6 +449,24 @@ DLB_EXPORT int dlb_euler_step(const float* x, const void* vc, const void* vu, in
     euler_step_kernel<float><<<grid_for(n), 256, 0, stream>>>(x, (const float*)vc, (const float*)vu, guidance, dt, t_curr, x_prev, x0_est, v_out, n);
   dlb_count_launch();
   return dlb_check_launch("euler_step");
+}
+
+// table: [n_steps, 16] fp32 (columns GS_*), t: [B] int32 timestep indices into it. sampler 0 = DDPM, 1 = DDIM (eta);
+// mean_type 0 = epsilon, 1 = xstart, 2 = xprev; pred_dtype 0 = bf16, 1 = fp32; logprob may be null.
+DLB_EXPORT int dlb_gaussian_step(const void* pred, int pred_dtype, const float* xt, const float* noise, const float* table,
+                                 const int* t, int sampler, int mean_type, int clamp, float eta, int64_t B, int64_t per_sample,
+                                 float* x_prev, float* x0, float* mean, float* logprob, cudaStream_t stream) {
+  DLB_REQUIRE(B > 0 && B < 65536 && per_sample > 0, DLB_ERR_SHAPE, "gaussian_step: bad shape B=%lld per_sample=%lld", (long long)B, (long long)per_sample);
+  DLB_REQUIRE((sampler == 0 || sampler == 1) && mean_type >= 0 && mean_type <= 2, DLB_ERR_UNSUPPORTED, "gaussian_step: bad sampler / mean_type");
+  int gx = (int)((per_sample + 255) / 256);
+  if (gx > 1024) gx = 1024;
+  dim3 grid(gx, (unsigned)B);
+  if (pred_dtype == 0)
+    gaussian_step_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)pred, xt, noise, table, t, sampler, mean_type, clamp, eta, per_sample, x_prev, x0, mean, logprob);
+  else
+    gaussian_step_kernel<float><<<grid, 256, 0, stream>>>((const float*)pred, xt, noise, table, t, sampler, mean_type, clamp, eta, per_sample, x_prev, x0, mean, logprob);
+  dlb_count_launch();
+  return dlb_check_launch("gaussian_step");
 }
 
 DLB_EXPORT int dlb_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, float* ema, float ema_decay,

@@ -1,6 +1,8 @@
 from .diffuser import Diffuser
 from .diffusion import Diffusion, SamplingOutput
 from .flow import Flow
-from .samplers import Euler, FlowSampler, Sampler, StepResult
+from .gaussian import GaussianDiffusion, space_timesteps
+from .samplers import DDIM, DDPM, Euler, FlowSampler, GaussianSampler, Sampler, StepResult
 
-__all__ = ["Diffuser", "Diffusion", "SamplingOutput", "Flow", "Euler", "FlowSampler", "Sampler", "StepResult"]
+__all__ = ["Diffuser", "Diffusion", "SamplingOutput", "Flow", "GaussianDiffusion", "space_timesteps", "Euler", "DDPM", "DDIM",
+           "FlowSampler", "GaussianSampler", "Sampler", "StepResult"]

@@ -10,10 +10,11 @@ from ..denoisers.common import Denoiser, ModelInput
 from ..losses.common import LossFunction
 from .diffusion import Diffusion, SamplingOutput
 from .flow import Flow
+from .gaussian import GaussianDiffusion
 
 
 class Diffuser:
-    model_registry: dict[str, type[Diffusion]] = {"rectified_flow": Flow}
+    model_registry: dict[str, type[Diffusion]] = {"rectified_flow": Flow, "gaussian_diffusion": GaussianDiffusion}
 
     def __init__(self, denoiser: Denoiser, sampling_method: str, model_type: str = "rectified_flow", n_steps: int = 1000,
                  vision_tower: Any | None = None, extra_args: dict[str, Any] = {}, extra_losses: list[LossFunction] = []):

@@ -554,6 +554,24 @@ def mse_bwd(pred: Tensor, x0: Tensor | None, eps: Tensor, gout: Tensor | None, x
     return dpred
 
 
+def gaussian_step(pred: Tensor, xt: Tensor, noise: Tensor, table: Tensor, t: Tensor, sampler: int, mean_type: int, clamp: bool,
+                  eta: float, want_logprob: bool) -> tuple[Tensor, Tensor, Tensor, Tensor | None]:
+    """One fused DDPM (sampler 0) / DDIM (sampler 1) reverse step -> (x_prev, x0, mean, logprob)."""
+    _req(xt, F32, "xt")
+    _req(noise, F32, "noise")
+    _req(table, F32, "table")
+    if t.dtype != torch.int32 or not t.is_contiguous() or not t.is_cuda:
+        raise ValueError("gaussian_step: timesteps must be a contiguous int32 CUDA tensor")
+    pred = pred.contiguous()
+    B = xt.shape[0]
+    x_prev, x0, mean = torch.empty_like(xt), torch.empty_like(xt), torch.empty_like(xt)
+    logprob = torch.empty_like(xt) if want_logprob else None
+    _lib_call("dlb_gaussian_step", pred.data_ptr(), _dt(pred), xt.data_ptr(), noise.data_ptr(), table.data_ptr(), t.data_ptr(),
+              int(sampler), int(mean_type), int(bool(clamp)), float(eta), B, xt.numel() // B, x_prev.data_ptr(), x0.data_ptr(),
+              mean.data_ptr(), _ptr(logprob), _stream())
+    return x_prev, x0, mean, logprob
+
+
 def repa_cos_fwd(s: Tensor, z: Tensor, coeff: float) -> Tensor:
     _req(s, BF16, "s")
     _req(z, F32, "z")

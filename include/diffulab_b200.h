@@ -190,6 +190,15 @@ int dlb_restore_rows_bwd(const void* dy, const int64_t* idx, const int32_t* inv,
 /* Euler step + optional CFG combine (samplers/flow/euler.py:37-39; flow.py:256-260) */
 int dlb_euler_step(const float* x, const void* vc, const void* vu, int v_dtype, float guidance, float t_curr,
                    float t_prev, float* x_prev, float* x0_est, float* v_out, int64_t n, dlb_stream_t stream);
+
+/* One reverse step of the Gaussian samplers, fused: replaces DDPM.step / DDIM.step
+ * (reference diffuse/samplers/gaussian_diffusion/ddpm.py `_get_p_mean_var` + `step`, ddim.py:27-103).
+ * table [n_steps,16] fp32 per-timestep coefficients (columns: 1/sqrt(ab), sqrt(1-ab)/sqrt(ab), 1/c1, c2/c1, c1, c2, var,
+ * exp(0.5 logvar), [t>0], sqrt(1/ab-1), sqrt(ab_prev), sqrt((1-ab_prev)/(1-ab)), sqrt(1-ab/ab_prev), ab_prev, 0, 0);
+ * t [B] int32; sampler 0 DDPM / 1 DDIM(eta); mean_type 0 epsilon / 1 xstart / 2 xprev; logprob nullable. */
+int dlb_gaussian_step(const void* pred, int pred_dtype, const float* xt, const float* noise, const float* table,
+                      const int* t, int sampler, int mean_type, int clamp, float eta, int64_t B, int64_t per_sample,
+                      float* x_prev, float* x0, float* mean, float* logprob, dlb_stream_t stream);
 /* torch.optim.AdamW step over a flat buffer (+ bf16 shadow, + optional EMA) (base_trainer.py:149-153) */
 int dlb_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, float* ema, float ema_decay,
                    int64_t n, float lr, float beta1, float beta2, float eps, float wd, int64_t step, float grad_scale,

@@ -1,0 +1,71 @@
+"""Host logic of the Gaussian-diffusion drop-ins (no GPU): schedules, respacing, timestep_map and the float32
+coefficient tables, against the reference's own outputs in tests/golden/gaussian.pt."""
+import os
+
+import pytest
+import torch
+
+
+@pytest.fixture(scope="module")
+def fx():
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "gaussian.pt"), weights_only=False)
+
+
+def test_schedules_and_respacing_match_reference(fx):
+    from diffulab_b200 import GaussianDiffusion
+
+    for tb in fx["tables"]:
+        gd = GaussianDiffusion(**tb["kw"])
+        if "set_steps" in tb:
+            n, sched, sec = tb["set_steps"]
+            gd.set_steps(n, schedule=sched, section_counts=sec)
+            assert gd.steps == n
+        assert gd.timestep_map == tb["timestep_map"]
+        assert torch.equal(gd.betas, tb["betas"]) and gd.betas.dtype == tb["betas"].dtype
+        assert torch.equal(gd.alphas_bar, tb["alphas_bar"])
+
+
+def test_coefficient_table_rows_are_what_the_reference_extracts(fx):
+    """Row t of the sampler table == the per-sample float32 scalars the oracle (pinned on the reference) derives."""
+    from diffulab_b200 import GaussianDiffusion
+    from oracle import gaussian_oracle as G
+
+    gd = GaussianDiffusion(n_steps=1000, sampling_method="ddpm", sampler_parameters={"var_type": "fixed_large"})
+    T = G.Tables(G.variance_schedule(1000))
+    tab = gd.sampler._table
+    t = torch.tensor([0, 1, 2, 500, 999])
+    ex = lambda a: a[t].float()  # noqa: E731
+    assert torch.equal(tab[t, 0], 1.0 / ex(T.sqrt_ab))
+    assert torch.equal(tab[t, 1], (1 - ex(T.ab)).sqrt() / ex(T.sqrt_ab))
+    assert torch.equal(tab[t, 4], ex(T.c1)) and torch.equal(tab[t, 5], ex(T.c2))
+    seq = torch.cat([T.post_var[1:2], T.betas[1:]])
+    assert torch.equal(tab[t, 6], ex(seq)) and torch.equal(tab[t, 7], torch.exp(0.5 * ex(torch.log(seq))))
+    assert tab[0, 8] == 0 and tab[1, 8] == 1
+    assert torch.equal(tab[t, 10], ex(T.ab_prev).sqrt())
+
+
+def test_space_timesteps_and_errors():
+    from diffulab_b200.diffuse import space_timesteps
+    from diffulab_b200 import DDPM, GaussianDiffusion
+
+    assert space_timesteps(1000, 10, ddim=True) == set(range(0, 1000, 100))  # the reference's own docstring example
+    assert space_timesteps(300, "10,10,10") == space_timesteps(300, "10,10,10")
+    assert len(space_timesteps(1000, 50)) == 50
+    with pytest.raises(ValueError):
+        space_timesteps(10, 11)
+    with pytest.raises(ValueError):
+        GaussianDiffusion(sampling_method="euler")
+    with pytest.raises(ValueError):
+        DDPM(mean_type="velocity")
+    with pytest.raises(NotImplementedError):
+        DDPM(var_type="learned_range")
+    t = GaussianDiffusion(n_steps=100).draw_timesteps(64)
+    assert t.dtype == torch.int32 and t.shape == (64,) and int(t.min()) >= 0 and int(t.max()) < 100
+
+
+def test_no_cpu_fallback():
+    from diffulab_b200 import GaussianDiffusion
+
+    gd = GaussianDiffusion(n_steps=10)
+    with pytest.raises((ValueError, RuntimeError)):
+        gd.add_noise(torch.zeros(2, 1, 4, 4), torch.tensor([1, 2], dtype=torch.int32), torch.zeros(2, 1, 4, 4))
