@@ -300,6 +300,28 @@ __global__ void gaussian_step_kernel(const TP* __restrict__ pred, const float* _
   }
 }
 
+// Euler-Maruyama flow step (reference samplers/flow/euler_meruyama.py:24-57):
+//   mean = x - (v + c (x + (1 - t) v)) dt,  c = sigma^2 / (2 t);  x_prev = mean + std * noise (or a given x_prev);
+//   x0_est = x - v t;  logprob = -((x_prev - mean)^2 / (2 std^2) + log std + 0.5 log 2 pi).  fp32, reference operation order.
+template <typename TV>
+__global__ void euler_maruyama_kernel(const float* __restrict__ x, const TV* __restrict__ v, const float* __restrict__ noise,
+                                      const float* __restrict__ x_prev_in, float c, float one_minus_t, float dt, float t_curr,
+                                      float stdv, float* __restrict__ x_prev, float* __restrict__ mean_out,
+                                      float* __restrict__ x0_est, float* __restrict__ logprob, int64_t n) {
+  const float two_s2 = __fmul_rn(2.f, __fmul_rn(stdv, stdv)), lstd = logf(stdv), lhalf = __fmul_rn(0.5f, logf(6.283185307179586f));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float xi = x[i], vi = (float)v[i];
+    const float inner = __fmul_rn(c, __fadd_rn(xi, __fmul_rn(one_minus_t, vi)));
+    const float mean = __fsub_rn(xi, __fmul_rn(__fadd_rn(vi, inner), dt));
+    const float xp = x_prev_in ? x_prev_in[i] : __fadd_rn(mean, __fmul_rn(stdv, noise[i]));
+    const float d = __fsub_rn(xp, mean);
+    x_prev[i] = xp;
+    mean_out[i] = mean;
+    x0_est[i] = __fsub_rn(xi, __fmul_rn(vi, t_curr));
+    logprob[i] = -__fadd_rn(__fadd_rn(__fdiv_rn(__fmul_rn(d, d), two_s2), lstd), lhalf);
+  }
+}
+
 // torch.optim.AdamW (no amsgrad, no maximize): p *= 1 - lr*wd; m,v update; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).
 // Also refreshes the bf16 shadow copy used by the GEMMs and (optionally) the EMA copy.
 __device__ __forceinline__ void adamw_one(float& pi, float gi, float& mi, float& vi, float lr, float beta1, float beta2,
@@ -467,6 +489,20 @@ DLB_EXPORT int dlb_gaussian_step(const void* pred, int pred_dtype, const float* 
     gaussian_step_kernel<float><<<grid, 256, 0, stream>>>((const float*)pred, xt, noise, table, t, sampler, mean_type, clamp, eta, per_sample, x_prev, x0, mean, logprob);
   dlb_count_launch();
   return dlb_check_launch("gaussian_step");
+}
+
+// exactly one of noise / x_prev_in is non-null; v_dtype 0 = bf16, 1 = fp32; scalars as computed by the caller in double
+// and rounded to float (python-scalar semantics of the reference expression)
+DLB_EXPORT int dlb_euler_maruyama_step(const float* x, const void* v, int v_dtype, const float* noise, const float* x_prev_in,
+                                       float c, float one_minus_t, float dt, float t_curr, float stdv, float* x_prev,
+                                       float* mean, float* x0_est, float* logprob, int64_t n, cudaStream_t stream) {
+  DLB_REQUIRE(n > 0 && ((noise == nullptr) != (x_prev_in == nullptr)), DLB_ERR_SHAPE, "euler_maruyama_step: need exactly one of noise / x_prev");
+  if (v_dtype == 0)
+    euler_maruyama_kernel<bf16><<<grid_for(n), 256, 0, stream>>>(x, (const bf16*)v, noise, x_prev_in, c, one_minus_t, dt, t_curr, stdv, x_prev, mean, x0_est, logprob, n);
+  else
+    euler_maruyama_kernel<float><<<grid_for(n), 256, 0, stream>>>(x, (const float*)v, noise, x_prev_in, c, one_minus_t, dt, t_curr, stdv, x_prev, mean, x0_est, logprob, n);
+  dlb_count_launch();
+  return dlb_check_launch("euler_maruyama_step");
 }
 
 DLB_EXPORT int dlb_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, float* ema, float ema_decay,

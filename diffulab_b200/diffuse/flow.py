@@ -14,7 +14,7 @@ from .. import ops
 from ..denoisers.common import Denoiser, ModelInput, ModelOutput
 from ..losses.common import LossFunction
 from .diffusion import Diffusion, SamplingOutput
-from .samplers import Euler, StepResult
+from .samplers import Euler, EulerMaruyama, StepResult
 
 
 class _FlowLossFn(torch.autograd.Function):
@@ -33,12 +33,12 @@ class _FlowLossFn(torch.autograd.Function):
 
 
 class Flow(Diffusion):
-    sampler_registry = {"euler": Euler}
+    sampler_registry = {"euler": Euler, "euler_maruyama": EulerMaruyama}
 
     def __init__(
         self,
         n_steps: int = 50,
-        sampling_method: Literal["euler"] = "euler",
+        sampling_method: Literal["euler", "euler_maruyama"] = "euler",
         schedule: Literal["linear"] = "linear",
         latent_diffusion: bool = False,
         logits_normal: bool = False,
@@ -145,6 +145,9 @@ class Flow(Diffusion):
             model_inputs["x"] = torch.randn(data_shape, device=device, dtype=dtype)
         all_x0: list[Tensor] = []
         all_xt: list[Tensor] = [model_inputs["x"]]
+        all_xt_mean: list[Tensor] = []
+        all_xt_std: list[Tensor] = []
+        all_logprobs: list[Tensor] = []
         for t_curr, t_prev in zip(self.timesteps[:-1], self.timesteps[1:]):
             step_output = self.one_step_denoise(model, model_inputs, t_curr=t_curr, t_prev=t_prev, guidance_scale=guidance_scale,
                                                 sampler_args=sampler_args)
@@ -152,10 +155,22 @@ class Flow(Diffusion):
             if return_intermediates:
                 all_xt.append(step_output["x_prev"])
                 all_x0.append(step_output["estimated_x0"])
+                if "x_prev_mean" in step_output:
+                    all_xt_mean.append(step_output["x_prev_mean"])
+                if "x_prev_std" in step_output:
+                    all_xt_std.append(step_output["x_prev_std"])
+                if "logprob" in step_output:
+                    all_logprobs.append(step_output["logprob"])
         if clamp_x:
             model_inputs["x"] = model_inputs["x"].clamp(-1, 1)
         out: SamplingOutput = {"x": model_inputs["x"]}
         if return_intermediates:
             out["xt"] = torch.stack(all_xt, dim=1)
             out["estimated_x0"] = torch.stack(all_x0, dim=1)
+            if all_xt_mean:
+                out["xt_mean"] = torch.stack(all_xt_mean, dim=1)
+            if all_xt_std:
+                out["xt_std"] = torch.stack(all_xt_std, dim=0)  # dim 0, as in the reference (scalar per step)
+            if all_logprobs:
+                out["logprob"] = torch.stack(all_logprobs, dim=1)
         return out

@@ -1,5 +1,6 @@
 from .common import FlowSampler, Sampler, StepResult
 from .euler import Euler
+from .euler_maruyama import EulerMaruyama
 from .gaussian import DDIM, DDPM, GaussianSampler
 
-__all__ = ["Sampler", "FlowSampler", "GaussianSampler", "StepResult", "Euler", "DDPM", "DDIM"]
+__all__ = ["Sampler", "FlowSampler", "GaussianSampler", "StepResult", "Euler", "EulerMaruyama", "DDPM", "DDIM"]

@@ -554,6 +554,20 @@ def mse_bwd(pred: Tensor, x0: Tensor | None, eps: Tensor, gout: Tensor | None, x
     return dpred
 
 
+def euler_maruyama_step(x: Tensor, v: Tensor, noise: Tensor | None, x_prev_in: Tensor | None, c: float, one_minus_t: float, dt: float,
+                        t_curr: float, std: float) -> tuple[Tensor, Tensor, Tensor, Tensor]:
+    """-> (x_prev, x_prev_mean, estimated_x0, logprob); exactly one of noise / x_prev_in."""
+    _req(x, F32, "x")
+    v = v.contiguous()
+    for name, t in (("noise", noise), ("x_prev", x_prev_in)):
+        if t is not None:
+            _req(t, F32, name)
+    x_prev, mean, x0, logprob = (torch.empty_like(x) for _ in range(4))
+    _lib_call("dlb_euler_maruyama_step", x.data_ptr(), v.data_ptr(), _dt(v), _ptr(noise), _ptr(x_prev_in), float(c), float(one_minus_t),
+              float(dt), float(t_curr), float(std), x_prev.data_ptr(), mean.data_ptr(), x0.data_ptr(), logprob.data_ptr(), x.numel(), _stream())
+    return x_prev, mean, x0, logprob
+
+
 def gaussian_step(pred: Tensor, xt: Tensor, noise: Tensor, table: Tensor, t: Tensor, sampler: int, mean_type: int, clamp: bool,
                   eta: float, want_logprob: bool) -> tuple[Tensor, Tensor, Tensor, Tensor | None]:
     """One fused DDPM (sampler 0) / DDIM (sampler 1) reverse step -> (x_prev, x0, mean, logprob)."""

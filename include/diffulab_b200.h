@@ -199,6 +199,12 @@ int dlb_euler_step(const float* x, const void* vc, const void* vu, int v_dtype, 
 int dlb_gaussian_step(const void* pred, int pred_dtype, const float* xt, const float* noise, const float* table,
                       const int* t, int sampler, int mean_type, int clamp, float eta, int64_t B, int64_t per_sample,
                       float* x_prev, float* x0, float* mean, float* logprob, dlb_stream_t stream);
+
+/* Euler-Maruyama flow step with log-probability (reference diffuse/samplers/flow/euler_meruyama.py:24-57), one launch.
+ * c = sigma^2/(2 t_curr), stdv = sigma sqrt(t_curr - t_prev); exactly one of noise / x_prev_in is non-null. */
+int dlb_euler_maruyama_step(const float* x, const void* v, int v_dtype, const float* noise, const float* x_prev_in, float c,
+                            float one_minus_t, float dt, float t_curr, float stdv, float* x_prev, float* mean,
+                            float* x0_est, float* logprob, int64_t n, dlb_stream_t stream);
 /* torch.optim.AdamW step over a flat buffer (+ bf16 shadow, + optional EMA) (base_trainer.py:149-153) */
 int dlb_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, float* ema, float ema_decay,
                    int64_t n, float lr, float beta1, float beta2, float eps, float wd, int64_t step, float grad_scale,

@@ -138,3 +138,14 @@ def ddim_step(betas, mean_type, pred, xt, t, noise, clamp=False, eta=0.0):
         out["x_prev_std"] = sigma
         out["logprob"] = -((x_prev - mean) ** 2 / (2 * sigma**2) + torch.log(sigma) + 0.5 * torch.log(torch.tensor(2 * torch.pi)))
     return out
+
+
+def euler_maruyama_step(eta: float, tmax: float, x_t, v, t_curr: float, t_prev: float, noise=None, x_prev=None):
+    """samplers/flow/euler_meruyama.py:24-57 (python-float schedule scalars, fp32 tensors)."""
+    sigma = ((t_curr / (1 - min(t_curr, tmax))) ** 0.5) * eta
+    mean = x_t - (v + sigma**2 / (2 * t_curr) * (x_t + (1 - t_curr) * v)) * (t_curr - t_prev)
+    std = torch.tensor(sigma * (t_curr - t_prev) ** 0.5)
+    if x_prev is None:
+        x_prev = mean + std * noise
+    logprob = -((x_prev - mean) ** 2 / (2 * std**2) + torch.log(std) + 0.5 * torch.log(torch.tensor(2 * torch.pi)))
+    return {"x_prev": x_prev, "x_prev_mean": mean, "x_prev_std": std, "estimated_x0": x_t - v * t_curr, "logprob": logprob}

@@ -100,6 +100,35 @@ def main():
     loss = gd.compute_loss(model, {"x": x.clone()}, t, noise)["loss"]
     loss.backward()
     fx["loss"] = {"x": x, "noise": noise, "t": t, "loss": loss.detach(), "grad_a": model.a.grad.clone(), "grad_b": model.b.grad.clone()}
+    # ---- Euler-Maruyama flow sampler (samplers/flow/euler_meruyama.py) + a short stochastic Flow.denoise
+    from diffulab.diffuse.modelizations.flow import Flow
+
+    fx["em_steps"] = []
+    for eta, n, idx, given in ((0.7, 10, 0, False), (0.7, 10, 4, False), (0.3, 25, 24, False), (1.0, 10, 9, True)):
+        fl = Flow(n_steps=n, sampling_method="euler_maruyama", sampler_parameters={"eta": eta})
+        x_t = torch.randn(3, 4, 8, 8, generator=g)
+        v = torch.randn(3, 4, 8, 8, generator=g)
+        t_curr, t_prev = fl.timesteps[idx], fl.timesteps[idx + 1]
+        xp_in = torch.randn(3, 4, 8, 8, generator=g) if given else None
+        seed += 1
+        torch.manual_seed(seed)
+        out = fl.sampler.step(x_t, v, t_curr, t_prev, x_prev=xp_in)
+        torch.manual_seed(seed)
+        noise_ = torch.randn_like(x_t)
+        fx["em_steps"].append({"eta": eta, "n": n, "idx": idx, "x_t": x_t, "v": v, "x_prev_in": xp_in, "noise": noise_,
+                               "t_curr": t_curr, "t_prev": t_prev, "out": {k: v_.clone() for k, v_ in out.items()}})
+
+    class ToyFlow(ToyDenoiser):
+        def forward(self, x, timesteps, p=0.0, **_):
+            s = torch.sin(timesteps.float() * 3.0).view(-1, 1, 1, 1)
+            return {"x": self.a * x + self.b * s * (0.5 if p == 1 else 1.0)}
+
+    fl = Flow(n_steps=8, sampling_method="euler_maruyama", sampler_parameters={"eta": 0.5})
+    x0 = torch.randn(2, 1, 8, 8, generator=g)
+    torch.manual_seed(4321)
+    out = fl.denoise(ToyFlow(), {"x": x0.clone()}, use_tqdm=False, guidance_scale=1.5, return_intermediates=True)
+    fx["em_denoise"] = {"n": 8, "eta": 0.5, "guidance": 1.5, "x_init": x0, "seed": 4321,
+                        "out": {k: v_.clone() for k, v_ in out.items()}}
     torch.save(fx, OUT)
     print("wrote", OUT, os.path.getsize(OUT) // 1024, "KiB;", len(fx["steps"]), "step cases")
 

@@ -125,3 +125,45 @@ def test_diffuser_registry_builds_gaussian(cuda_device):
 
     d = Diffuser(Toy().cuda(), sampling_method="ddim", model_type="gaussian_diffusion", n_steps=25)
     assert isinstance(d.diffusion, GaussianDiffusion) and d.diffusion.sampler.name == "ddim"
+
+
+def test_euler_maruyama_steps_match_reference(cuda_device, fx):
+    from diffulab_b200 import Flow
+
+    for c in fx["em_steps"]:
+        fl = Flow(n_steps=c["n"], sampling_method="euler_maruyama", sampler_parameters={"eta": c["eta"]})
+        assert fl.timesteps[c["idx"]] == c["t_curr"] and fl.timesteps[c["idx"] + 1] == c["t_prev"]
+        orig = torch.randn_like
+        torch.randn_like = lambda t, *a, **k: c["noise"].to(t.device)
+        try:
+            given = None if c["x_prev_in"] is None else c["x_prev_in"].cuda()
+            out = fl.sampler.step(c["x_t"].cuda(), c["v"].cuda(), c["t_curr"], c["t_prev"], x_prev=given)
+        finally:
+            torch.randn_like = orig
+        assert set(out) == set(c["out"])
+        for k, v in c["out"].items():
+            close(out[k], v, f"euler_maruyama eta={c['eta']} idx={c['idx']}:{k}", rtol=2e-5 if k == "logprob" else 2e-6, atol=2e-5 if k == "logprob" else 2e-6)
+
+
+def test_euler_maruyama_denoise_matches_reference(cuda_device, fx):
+    from diffulab_b200 import Flow
+
+    c = fx["em_denoise"]
+
+    class ToyFlow(Toy):
+        def forward(self, x, timesteps, p=0.0, **_):
+            s = torch.sin(timesteps.float() * 3.0).view(-1, 1, 1, 1)
+            return {"x": self.a * x + self.b * s * (0.5 if p == 1 else 1.0)}
+
+    fl = Flow(n_steps=c["n"], sampling_method="euler_maruyama", sampler_parameters={"eta": c["eta"]})
+    torch.manual_seed(c["seed"])
+    orig = torch.randn_like
+    torch.randn_like = lambda t, *a, **k: torch.randn(t.shape).to(t.device)
+    try:
+        out = fl.denoise(ToyFlow().cuda(), {"x": c["x_init"].cuda()}, use_tqdm=False, guidance_scale=c["guidance"], return_intermediates=True)
+    finally:
+        torch.randn_like = orig
+    assert set(out) == set(c["out"])
+    for k, v in c["out"].items():
+        assert tuple(out[k].shape) == tuple(v.shape), (k, out[k].shape, v.shape)
+        close(out[k], v, f"euler_maruyama denoise {k}", rtol=1e-4, atol=1e-4)
