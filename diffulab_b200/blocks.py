@@ -275,8 +275,11 @@ def attn_bwd(dprojs: list[Tensor | None], streams: list[StreamSpec], rope: RopeC
 
 
 def mlp_fwd(h: Tensor, w_up: Tensor, w_down: Tensor, save: dict) -> Tensor:
-    u = ops.gemm(h, wb(w_up))
-    s = ops.swiglu_fwd(u)
+    if (w_up.shape[0] // 2) % 128 == 0:
+        u, s = ops.gemm_swiglu(h, wb(w_up))  # SwiGLU in the fc1 epilogue: u is written once and never re-read in forward
+    else:
+        u = ops.gemm(h, wb(w_up))
+        s = ops.swiglu_fwd(u)
     m = ops.gemm(s, wb(w_down))
     save.update(mlp_h=h, mlp_u=u, mlp_s=s)
     return m

@@ -82,6 +82,14 @@ __device__ __forceinline__ bf16x8 ld8(const __nv_bfloat16* p) { return *reinterp
 __device__ __forceinline__ void st8(__nv_bfloat16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// silu(x) = x * sigmoid(x) = h * tanh(h) + h with h = x / 2: one MUFU op and no division (the GEMM-epilogue version; the
+// result is rounded to bf16 by every caller, tanh.approx's 2^-11 relative error sits below that rounding)
+__device__ __forceinline__ float silu_fast(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 // d/dx silu(x) = s + x s (1 - s), s = sigmoid(x)
 __device__ __forceinline__ float dsilu_f(float x) {
   float s = 1.f / (1.f + __expf(-x));

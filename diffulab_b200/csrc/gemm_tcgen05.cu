@@ -53,11 +53,17 @@ __device__ __forceinline__ TileCoord decode_tile(int t, int mb, int nb, int kb_t
   return c;
 }
 
-template <int BN, bool A_MN, bool B_MN, int OUT>
+// SWIGLU variant (fc1 of the packed-SwiGLU MLP, reference nn.py:478-486 + mmdit.py:260-264): the weight is [2F, K]
+// with the silu-ed half in rows [0, F) and the multiplied half in rows [F, 2F). A tile then covers BN/2 columns of EACH
+// half (two TMA boxes of BN/2 weight rows), so the accumulator holds matching (a, g) column pairs and the epilogue
+// writes the pre-activation h = [a | g] (saved for backward) AND silu(a) * g in one pass. N = F here.
+template <int BN, bool A_MN, bool B_MN, int OUT, bool SWIGLU = false>
 __global__ void __launch_bounds__(256, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K,
-                    int split_k) {
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+                    const float* __restrict__ bias, int M, int N, int K, int split_k) {
+  static_assert(!SWIGLU || (!A_MN && !B_MN && OUT == OUT_BF16 && BN == 256), "SWIGLU epilogue: K-major bf16 128x256 tiles only");
+  constexpr int BNT = SWIGLU ? BN / 2 : BN;  // output columns (of each half) per tile
   using C = Cfg<BN>;
   constexpr int NST = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -73,7 +79,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler (role dispatch + uniform MMA issue)
-  const int mb = (M + BM - 1) / BM, nb = (N + BN - 1) / BN;
+  const int mb = (M + BM - 1) / BM, nb = (N + BNT - 1) / BNT;
   const int kb_total = (K + BK - 1) / BK;
   const int kb_per = (kb_total + split_k - 1) / split_k;
   const int tiles = mb * nb * split_k;
@@ -82,6 +88,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     ptx::prefetch_tmap(&tmC);
+    if constexpr (SWIGLU) ptx::prefetch_tmap(&tmC2);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NST; ++i) {
@@ -120,7 +127,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               for (int i = 0; i < BM / 64; ++i)
                 ptx::tma_load_2d(a + i * MN_BLOCK_BYTES, &tmA, &full[stage], tc.m_blk * BM + i * 64, kb * BK);
             }
-            if constexpr (!B_MN) {
+            if constexpr (SWIGLU) {
+              ptx::tma_load_2d(b, &tmB, &full[stage], kb * BK, tc.n_blk * BNT);                       // rows of the silu-ed half
+              ptx::tma_load_2d(b + BNT * BK * 2, &tmB, &full[stage], kb * BK, N + tc.n_blk * BNT);    // matching rows of the other half
+            } else if constexpr (!B_MN) {
               ptx::tma_load_2d(b, &tmB, &full[stage], kb * BK, tc.n_blk * BN);
             } else {
 #pragma unroll
@@ -183,6 +193,55 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row0 = tc.m_blk * BM + ew * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
       const bool add_bias = (bias != nullptr) && (tc.ks == 0);
+      if constexpr (SWIGLU) {
+        // 64-column chunks of the two halves: h_a -> tmC(col), h_g -> tmC(N + col), silu(a) * g -> tmC2(col)
+        auto stage_store = [&](const uint32_t* packed, const CUtensorMap* tm, int col) {
+          uint8_t* buf = ebase + ebuf * EPI_BUF_BYTES;
+          if (lane == 0) ptx::tma_wait_group_read<1>();
+          __syncwarp();
+          uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < M) {
+            ptx::tma_store_2d(tm, buf, col, row0);
+            ptx::tma_commit_group();
+          }
+          ebuf ^= 1;
+        };
+        auto load_pack = [&](uint32_t tcol, int bias_col, uint32_t* packed) {  // 64 fp32 columns (+ bias) -> 32 packed bf16 pairs
+#pragma unroll
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            uint32_t r[32];
+            ptx::tmem_ld32(taddr + tcol + hlf * 32, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
+              if (add_bias) { v0 += __ldg(bias + bias_col + hlf * 32 + i); v1 += __ldg(bias + bias_col + hlf * 32 + i + 1); }
+              packed[hlf * 16 + i / 2] = pack_bf16x2(v0, v1);
+            }
+          }
+        };
+#pragma unroll 1
+        for (int c = 0; c < BNT; c += 64) {
+          const int col0 = tc.n_blk * BNT + c;
+          if (col0 >= N) break;
+          uint32_t pa[32], pg[32];
+          load_pack(c, col0, pa);
+          stage_store(pa, &tmC, col0);
+          load_pack(BNT + c, N + col0, pg);
+          stage_store(pg, &tmC, N + col0);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {  // out = bf16(bf16(silu(a)) * g) on the bf16-rounded pre-activations (autocast numerics)
+            const float2 a = unpack_bf16x2(pa[i]), g = unpack_bf16x2(pg[i]);
+            pa[i] = pack_bf16x2(bf16_round(silu_fast(a.x)) * g.x, bf16_round(silu_fast(a.y)) * g.y);
+          }
+          stage_store(pa, &tmC2, col0);
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < BN; c += CH) {
         const int col0 = tc.n_blk * BN + c;
@@ -223,6 +282,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           ptx::tma_commit_group();
         }
         ebuf ^= 1;
+      }
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -284,7 +344,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   const int mb = (M + BM - 1) / BM, nb = (N + BN - 1) / BN;
   const int tiles = mb * nb * split_k;
   const int grid = tiles < dlb_num_sms() ? tiles : dlb_num_sms();
-  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(ta, tb, tc, bias, M, N, K, split_k);
+  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(ta, tb, tc, tc, bias, M, N, K, split_k);
   dlb_count_launch();
   return dlb_check_launch("gemm_tcgen05");
 }
@@ -392,4 +452,39 @@ DLB_EXPORT int dlb_gemm_bf16(const void* A, const void* B, void* Cout, const flo
     case 192: return dispatch_major<192>(a_mn_major, b_mn_major, out_mode, ta, tb, tc, bias, M, N, K, split_k, stream);
     default: return dispatch_major<256>(a_mn_major, b_mn_major, out_mode, ta, tb, tc, bias, M, N, K, split_k, stream);
   }
+}
+
+
+// H[M, 2F] = A[M,K] * W[2F,K]^T + bias (bf16, the saved pre-activation) and ACT[M, F] = silu(H[:, :F]) * H[:, F:] in one
+// launch. Replaces Linear + PackedSwiGLU.forward (reference mmdit.py:260-264, nn.py:478-486). F % 128 == 0.
+DLB_EXPORT int dlb_gemm_swiglu_bf16(const void* A, const void* W, const float* bias, void* H, void* ACT, int64_t M, int64_t F,
+                                    int64_t K, int64_t lda, int64_t ldw, int64_t ldh, int64_t ldact, cudaStream_t stream) {
+  DLB_REQUIRE(M > 0 && F > 0 && K > 0 && M < (1ll << 31) && F < (1ll << 30) && K < (1ll << 31), DLB_ERR_SHAPE,
+              "gemm_swiglu: bad problem M=%lld F=%lld K=%lld", (long long)M, (long long)F, (long long)K);
+  DLB_REQUIRE(F % 128 == 0, DLB_ERR_UNSUPPORTED, "gemm_swiglu: F must be a multiple of 128 (got %lld)", (long long)F);
+  DLB_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ldh % 8 == 0 && ldact % 8 == 0, DLB_ERR_ALIGN, "gemm_swiglu: strides must be multiples of 8 elements");
+  DLB_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)W % 16) == 0 && ((uintptr_t)H % 16) == 0 && ((uintptr_t)ACT % 16) == 0, DLB_ERR_ALIGN,
+              "gemm_swiglu: operand pointers must be 16-byte aligned");
+  CUtensorMap ta, tb, tc, tc2;
+  int rc = encode2d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, K, M, lda, BK, BM);
+  if (rc) return rc;
+  rc = encode2d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, K, 2 * F, ldw, BK, 128);
+  if (rc) return rc;
+  rc = encode2d(&tc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, 2 * F, M, ldh, 64, 32);
+  if (rc) return rc;
+  rc = encode2d(&tc2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ACT, F, M, ldact, 64, 32);
+  if (rc) return rc;
+  using C = Cfg<256>;
+  auto kern = gemm_tcgen05_kernel<256, false, false, OUT_BF16, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    DLB_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(smem=%d): %s", C::SMEM_BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles = (int)(((M + BM - 1) / BM) * (F / 128));
+  const int grid = tiles < dlb_num_sms() ? tiles : dlb_num_sms();
+  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(ta, tb, tc, tc2, bias, (int)M, (int)F, (int)K, 1);
+  dlb_count_launch();
+  return dlb_check_launch("gemm_swiglu");
 }

@@ -392,7 +392,7 @@ swiglu_fwd_kernel(const bf16* __restrict__ h, bf16* __restrict__ out, int64_t R,
     unpack8(av, a);
     unpack8(gv, g);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = bf16_round(silu_f(a[j])) * g[j];
+    for (int j = 0; j < 8; ++j) o[j] = bf16_round(silu_fast(a[j])) * g[j];
     st8(out + row * F + v * 8, pack8(o));
   }
 }

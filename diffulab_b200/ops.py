@@ -253,6 +253,26 @@ def gate_residual_bwd(dout: Tensor, a1: Tensor, a2: Tensor | None, gate: Tensor,
 # ---------------------------------------------------------------------------------------------------------
 # SwiGLU
 # ---------------------------------------------------------------------------------------------------------
+def gemm_swiglu(a: Tensor, w: Tensor, bias: Tensor | None = None) -> tuple[Tensor, Tensor]:
+    """(H, ACT) = (a @ w^T (+ bias), silu(H[:, :F]) * H[:, F:]) with the activation fused into the GEMM epilogue.
+    a [M,K], w [2F,K] bf16; F % 128 == 0 (callers fall back to gemm + swiglu_fwd otherwise)."""
+    _check_2d(a, "a")
+    _check_2d(w, "w")
+    if a.dtype != BF16 or w.dtype != BF16:
+        raise ValueError("gemm_swiglu operands must be bfloat16")
+    M, K = a.shape
+    F = w.shape[0] // 2
+    if w.shape[1] != K or w.shape[0] != 2 * F:
+        raise ValueError(f"gemm_swiglu: weight shape {tuple(w.shape)} does not match K={K}")
+    h = torch.empty((M, 2 * F), device=a.device, dtype=BF16)
+    act = torch.empty((M, F), device=a.device, dtype=BF16)
+    with _Timed(f"gemm_swiglu_fwd {M}x{2 * F}x{K}" if _prof is not None else "gemm_swiglu_fwd", 2.0 * M * 2 * F * K):
+        rc = _lib.load().dlb_gemm_swiglu_bf16(a.data_ptr(), w.data_ptr(), _ptr(bias), h.data_ptr(), act.data_ptr(), M, F, K,
+                                              a.stride(0), w.stride(0), h.stride(0), act.stride(0), _stream())
+    _lib.check(rc, "dlb_gemm_swiglu_bf16")
+    return h, act
+
+
 def swiglu_fwd(h: Tensor) -> Tensor:
     _req(h, BF16, "h")
     F = h.shape[-1] // 2

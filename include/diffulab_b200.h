@@ -54,6 +54,12 @@ int dlb_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int6
                   int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major, int out_mode, int split_k,
                   int tile_n, dlb_stream_t stream);
 
+/* fc1 of the packed-SwiGLU MLP with the activation fused into the epilogue: H[M,2F] = A[M,K] W[2F,K]^T (+ bias[2F]) in bf16
+ * (the pre-activation saved for backward) and ACT[M,F] = silu(H[:, :F]) * H[:, F:], one launch. Replaces nn.Linear +
+ * PackedSwiGLU.forward (reference networks/denoisers/mmdit.py:260-264, networks/utils/nn.py:478-486). F % 128 == 0. */
+int dlb_gemm_swiglu_bf16(const void* A, const void* W, const float* bias, void* H, void* ACT, int64_t M, int64_t F, int64_t K,
+                         int64_t lda, int64_t ldw, int64_t ldh, int64_t ldact, dlb_stream_t stream);
+
 /* ---- LayerNorm (+affine) + adaLN modulate ----------------------------------------------------------------
  * y = (LN(x) * w + b) * (1 + scale) + shift; x,y bf16 [R,d]; w,b fp32 [d] or both NULL; scale/shift bf16 rows of
  * a [G, k*d] adaLN output (row stride mod_ld), row r uses modulation row r / rows_per_mod (1 = per token).

@@ -120,3 +120,23 @@ def test_gemm_bad_args(cuda_device):
     b = torch.zeros(8, 12, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(_lib.DlbError):
         ops.gemm(a, b)  # K=12 rows are 24 bytes: violates the 16-byte stride rule, must fail loudly
+
+
+@pytest.mark.parametrize("M,F,K,with_bias", [(256, 128, 64, False), (300, 256, 192, True), (1024, 1152, 288, False), (4096, 4608, 1152, False)])
+def test_gemm_swiglu_fused_matches_unfused(cuda_device, M, F, K, with_bias):
+    """fc1 + SwiGLU epilogue == gemm followed by the standalone swiglu kernel, bit for bit (same bf16 rounding points)."""
+    from diffulab_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M + F)
+    a = (torch.randn(M, K, device="cuda", generator=g)).bfloat16()
+    w = (torch.randn(2 * F, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(2 * F, device="cuda", generator=g) if with_bias else None
+    h_ref = ops.gemm(a, w, bias=bias)
+    act_ref = ops.swiglu_fwd(h_ref)
+    h, act = ops.gemm_swiglu(a, w, bias)
+    assert torch.equal(h, h_ref)
+    assert torch.equal(act, act_ref)
+    # and against an fp32 torch restatement
+    hf = a.float() @ w.float().t() + (bias if bias is not None else 0)
+    ref = torch.nn.functional.silu(hf[:, :F]) * hf[:, F:]
+    assert ((act.float() - ref).norm() / ref.norm()).item() < 1e-2
