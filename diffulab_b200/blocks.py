@@ -286,9 +286,11 @@ def mlp_fwd(h: Tensor, w_up: Tensor, w_down: Tensor, save: dict) -> Tensor:
 
 
 def mlp_bwd(dm: Tensor, w_up: Tensor, w_down: Tensor, save: dict) -> Tensor:
-    ds = ops.gemm(dm, wb(w_down), b_mn=True)
+    if w_down.shape[1] % 128 == 0:
+        du = ops.gemm_swiglu_bwd(dm, wb(w_down), save["mlp_u"])  # d(act) never leaves the SM
+    else:
+        du = ops.swiglu_bwd(ops.gemm(dm, wb(w_down), b_mn=True), save["mlp_u"])
     wgrad_(w_down, dm, save["mlp_s"])
-    du = ops.swiglu_bwd(ds, save["mlp_u"])
     dh = ops.gemm(du, wb(w_up), b_mn=True)
     wgrad_(w_up, du, save["mlp_h"])
     return dh

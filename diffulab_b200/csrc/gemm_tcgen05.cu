@@ -24,19 +24,21 @@ constexpr int EPI_BUF_BYTES = 32 * 128;              // 32 rows x 128 B per warp
 constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF_BYTES;  // 32 KB
 constexpr int SMEM_LIMIT = 232448;                   // 227 KB opt-in maximum per CTA
 
-template <int BN>
+template <int BN, int EPIB = EPI_BYTES>
 struct Cfg {
   static constexpr int B_TILE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  static constexpr int STAGES_RAW = (SMEM_LIMIT - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (SMEM_LIMIT - 1024 - 256 - EPIB) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPIB + 256;
   static_assert(STAGES >= 3, "pipeline too shallow");
   static_assert(SMEM_BYTES <= SMEM_LIMIT, "shared memory budget exceeded");
 };
 
 enum { OUT_BF16 = 0, OUT_F32 = 1, OUT_F32_ADD = 2 };
+enum { EPI_NONE = 0, EPI_SWIGLU = 1, EPI_SWIGLU_BWD = 2 };
+constexpr int EPI_BWD_BYTES = EPI_WARPS * 2 * 2 * EPI_BUF_BYTES;  // per warp: 2 chunk slots x {a, g} tiles = 64 KB
 
 struct TileCoord {
   int m_blk, n_blk, kb0, kb1, ks;
@@ -57,25 +59,34 @@ __device__ __forceinline__ TileCoord decode_tile(int t, int mb, int nb, int kb_t
 // with the silu-ed half in rows [0, F) and the multiplied half in rows [F, 2F). A tile then covers BN/2 columns of EACH
 // half (two TMA boxes of BN/2 weight rows), so the accumulator holds matching (a, g) column pairs and the epilogue
 // writes the pre-activation h = [a | g] (saved for backward) AND silu(a) * g in one pass. N = F here.
-template <int BN, bool A_MN, bool B_MN, int OUT, bool SWIGLU = false>
+//
+// SWIGLU_BWD variant (dgrad of fc2 fused with the SwiGLU backward): the accumulator tile is d(act)[128 x 128]; the
+// epilogue warps TMA-load the matching (a, g) tiles of the saved pre-activation H (prefetched during the tile's
+// main loop), compute da = dact * g * silu'(a), dg = dact * silu(a) in place and TMA-store them to dH[:, n] / dH[:, F+n].
+// d(act) is never written to memory. N = F here.
+template <int BN, bool A_MN, bool B_MN, int OUT, int EPI = EPI_NONE>
 __global__ void __launch_bounds__(256, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
                     const float* __restrict__ bias, int M, int N, int K, int split_k) {
+  constexpr bool SWIGLU = EPI == EPI_SWIGLU, SWIGLU_BWD = EPI == EPI_SWIGLU_BWD;
   static_assert(!SWIGLU || (!A_MN && !B_MN && OUT == OUT_BF16 && BN == 256), "SWIGLU epilogue: K-major bf16 128x256 tiles only");
+  static_assert(!SWIGLU_BWD || (!A_MN && B_MN && OUT == OUT_BF16 && BN == 128), "SWIGLU_BWD epilogue: dgrad bf16 128x128 tiles only");
   constexpr int BNT = SWIGLU ? BN / 2 : BN;  // output columns (of each half) per tile
-  using C = Cfg<BN>;
+  constexpr int EPIB = SWIGLU_BWD ? EPI_BWD_BYTES : EPI_BYTES;
+  using C = Cfg<BN, EPIB>;
   constexpr int NST = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = sA + NST * A_TILE_BYTES;
   uint8_t* sE = sB + NST * C::B_TILE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sE + EPI_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sE + EPIB);
   uint64_t* empty = full + NST;
   uint64_t* tfull = empty + NST;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* lbar = tempty + 2;  // SWIGLU_BWD: [EPI_WARPS][2] "h tiles landed" barriers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lbar + 2 * EPI_WARPS);
 
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler (role dispatch + uniform MMA issue)
@@ -88,7 +99,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     ptx::prefetch_tmap(&tmC);
-    if constexpr (SWIGLU) ptx::prefetch_tmap(&tmC2);
+    if constexpr (SWIGLU || SWIGLU_BWD) ptx::prefetch_tmap(&tmC2);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NST; ++i) {
@@ -99,6 +110,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::mbar_init(&tfull[i], 1);
       ptx::mbar_init(&tempty[i], EPI_WARPS);
     }
+    for (int i = 0; i < 2 * EPI_WARPS; ++i) ptx::mbar_init(&lbar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) ptx::tmem_alloc<C::TMEM_COLS>(tmem_slot);
@@ -186,6 +198,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int ebuf = 0;
     int as = 0;
     uint32_t aphase = 0;
+    [[maybe_unused]] uint32_t hphase = 0;
+    [[maybe_unused]] auto issue_h_loads = [&](int tn, bool wait_stores) {
+      if constexpr (SWIGLU_BWD) {
+        const TileCoord tcn = decode_tile(tn, mb, nb, kb_total, kb_per);
+        const int r0 = tcn.m_blk * BM + ew * 32;
+        if (lane == 0 && r0 < M) {
+          if (wait_stores) ptx::tma_wait_group_read<0>();  // my staged stores have been read: the slots are free
+          uint8_t* wb_ = sE + ew * (4 * EPI_BUF_BYTES);
+#pragma unroll
+          for (int slot = 0; slot < 2; ++slot) {
+            const int col = tcn.n_blk * BN + slot * 64;
+            uint64_t* b = &lbar[ew * 2 + slot];
+            ptx::mbar_expect_tx(b, 2 * EPI_BUF_BYTES);
+            ptx::tma_load_2d(wb_ + slot * 2 * EPI_BUF_BYTES, &tmC2, b, col, r0);
+            ptx::tma_load_2d(wb_ + slot * 2 * EPI_BUF_BYTES + EPI_BUF_BYTES, &tmC2, b, N + col, r0);
+          }
+        }
+        __syncwarp();
+      }
+    };
+    if constexpr (SWIGLU_BWD) {
+      if ((int)blockIdx.x < tiles) issue_h_loads(blockIdx.x, false);
+    }
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(t, mb, nb, kb_total, kb_per);
       ptx::mbar_wait(&tfull[as], aphase);
@@ -193,7 +228,52 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row0 = tc.m_blk * BM + ew * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
       const bool add_bias = (bias != nullptr) && (tc.ks == 0);
-      if constexpr (SWIGLU) {
+      if constexpr (SWIGLU_BWD) {
+        uint8_t* wbase = sE + ew * (4 * EPI_BUF_BYTES);  // [slot][a | g] tiles of 32 rows x 128 B (128B-swizzled, as TMA lays them)
+        uint64_t* lb = lbar + ew * 2;
+        const bool rows_ok = row0 < M;
+#pragma unroll 1
+        for (int slot = 0; slot < 2; ++slot) {
+          const int col0 = tc.n_blk * BN + slot * 64;
+          uint8_t* abuf = wbase + slot * 2 * EPI_BUF_BYTES;
+          uint8_t* gbuf = abuf + EPI_BUF_BYTES;
+          uint32_t r[64];
+          ptx::tmem_ld32(taddr + slot * 64, r);
+          ptx::tmem_ld32(taddr + slot * 64 + 32, r + 32);
+          ptx::tmem_ld_wait();
+          if (rows_ok) ptx::mbar_wait(&lb[slot], hphase);
+          uint8_t* rowa = abuf + lane * 128;
+          uint8_t* rowg = gbuf + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int off = (j ^ (lane & 7)) << 4;
+            const bf16x8 av = *reinterpret_cast<const bf16x8*>(rowa + off), gv = *reinterpret_cast<const bf16x8*>(rowg + off);
+            float a[8], g[8], da[8], dg[8];
+            unpack8(av, a);
+            unpack8(gv, g);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float go = bf16_round(__uint_as_float(r[8 * j + i]));  // d(act) as the bf16 tensor autocast would hold
+              const float hh = 0.5f * a[i];
+              float th;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hh));
+              const float sg = fmaf(0.5f, th, 0.5f);  // sigmoid(a)
+              da[i] = go * g[i] * sg * (1.f + a[i] * (1.f - sg));
+              dg[i] = go * a[i] * sg;
+            }
+            *reinterpret_cast<bf16x8*>(rowa + off) = pack8(da);
+            *reinterpret_cast<bf16x8*>(rowg + off) = pack8(dg);
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && rows_ok) {
+            ptx::tma_store_2d(&tmC, abuf, col0, row0);
+            ptx::tma_store_2d(&tmC, gbuf, N + col0, row0);
+            ptx::tma_commit_group();
+          }
+        }
+        if (rows_ok) hphase ^= 1;  // the barriers are only armed for tiles whose rows exist
+      } else if constexpr (SWIGLU) {
         // 64-column chunks of the two halves: h_a -> tmC(col), h_g -> tmC(N + col), silu(a) * g -> tmC2(col)
         auto stage_store = [&](const uint32_t* packed, const CUtensorMap* tm, int col) {
           uint8_t* buf = ebase + ebuf * EPI_BUF_BYTES;
@@ -289,6 +369,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (lane == 0) ptx::mbar_arrive(&tempty[as]);
       as ^= 1;
       if (as == 0) aphase ^= 1;
+      if constexpr (SWIGLU_BWD) {  // h tiles of my next output tile: they land while its main loop runs
+        if (t + (int)gridDim.x < tiles) issue_h_loads(t + gridDim.x, true);
+      }
     }
     if (lane == 0) ptx::tma_wait_group<0>();
   }
@@ -475,7 +558,7 @@ DLB_EXPORT int dlb_gemm_swiglu_bf16(const void* A, const void* W, const float* b
   rc = encode2d(&tc2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ACT, F, M, ldact, 64, 32);
   if (rc) return rc;
   using C = Cfg<256>;
-  auto kern = gemm_tcgen05_kernel<256, false, false, OUT_BF16, true>;
+  auto kern = gemm_tcgen05_kernel<256, false, false, OUT_BF16, EPI_SWIGLU>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -487,4 +570,41 @@ DLB_EXPORT int dlb_gemm_swiglu_bf16(const void* A, const void* W, const float* b
   kern<<<grid, 256, C::SMEM_BYTES, stream>>>(ta, tb, tc, tc2, bias, (int)M, (int)F, (int)K, 1);
   dlb_count_launch();
   return dlb_check_launch("gemm_swiglu");
+}
+
+
+// dH[M, 2F] = SwiGLU'(H) applied to d(act) = dY[M,D] * W2[D,F]: the dgrad of the MLP down-projection with the SwiGLU
+// backward fused into its epilogue (d(act) never reaches memory). Replaces the autograd mirror of
+// PackedSwiGLU.forward + nn.Linear (reference nn.py:478-486, mmdit.py:260-264). W2 is the row-major [D, F] weight of the
+// down projection (nn.Linear(F, D).weight); F % 128 == 0.
+DLB_EXPORT int dlb_gemm_swiglu_bwd_bf16(const void* dY, const void* W2, const void* H, void* dH, int64_t M, int64_t F, int64_t D,
+                                        int64_t lddy, int64_t ldw2, int64_t ldh, int64_t lddh, cudaStream_t stream) {
+  DLB_REQUIRE(M > 0 && F > 0 && D > 0 && M < (1ll << 31) && F < (1ll << 30) && D < (1ll << 31), DLB_ERR_SHAPE,
+              "gemm_swiglu_bwd: bad problem M=%lld F=%lld D=%lld", (long long)M, (long long)F, (long long)D);
+  DLB_REQUIRE(F % 128 == 0, DLB_ERR_UNSUPPORTED, "gemm_swiglu_bwd: F must be a multiple of 128 (got %lld)", (long long)F);
+  DLB_REQUIRE(lddy % 8 == 0 && ldw2 % 8 == 0 && ldh % 8 == 0 && lddh % 8 == 0, DLB_ERR_ALIGN, "gemm_swiglu_bwd: strides must be multiples of 8 elements");
+  DLB_REQUIRE(((uintptr_t)dY % 16) == 0 && ((uintptr_t)W2 % 16) == 0 && ((uintptr_t)H % 16) == 0 && ((uintptr_t)dH % 16) == 0, DLB_ERR_ALIGN,
+              "gemm_swiglu_bwd: operand pointers must be 16-byte aligned");
+  CUtensorMap ta, tb, tc, tc2;
+  int rc = encode2d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dY, D, M, lddy, BK, BM);   // A = dY, K-major (K = D)
+  if (rc) return rc;
+  rc = encode2d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W2, F, D, ldw2, 64, BK);        // B = W2^T read MN-major
+  if (rc) return rc;
+  rc = encode2d(&tc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dH, 2 * F, M, lddh, 64, 32);
+  if (rc) return rc;
+  rc = encode2d(&tc2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, 2 * F, M, ldh, 64, 32);
+  if (rc) return rc;
+  using C = Cfg<128, EPI_BWD_BYTES>;
+  auto kern = gemm_tcgen05_kernel<128, false, true, OUT_BF16, EPI_SWIGLU_BWD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    DLB_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(smem=%d): %s", C::SMEM_BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles = (int)(((M + BM - 1) / BM) * (F / 128));
+  const int grid = tiles < dlb_num_sms() ? tiles : dlb_num_sms();
+  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(ta, tb, tc, tc2, nullptr, (int)M, (int)F, (int)D, 1);
+  dlb_count_launch();
+  return dlb_check_launch("gemm_swiglu_bwd");
 }

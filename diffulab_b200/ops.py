@@ -273,6 +273,25 @@ def gemm_swiglu(a: Tensor, w: Tensor, bias: Tensor | None = None) -> tuple[Tenso
     return h, act
 
 
+def gemm_swiglu_bwd(dy: Tensor, w2: Tensor, h: Tensor) -> Tensor:
+    """dH = SwiGLU-backward(h, dy @ w2) with d(act) kept on chip. dy [M,D], w2 [D,F] (the down-projection weight), h [M,2F]."""
+    _check_2d(dy, "dy")
+    _check_2d(w2, "w2")
+    _check_2d(h, "h")
+    if dy.dtype != BF16 or w2.dtype != BF16 or h.dtype != BF16:
+        raise ValueError("gemm_swiglu_bwd operands must be bfloat16")
+    M, D = dy.shape
+    F = w2.shape[1]
+    if w2.shape[0] != D or tuple(h.shape) != (M, 2 * F):
+        raise ValueError(f"gemm_swiglu_bwd: shapes dy {tuple(dy.shape)}, w2 {tuple(w2.shape)}, h {tuple(h.shape)} do not match")
+    dh = torch.empty_like(h)
+    with _Timed(f"gemm_swiglu_bwd {M}x{F}x{D}" if _prof is not None else "gemm_swiglu_bwd", 2.0 * M * F * D):
+        rc = _lib.load().dlb_gemm_swiglu_bwd_bf16(dy.data_ptr(), w2.data_ptr(), h.data_ptr(), dh.data_ptr(), M, F, D, dy.stride(0),
+                                                  w2.stride(0), h.stride(0), dh.stride(0), _stream())
+    _lib.check(rc, "dlb_gemm_swiglu_bwd_bf16")
+    return dh
+
+
 def swiglu_fwd(h: Tensor) -> Tensor:
     _req(h, BF16, "h")
     F = h.shape[-1] // 2

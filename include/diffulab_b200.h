@@ -60,6 +60,12 @@ int dlb_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int6
 int dlb_gemm_swiglu_bf16(const void* A, const void* W, const float* bias, void* H, void* ACT, int64_t M, int64_t F, int64_t K,
                          int64_t lda, int64_t ldw, int64_t ldh, int64_t ldact, dlb_stream_t stream);
 
+/* dgrad of the MLP down-projection with the SwiGLU backward fused into the epilogue: d(act) = dY[M,D] W2[D,F] stays in
+ * TMEM / registers; dH[M,2F] = [d(act) * g * silu'(a) | d(act) * silu(a)] with (a, g) = the saved H[M,2F] (TMA-prefetched
+ * per tile). Replaces the autograd mirror of nn.Linear(F, D) + PackedSwiGLU (reference nn.py:478-486). F % 128 == 0. */
+int dlb_gemm_swiglu_bwd_bf16(const void* dY, const void* W2, const void* H, void* dH, int64_t M, int64_t F, int64_t D,
+                             int64_t lddy, int64_t ldw2, int64_t ldh, int64_t lddh, dlb_stream_t stream);
+
 /* ---- LayerNorm (+affine) + adaLN modulate ----------------------------------------------------------------
  * y = (LN(x) * w + b) * (1 + scale) + shift; x,y bf16 [R,d]; w,b fp32 [d] or both NULL; scale/shift bf16 rows of
  * a [G, k*d] adaLN output (row stride mod_ld), row r uses modulation row r / rows_per_mod (1 = per token).
