@@ -54,6 +54,7 @@ _SIGNATURES: dict[str, list] = {
     "dlb_cast_bf16_f32": [p, p, i64, p],
     "dlb_umma_probe": [p, p, p, i32, i32, i32, i32, i32, p],
     "dlb_attn_set_trace": [p],
+    "dlb_gemm2_bf16": [p, p, p, p, i64, i64, i64, i64, i64, i64, i32, i32, i32, i32, i32, p],
     # dY, W2, H, dH, M, F, D, lddy, ldw2, ldh, lddh, stream
     "dlb_gemm_swiglu_bwd_bf16": [p, p, p, p, i64, i64, i64, i64, i64, i64, i64, p],
     # A, W, bias, H, ACT, M, F, K, lda, ldw, ldh, ldact, stream

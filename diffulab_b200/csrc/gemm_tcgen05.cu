@@ -382,6 +382,211 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs (one TPC) computes a 256 x BN tile with ONE stream of
+// tcgen05.mma.cta_group::2 issued by the even CTA. Each CTA stages its own 128 rows of A and only HALF of the B tile
+// (BN/2 rows), so the L2 -> shared-memory traffic per output element drops by a third against the single-CTA kernel —
+// the single-CTA kernel is bound by exactly that traffic. Protocol:
+//   full[s]   (even CTA)  1 arrival (its producer's expect_tx) + the bytes of BOTH CTAs' TMA loads (.cta_group::2 loads
+//                         credit the even CTA's barrier)
+//   empty[s]  (each CTA)  tcgen05.commit multicast to both CTAs: stage s may be refilled
+//   tfull[a]  (each CTA)  tcgen05.commit multicast: accumulator stage a is complete; every CTA drains its own 128 lanes
+//   tempty[a] (even CTA)  2 x EPI_WARPS arrivals (the odd CTA's epilogue warps arrive remotely)
+// ---------------------------------------------------------------------------------------------------------
+template <int BN>
+struct Cfg2 {
+  static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_HALF_BYTES;  // per CTA
+  static constexpr int STAGES_RAW = (SMEM_LIMIT - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256;
+};
+
+template <int BN, bool A_MN, bool B_MN, int OUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K, int split_k) {
+  static_assert(!B_MN || (BN / 2) % 64 == 0, "MN-major B: each CTA's half must be whole 64-column blocks");
+  using C = Cfg2<BN>;
+  constexpr int NST = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + NST * A_TILE_BYTES;
+  uint8_t* sE = sB + NST * C::B_HALF_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sE + EPI_BYTES);
+  uint64_t* empty = full + NST;
+  uint64_t* tfull = empty + NST;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int rank = (int)ptx::cluster_ctarank();  // 0 = the even ("leader") CTA, which issues the MMAs
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int mb = (M + 2 * BM - 1) / (2 * BM), nb = (N + BN - 1) / BN;
+  const int kb_total = (K + BK - 1) / BK;
+  const int kb_per = (kb_total + split_k - 1) / split_k;
+  const int tiles = mb * nb * split_k;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NST; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull[i], 1);
+      ptx::mbar_init(&tempty[i], 2 * EPI_WARPS);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) ptx::tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();  // barriers of both CTAs are initialised before anyone signals them
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; each loads its A rows and its half of B) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = cluster_id; t < tiles; t += n_clusters) {
+      const TileCoord tc = decode_tile(t, mb, nb, kb_total, kb_per);
+      const int m0 = (tc.m_blk * 2 + rank) * BM;
+      const int n0 = tc.n_blk * BN + rank * (BN / 2);
+      for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        if (ptx::elect_one()) {
+          if (rank == 0) ptx::mbar_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+          uint8_t* a = sA + stage * A_TILE_BYTES;
+          uint8_t* b = sB + stage * C::B_HALF_BYTES;
+          if constexpr (!A_MN) {
+            ptx::tma_load_2d_2sm(a, &tmA, &full[stage], kb * BK, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) ptx::tma_load_2d_2sm(a + i * MN_BLOCK_BYTES, &tmA, &full[stage], m0 + i * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            ptx::tma_load_2d_2sm(b, &tmB, &full[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 128; ++i) ptx::tma_load_2d_2sm(b + i * MN_BLOCK_BYTES, &tmB, &full[stage], n0 + i * 64, kb * BK);
+          }
+        }
+        __syncwarp();
+        if (++stage == NST) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (even CTA only; warp-uniform code, one elected lane issues) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(2 * BM, BN, A_MN, B_MN);
+      constexpr uint64_t A_KSTEP = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4, B_KSTEP = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t a_base = ptx::smem_u32(sA), b_base = ptx::smem_u32(sB);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = cluster_id; t < tiles; t += n_clusters) {
+        const TileCoord tc = decode_tile(t, mb, nb, kb_total, kb_per);
+        ptx::mbar_wait(&tempty[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_u + as * BN;
+        for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = a_base + stage * A_TILE_BYTES;
+          const uint32_t b_addr = b_base + stage * C::B_HALF_BYTES;
+          const uint64_t adesc0 = A_MN ? ptx::make_smem_desc_sw128(a_addr, MN_BLOCK_BYTES, 1024) : ptx::make_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t bdesc0 = B_MN ? ptx::make_smem_desc_sw128(b_addr, MN_BLOCK_BYTES, 1024) : ptx::make_smem_desc_sw128(b_addr, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            ptx::umma_bf16_elect_2sm(d_tmem, adesc0 + k * A_KSTEP, bdesc0 + k * B_KSTEP, idesc, (kb > tc.kb0 || k > 0) ? 1u : 0u);
+          ptx::umma_commit_elect_2sm(&empty[stage]);
+          if (++stage == NST) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit_elect_2sm(&tfull[as]);
+        as ^= 1;
+        if (as == 0) aphase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows): TMEM -> registers -> swizzled smem -> TMA store =====================
+    const int ew = warp - 4;
+    constexpr int CH = (OUT == OUT_BF16) ? 64 : 32;
+    uint8_t* ebase = sE + ew * (2 * EPI_BUF_BYTES);
+    int ebuf = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = cluster_id; t < tiles; t += n_clusters) {
+      const TileCoord tc = decode_tile(t, mb, nb, kb_total, kb_per);
+      ptx::mbar_wait(&tfull[as], aphase);
+      ptx::tc_fence_after();
+      const int row0 = (tc.m_blk * 2 + rank) * BM + ew * 32;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
+      const bool add_bias = (bias != nullptr) && (tc.ks == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += CH) {
+        const int col0 = tc.n_blk * BN + c;
+        if (col0 >= N) break;
+        uint32_t r[CH];
+        ptx::tmem_ld32(taddr + c, r);
+        if constexpr (CH == 64) ptx::tmem_ld32(taddr + c + 32, r + 32);
+        ptx::tmem_ld_wait();
+        if (add_bias) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            const float bv = (col0 + i < N) ? __ldg(bias + col0 + i) : 0.f;
+            r[i] = __float_as_uint(__uint_as_float(r[i]) + bv);
+          }
+        }
+        uint8_t* buf = ebase + ebuf * EPI_BUF_BYTES;
+        if (lane == 0) ptx::tma_wait_group_read<1>();
+        __syncwarp();
+        uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 v;
+          if constexpr (OUT == OUT_BF16) {
+            v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+            v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+            v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+            v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+          } else {
+            v.x = r[4 * j + 0]; v.y = r[4 * j + 1]; v.z = r[4 * j + 2]; v.w = r[4 * j + 3];
+          }
+          *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = v;
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && row0 < M) {
+          if constexpr (OUT == OUT_F32_ADD) ptx::tma_reduce_add_2d(&tmC, buf, col0, row0);
+          else ptx::tma_store_2d(&tmC, buf, col0, row0);
+          ptx::tma_commit_group();
+        }
+        ebuf ^= 1;
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(&tempty[as], 0);  // the even CTA's MMA warp owns the accumulator hand-off
+      as ^= 1;
+      if (as == 0) aphase ^= 1;
+    }
+    if (lane == 0) ptx::tma_wait_group<0>();
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still signal or read
+  if (warp == 2) ptx::tmem_dealloc_2sm<C::TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
@@ -462,29 +667,48 @@ double tile_cost(int M, int N, int kb_total, int bn, int split_k) {
   return (double)waves * ((double)kb_per * (bn + 100.0) + 8.0 * bn);
 }
 
-void pick_config(int M, int N, int K, bool allow_split, int& tile_n, int& split_k) {
+// CTA-pair kernel: 256 x BN tiles over sms/2 clusters; a k-block costs ~(BN + 60) (half of B per CTA -> less L2 traffic)
+double pair_cost(int M, int N, int kb_total, int bn, int split_k) {
+  const int clusters = dlb_num_sms() / 2;
+  const int kb_per = (kb_total + split_k - 1) / split_k;
+  const int splits = (kb_total + kb_per - 1) / kb_per;
+  const long tiles = (long)((M + 2 * BM - 1) / (2 * BM)) * ((N + bn - 1) / bn) * splits;
+  const long waves = (tiles + clusters - 1) / clusters;
+  return (double)waves * ((double)kb_per * (bn + 60.0) + 8.0 * bn);
+}
+
+// tile_n / split_k: > 0 = forced by the caller, else chosen here. pair: -1 = choose, 0 = single-CTA kernel, 1 = CTA pair.
+void pick_config(int M, int N, int K, bool allow_split, int& tile_n, int& split_k, int& pair) {
   const int kb_total = (K + BK - 1) / BK;
   const int cands[4] = {256, 192, 128, 64};
   const int splits[6] = {1, 2, 4, 8, 16, 32};
   double best = 1e300;
-  int best_bn = 128, best_sk = 1;
-  for (int i = 0; i < 4; ++i) {
-    const int bn = cands[i];
-    if (tile_n > 0 && bn != tile_n) continue;
-    if (tile_n <= 0 && bn == 64 && N > 64) continue;
-    if (tile_n <= 0 && bn > 64 && N <= 64) continue;
-    for (int j = 0; j < 6; ++j) {
-      const int sk = splits[j];
-      if (split_k > 0 && sk != split_k) continue;
-      if (sk > 1 && (!allow_split || kb_total / sk < 4)) continue;
-      const double c = tile_cost(M, N, kb_total, bn, sk);
-      if (c < best * (1.0 - 1e-9)) { best = c; best_bn = bn; best_sk = sk; }
+  int best_bn = 128, best_sk = 1, best_pair = 0;
+  for (int pr = 0; pr < 2; ++pr) {
+    if (pair >= 0 && pr != pair) continue;
+    if (pr == 1 && (M <= 128 || N <= 64)) continue;  // a pair needs two row tiles and whole 64-column halves
+    for (int i = 0; i < 4; ++i) {
+      const int bn = cands[i];
+      if (tile_n > 0 && bn != tile_n) continue;
+      if (pr == 1 && bn != 256 && bn != 128) continue;
+      if (tile_n <= 0 && bn == 64 && N > 64) continue;
+      if (tile_n <= 0 && bn > 64 && N <= 64) continue;
+      for (int j = 0; j < 6; ++j) {
+        const int sk = splits[j];
+        if (split_k > 0 && sk != split_k) continue;
+        if (sk > 1 && (!allow_split || kb_total / sk < 4)) continue;
+        const double c = pr ? pair_cost(M, N, kb_total, bn, sk) : tile_cost(M, N, kb_total, bn, sk);
+        if (c < best * (1.0 - 1e-9)) { best = c; best_bn = bn; best_sk = sk; best_pair = pr; }
+      }
     }
   }
   if (tile_n <= 0) tile_n = best_bn;
   if (split_k <= 0) split_k = best_sk;
+  pair = best_pair;
 }
 
+int dispatch_pair(int bn, int a_mn, int b_mn, int out_mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                  const float* bias, int M, int N, int K, int split_k, cudaStream_t s);
 }  // namespace
 
 // See include/diffulab_b200.h for the contract.
@@ -509,7 +733,8 @@ DLB_EXPORT int dlb_gemm_bf16(const void* A, const void* B, void* Cout, const flo
               "gemm: tile_n %d unsupported", tile_n);
   if (split_k < 0) split_k = 1;
   int bn = tile_n;
-  pick_config((int)M, (int)N, (int)K, out_mode == OUT_F32_ADD, bn, split_k);
+  int pair = (tile_n == 64 || tile_n == 192) ? 0 : -1;
+  pick_config((int)M, (int)N, (int)K, out_mode == OUT_F32_ADD, bn, split_k, pair);
   if (split_k > kb_total) split_k = kb_total;
   if (split_k > 1) {
     const int kb_per = (kb_total + split_k - 1) / split_k;
@@ -522,13 +747,14 @@ DLB_EXPORT int dlb_gemm_bf16(const void* A, const void* B, void* Cout, const flo
   if (!a_mn_major) rc = encode2d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, K, M, lda, BK, BM);
   else rc = encode2d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda, 64, BK);
   if (rc) return rc;
-  if (!b_mn_major) rc = encode2d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, K, N, ldb, BK, bn);
+  if (!b_mn_major) rc = encode2d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, K, N, ldb, BK, pair ? bn / 2 : bn);
   else rc = encode2d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, N, K, ldb, 64, BK);
   if (rc) return rc;
   if (out_mode == OUT_BF16) rc = encode2d(&tc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Cout, N, M, ldc, 64, 32);
   else rc = encode2d(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Cout, N, M, ldc, 32, 32);
   if (rc) return rc;
 
+  if (pair) return dispatch_pair(bn, a_mn_major, b_mn_major, out_mode, ta, tb, tc, bias, (int)M, (int)N, (int)K, split_k, stream);
   switch (bn) {
     case 64: return dispatch_major<64>(a_mn_major, b_mn_major, out_mode, ta, tb, tc, bias, M, N, K, split_k, stream);
     case 128: return dispatch_major<128>(a_mn_major, b_mn_major, out_mode, ta, tb, tc, bias, M, N, K, split_k, stream);
@@ -607,4 +833,84 @@ DLB_EXPORT int dlb_gemm_swiglu_bwd_bf16(const void* dY, const void* W2, const vo
   kern<<<grid, 256, C::SMEM_BYTES, stream>>>(ta, tb, tc, tc2, nullptr, (int)M, (int)F, (int)D, 1);
   dlb_count_launch();
   return dlb_check_launch("gemm_swiglu_bwd");
+}
+
+
+namespace {
+template <int BN, bool A_MN, bool B_MN, int OUT>
+int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const float* bias, int M, int N, int K, int split_k,
+            cudaStream_t stream) {
+  using C = Cfg2<BN>;
+  auto kern = gemm2_tcgen05_kernel<BN, A_MN, B_MN, OUT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    DLB_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(smem=%d): %s", C::SMEM_BYTES, cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int mb = (M + 2 * BM - 1) / (2 * BM), nb = (N + BN - 1) / BN;
+  const int tiles = mb * nb * split_k;
+  const int max_clusters = dlb_num_sms() / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  kern<<<2 * clusters, 256, C::SMEM_BYTES, stream>>>(ta, tb, tc, bias, M, N, K, split_k);
+  dlb_count_launch();
+  return dlb_check_launch("gemm2_tcgen05");
+}
+template <int BN, bool A_MN, bool B_MN>
+int dispatch_out2(int out_mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const float* bias, int M, int N,
+                  int K, int split_k, cudaStream_t s) {
+  switch (out_mode) {
+    case OUT_BF16: return launch2<BN, A_MN, B_MN, OUT_BF16>(ta, tb, tc, bias, M, N, K, split_k, s);
+    case OUT_F32: return launch2<BN, A_MN, B_MN, OUT_F32>(ta, tb, tc, bias, M, N, K, split_k, s);
+    default: return launch2<BN, A_MN, B_MN, OUT_F32_ADD>(ta, tb, tc, bias, M, N, K, split_k, s);
+  }
+}
+template <int BN>
+int dispatch_major2(int a_mn, int b_mn, int out_mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                    const float* bias, int M, int N, int K, int split_k, cudaStream_t s) {
+  if (!a_mn && !b_mn) return dispatch_out2<BN, false, false>(out_mode, ta, tb, tc, bias, M, N, K, split_k, s);
+  if (!a_mn && b_mn) return dispatch_out2<BN, false, true>(out_mode, ta, tb, tc, bias, M, N, K, split_k, s);
+  if (a_mn && !b_mn) return dispatch_out2<BN, true, false>(out_mode, ta, tb, tc, bias, M, N, K, split_k, s);
+  return dispatch_out2<BN, true, true>(out_mode, ta, tb, tc, bias, M, N, K, split_k, s);
+}
+int dispatch_pair(int bn, int a_mn, int b_mn, int out_mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                  const float* bias, int M, int N, int K, int split_k, cudaStream_t s) {
+  if (bn == 128) return dispatch_major2<128>(a_mn, b_mn, out_mode, ta, tb, tc, bias, M, N, K, split_k, s);
+  return dispatch_major2<256>(a_mn, b_mn, out_mode, ta, tb, tc, bias, M, N, K, split_k, s);
+}
+}  // namespace
+
+// CTA-pair (cta_group::2, 256 x tile_n tiles) version of dlb_gemm_bf16: same contract; tile_n in {128, 256}; split_k >= 1.
+DLB_EXPORT int dlb_gemm2_bf16(const void* A, const void* B, void* Cout, const float* bias, int64_t M, int64_t N, int64_t K,
+                              int64_t lda, int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major, int out_mode, int split_k,
+                              int tile_n, cudaStream_t stream) {
+  DLB_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), DLB_ERR_SHAPE, "gemm2: bad problem");
+  DLB_REQUIRE(out_mode >= 0 && out_mode <= 2, DLB_ERR_UNSUPPORTED, "gemm2: bad out_mode %d", out_mode);
+  DLB_REQUIRE(tile_n == 128 || tile_n == 256, DLB_ERR_UNSUPPORTED, "gemm2: tile_n must be 128 or 256 (got %d)", tile_n);
+  DLB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, DLB_ERR_ALIGN, "gemm2: lda/ldb must be multiples of 8 elements");
+  const int c_elem = out_mode == OUT_BF16 ? 2 : 4;
+  DLB_REQUIRE((ldc * c_elem) % 16 == 0, DLB_ERR_ALIGN, "gemm2: ldc*elem must be a multiple of 16 bytes");
+  DLB_REQUIRE(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 && ((uintptr_t)Cout % 16) == 0, DLB_ERR_ALIGN, "gemm2: pointers must be 16-byte aligned");
+  if (split_k < 1) split_k = 1;
+  if (split_k > 1) DLB_REQUIRE(out_mode == OUT_F32_ADD, DLB_ERR_UNSUPPORTED, "gemm2: split_k>1 needs out_mode=2");
+  const int kb_total = (int)((K + BK - 1) / BK);
+  if (split_k > kb_total) split_k = kb_total;
+  if (split_k > 1) {
+    const int kb_per = (kb_total + split_k - 1) / split_k;
+    split_k = (kb_total + kb_per - 1) / kb_per;
+  }
+  const int bn = tile_n;
+  CUtensorMap ta, tb, tc;
+  int rc;
+  if (!a_mn_major) rc = encode2d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, K, M, lda, BK, BM);
+  else rc = encode2d(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, M, K, lda, 64, BK);
+  if (rc) return rc;
+  if (!b_mn_major) rc = encode2d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, K, N, ldb, BK, bn / 2);
+  else rc = encode2d(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, B, N, K, ldb, 64, BK);
+  if (rc) return rc;
+  if (out_mode == OUT_BF16) rc = encode2d(&tc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Cout, N, M, ldc, 64, 32);
+  else rc = encode2d(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Cout, N, M, ldc, 32, 32);
+  if (rc) return rc;
+  if (bn == 128) return dispatch_major2<128>(a_mn_major, b_mn_major, out_mode, ta, tb, tc, bias, (int)M, (int)N, (int)K, split_k, stream);
+  return dispatch_major2<256>(a_mn_major, b_mn_major, out_mode, ta, tb, tc, bias, (int)M, (int)N, (int)K, split_k, stream);
 }

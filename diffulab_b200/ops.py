@@ -86,6 +86,7 @@ def gemm(
     accumulate: bool = False,
     split_k: int | None = None,
     tile_n: int = 0,
+    pair: bool = False,
 ) -> Tensor:
     """C[M,N] (+)= A @ B^T (+ bias) with bf16 operands and fp32 accumulation on tcgen05.
 
@@ -119,9 +120,11 @@ def gemm(
         raise ValueError("gemm: bias must be a contiguous fp32 vector of length N")
     kind = "gemm_wgrad" if (a_mn and b_mn) else ("gemm_dgrad" if b_mn else "gemm_fwd")
     with _Timed(f"{kind} {M}x{N}x{K}" if _prof is not None else kind, 2.0 * M * N * K):
-        rc = _lib.load().dlb_gemm_bf16(
+        fn = _lib.load().dlb_gemm2_bf16 if pair else _lib.load().dlb_gemm_bf16  # pair: force the CTA-pair kernel (tests / benches)
+        rc = fn(
             a.data_ptr(), b.data_ptr(), out.data_ptr(), _ptr(bias), M, N, K,
-            a.stride(0), b.stride(0), out.stride(0), int(a_mn), int(b_mn), mode, split_k, tile_n, _stream(),
+            a.stride(0), b.stride(0), out.stride(0), int(a_mn), int(b_mn), mode, max(split_k, 1) if pair else split_k,
+            (tile_n or 256) if pair else tile_n, _stream(),
         )
     _lib.check(rc, "dlb_gemm_bf16")
     return out

@@ -160,3 +160,36 @@ def test_gemm_swiglu_bwd_fused_matches_unfused(cuda_device, M, F, D):
     sg = torch.sigmoid(a)
     ref = torch.cat([dact * gg * sg * (1 + a * (1 - sg)), dact * a * sg], 1)
     assert ((got.float() - ref).norm() / ref.norm()).item() < 1e-2
+
+
+@pytest.mark.parametrize("tile_n", [128, 256])
+@pytest.mark.parametrize("mode", ["fwd", "dgrad", "wgrad", "wgrad_splitk", "fwd_bias_f32"])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 384, 192), (1000, 520, 200), (4096, 1152, 1152)])
+def test_gemm_cta_pair_matches_single_cta(cuda_device, M, N, K, mode, tile_n):
+    """cta_group::2 kernel == single-CTA kernel bit for bit (same k-order of fp32 accumulation), all operand majors."""
+    from diffulab_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    rnd = lambda *s: (torch.randn(*s, device="cuda", generator=g) * 0.5).bfloat16()  # noqa: E731
+    if mode in ("fwd", "fwd_bias_f32"):
+        a, b, kw = rnd(M, K), rnd(N, K), {}
+        if mode == "fwd_bias_f32":
+            kw = dict(bias=torch.randn(N, device="cuda", generator=g), out_dtype=torch.float32)
+    elif mode == "dgrad":
+        a, b, kw = rnd(M, K), rnd(K, N), dict(b_mn=True)
+    else:
+        a, b, kw = rnd(K, M), rnd(K, N), dict(a_mn=True, b_mn=True)
+    if mode.startswith("wgrad"):
+        sk = 4 if mode == "wgrad_splitk" else 1
+        ref = torch.zeros(M, N, device="cuda")
+        got = torch.zeros(M, N, device="cuda")
+        ops.gemm(a, b, out=ref, accumulate=True, split_k=1, tile_n=192, **kw)  # tile_n 192 exists only in the single-CTA kernel
+        ops.gemm(a, b, out=got, accumulate=True, split_k=sk, tile_n=tile_n, pair=True, **kw)
+        if sk == 1:
+            assert torch.equal(got, ref)
+        else:
+            torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-3)
+    else:
+        ref = ops.gemm(a, b, tile_n=192, **kw)  # single-CTA kernel
+        got = ops.gemm(a, b, tile_n=tile_n, pair=True, **kw)
+        assert torch.equal(got, ref)
