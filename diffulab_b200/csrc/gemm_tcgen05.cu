@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cudaTypedefs.h>
+#include <cstdlib>
 
 namespace {
 
@@ -53,6 +54,177 @@ __device__ __forceinline__ TileCoord decode_tile(int t, int mb, int nb, int kb_t
   c.kb0 = c.ks * kb_per;
   c.kb1 = min(c.kb0 + kb_per, kb_total);
   return c;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Epilogue of one accumulator tile for one epilogue warp (shared by the single-CTA and the CTA-pair kernels):
+// this warp's 32 TMEM lanes x the tile's columns -> registers -> 128B-swizzled staging -> TMA store / reduce-add,
+// with the optional fused SwiGLU forward / backward math (see the kernel comments).
+// ---------------------------------------------------------------------------------------------------------
+template <int BN, int OUT, int EPI>
+__device__ __forceinline__ void epilogue_tile(const CUtensorMap& tmC, const CUtensorMap& tmC2, const float* __restrict__ bias,
+                                              bool add_bias, uint8_t* sE, uint64_t* lbar, int ew, int lane, int M, int N, int row0,
+                                              int n_blk, uint32_t taddr, int& ebuf, uint32_t& hphase) {
+  constexpr bool SWIGLU = EPI == EPI_SWIGLU, SWIGLU_BWD = EPI == EPI_SWIGLU_BWD;
+  constexpr int BNT = SWIGLU ? BN / 2 : BN;
+  constexpr int CH = (OUT == OUT_BF16) ? 64 : 32;  // columns per 128-byte staging row
+  uint8_t* ebase = sE + ew * (2 * EPI_BUF_BYTES);
+  (void)ebase; (void)lbar; (void)hphase; (void)bias; (void)add_bias;
+  if constexpr (SWIGLU_BWD) {
+    uint8_t* wbase = sE + ew * (4 * EPI_BUF_BYTES);  // [slot][a | g] tiles of 32 rows x 128 B (128B-swizzled, as TMA lays them)
+    uint64_t* lb = lbar + ew * 2;
+    const bool rows_ok = row0 < M;
+#pragma unroll 1
+    for (int slot = 0; slot < 2; ++slot) {
+      const int col0 = n_blk * BN + slot * 64;
+      uint8_t* abuf = wbase + slot * 2 * EPI_BUF_BYTES;
+      uint8_t* gbuf = abuf + EPI_BUF_BYTES;
+      uint32_t r[64];
+      ptx::tmem_ld32(taddr + slot * 64, r);
+      ptx::tmem_ld32(taddr + slot * 64 + 32, r + 32);
+      ptx::tmem_ld_wait();
+      if (rows_ok) ptx::mbar_wait(&lb[slot], hphase);
+      uint8_t* rowa = abuf + lane * 128;
+      uint8_t* rowg = gbuf + lane * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int off = (j ^ (lane & 7)) << 4;
+        const bf16x8 av = *reinterpret_cast<const bf16x8*>(rowa + off), gv = *reinterpret_cast<const bf16x8*>(rowg + off);
+        float a[8], g[8], da[8], dg[8];
+        unpack8(av, a);
+        unpack8(gv, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float go = bf16_round(__uint_as_float(r[8 * j + i]));  // d(act) as the bf16 tensor autocast would hold
+          const float hh = 0.5f * a[i];
+          float th;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hh));
+          const float sg = fmaf(0.5f, th, 0.5f);  // sigmoid(a)
+          da[i] = go * g[i] * sg * (1.f + a[i] * (1.f - sg));
+          dg[i] = go * a[i] * sg;
+        }
+        *reinterpret_cast<bf16x8*>(rowa + off) = pack8(da);
+        *reinterpret_cast<bf16x8*>(rowg + off) = pack8(dg);
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && rows_ok) {
+        ptx::tma_store_2d(&tmC, abuf, col0, row0);
+        ptx::tma_store_2d(&tmC, gbuf, N + col0, row0);
+        ptx::tma_commit_group();
+      }
+    }
+    if (rows_ok) hphase ^= 1;  // the barriers are only armed for tiles whose rows exist
+  } else if constexpr (SWIGLU) {
+    // 64-column chunks of the two halves: h_a -> tmC(col), h_g -> tmC(N + col), silu(a) * g -> tmC2(col)
+    auto stage_store = [&](const uint32_t* packed, const CUtensorMap* tm, int col) {
+      uint8_t* buf = ebase + ebuf * EPI_BUF_BYTES;
+      if (lane == 0) ptx::tma_wait_group_read<1>();
+      __syncwarp();
+      uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && row0 < M) {
+        ptx::tma_store_2d(tm, buf, col, row0);
+        ptx::tma_commit_group();
+      }
+      ebuf ^= 1;
+    };
+    auto load_pack = [&](uint32_t tcol, int bias_col, uint32_t* packed) {  // 64 fp32 columns (+ bias) -> 32 packed bf16 pairs
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        uint32_t r[32];
+        ptx::tmem_ld32(taddr + tcol + hlf * 32, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
+          if (add_bias) { v0 += __ldg(bias + bias_col + hlf * 32 + i); v1 += __ldg(bias + bias_col + hlf * 32 + i + 1); }
+          packed[hlf * 16 + i / 2] = pack_bf16x2(v0, v1);
+        }
+      }
+    };
+#pragma unroll 1
+    for (int c = 0; c < BNT; c += 64) {
+      const int col0 = n_blk * BNT + c;
+      if (col0 >= N) break;
+      uint32_t pa[32], pg[32];
+      load_pack(c, col0, pa);
+      stage_store(pa, &tmC, col0);
+      load_pack(BNT + c, N + col0, pg);
+      stage_store(pg, &tmC, N + col0);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {  // out = bf16(bf16(silu(a)) * g) on the bf16-rounded pre-activations (autocast numerics)
+        const float2 a = unpack_bf16x2(pa[i]), g = unpack_bf16x2(pg[i]);
+        pa[i] = pack_bf16x2(bf16_round(silu_fast(a.x)) * g.x, bf16_round(silu_fast(a.y)) * g.y);
+      }
+      stage_store(pa, &tmC2, col0);
+    }
+  } else {
+#pragma unroll 1
+  for (int c = 0; c < BN; c += CH) {
+    const int col0 = n_blk * BN + c;
+    if (col0 >= N) break;
+    uint32_t r[CH];
+    ptx::tmem_ld32(taddr + c, r);
+    if constexpr (CH == 64) ptx::tmem_ld32(taddr + c + 32, r + 32);
+    ptx::tmem_ld_wait();
+    if (add_bias) {
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const float bv = (col0 + i < N) ? __ldg(bias + col0 + i) : 0.f;
+        r[i] = __float_as_uint(__uint_as_float(r[i]) + bv);
+      }
+    }
+    uint8_t* buf = ebase + ebuf * EPI_BUF_BYTES;
+    if (lane == 0) ptx::tma_wait_group_read<1>();  // the store that last read this buffer is done
+    __syncwarp();
+    uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint4 v;
+      if constexpr (OUT == OUT_BF16) {
+        v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+        v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+        v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+        v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+      } else {
+        v.x = r[4 * j + 0]; v.y = r[4 * j + 1]; v.z = r[4 * j + 2]; v.w = r[4 * j + 3];
+      }
+      *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = v;  // 128B swizzle: chunk ^= row % 8
+    }
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && row0 < M) {
+      if constexpr (OUT == OUT_F32_ADD) ptx::tma_reduce_add_2d(&tmC, buf, col0, row0);
+      else ptx::tma_store_2d(&tmC, buf, col0, row0);
+      ptx::tma_commit_group();
+    }
+    ebuf ^= 1;
+  }
+  }
+}
+
+// SWIGLU_BWD: TMA-prefetch the (a, g) tiles of H that this warp's rows of the given output tile will need
+template <int BN>
+__device__ __forceinline__ void issue_h_tile_loads(const CUtensorMap& tmC2, uint8_t* sE, uint64_t* lbar, int ew, int lane, int M, int N,
+                                                   int r0, int n_blk, bool wait_stores) {
+  if (lane == 0 && r0 < M) {
+    if (wait_stores) ptx::tma_wait_group_read<0>();  // my staged stores have been read: the slots are free
+    uint8_t* wb_ = sE + ew * (4 * EPI_BUF_BYTES);
+#pragma unroll
+    for (int slot = 0; slot < 2; ++slot) {
+      const int col = n_blk * BN + slot * 64;
+      uint64_t* b = &lbar[ew * 2 + slot];
+      ptx::mbar_expect_tx(b, 2 * EPI_BUF_BYTES);
+      ptx::tma_load_2d(wb_ + slot * 2 * EPI_BUF_BYTES, &tmC2, b, col, r0);
+      ptx::tma_load_2d(wb_ + slot * 2 * EPI_BUF_BYTES + EPI_BUF_BYTES, &tmC2, b, N + col, r0);
+    }
+  }
+  __syncwarp();
 }
 
 // SWIGLU variant (fc1 of the packed-SwiGLU MLP, reference nn.py:478-486 + mmdit.py:260-264): the weight is [2F, K]
@@ -193,8 +365,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> swizzled smem -> TMA store =====================
     const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
-    constexpr int CH = (OUT == OUT_BF16) ? 64 : 32;  // columns per 128-byte staging row
-    uint8_t* ebase = sE + ew * (2 * EPI_BUF_BYTES);
     int ebuf = 0;
     int as = 0;
     uint32_t aphase = 0;
@@ -202,20 +372,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     [[maybe_unused]] auto issue_h_loads = [&](int tn, bool wait_stores) {
       if constexpr (SWIGLU_BWD) {
         const TileCoord tcn = decode_tile(tn, mb, nb, kb_total, kb_per);
-        const int r0 = tcn.m_blk * BM + ew * 32;
-        if (lane == 0 && r0 < M) {
-          if (wait_stores) ptx::tma_wait_group_read<0>();  // my staged stores have been read: the slots are free
-          uint8_t* wb_ = sE + ew * (4 * EPI_BUF_BYTES);
-#pragma unroll
-          for (int slot = 0; slot < 2; ++slot) {
-            const int col = tcn.n_blk * BN + slot * 64;
-            uint64_t* b = &lbar[ew * 2 + slot];
-            ptx::mbar_expect_tx(b, 2 * EPI_BUF_BYTES);
-            ptx::tma_load_2d(wb_ + slot * 2 * EPI_BUF_BYTES, &tmC2, b, col, r0);
-            ptx::tma_load_2d(wb_ + slot * 2 * EPI_BUF_BYTES + EPI_BUF_BYTES, &tmC2, b, N + col, r0);
-          }
-        }
-        __syncwarp();
+        issue_h_tile_loads<BN>(tmC2, sE, lbar, ew, lane, M, N, tcn.m_blk * BM + ew * 32, tcn.n_blk, wait_stores);
       }
     };
     if constexpr (SWIGLU_BWD) {
@@ -228,142 +385,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row0 = tc.m_blk * BM + ew * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
       const bool add_bias = (bias != nullptr) && (tc.ks == 0);
-      if constexpr (SWIGLU_BWD) {
-        uint8_t* wbase = sE + ew * (4 * EPI_BUF_BYTES);  // [slot][a | g] tiles of 32 rows x 128 B (128B-swizzled, as TMA lays them)
-        uint64_t* lb = lbar + ew * 2;
-        const bool rows_ok = row0 < M;
-#pragma unroll 1
-        for (int slot = 0; slot < 2; ++slot) {
-          const int col0 = tc.n_blk * BN + slot * 64;
-          uint8_t* abuf = wbase + slot * 2 * EPI_BUF_BYTES;
-          uint8_t* gbuf = abuf + EPI_BUF_BYTES;
-          uint32_t r[64];
-          ptx::tmem_ld32(taddr + slot * 64, r);
-          ptx::tmem_ld32(taddr + slot * 64 + 32, r + 32);
-          ptx::tmem_ld_wait();
-          if (rows_ok) ptx::mbar_wait(&lb[slot], hphase);
-          uint8_t* rowa = abuf + lane * 128;
-          uint8_t* rowg = gbuf + lane * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int off = (j ^ (lane & 7)) << 4;
-            const bf16x8 av = *reinterpret_cast<const bf16x8*>(rowa + off), gv = *reinterpret_cast<const bf16x8*>(rowg + off);
-            float a[8], g[8], da[8], dg[8];
-            unpack8(av, a);
-            unpack8(gv, g);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float go = bf16_round(__uint_as_float(r[8 * j + i]));  // d(act) as the bf16 tensor autocast would hold
-              const float hh = 0.5f * a[i];
-              float th;
-              asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hh));
-              const float sg = fmaf(0.5f, th, 0.5f);  // sigmoid(a)
-              da[i] = go * g[i] * sg * (1.f + a[i] * (1.f - sg));
-              dg[i] = go * a[i] * sg;
-            }
-            *reinterpret_cast<bf16x8*>(rowa + off) = pack8(da);
-            *reinterpret_cast<bf16x8*>(rowg + off) = pack8(dg);
-          }
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0 && rows_ok) {
-            ptx::tma_store_2d(&tmC, abuf, col0, row0);
-            ptx::tma_store_2d(&tmC, gbuf, N + col0, row0);
-            ptx::tma_commit_group();
-          }
-        }
-        if (rows_ok) hphase ^= 1;  // the barriers are only armed for tiles whose rows exist
-      } else if constexpr (SWIGLU) {
-        // 64-column chunks of the two halves: h_a -> tmC(col), h_g -> tmC(N + col), silu(a) * g -> tmC2(col)
-        auto stage_store = [&](const uint32_t* packed, const CUtensorMap* tm, int col) {
-          uint8_t* buf = ebase + ebuf * EPI_BUF_BYTES;
-          if (lane == 0) ptx::tma_wait_group_read<1>();
-          __syncwarp();
-          uint8_t* rowp = buf + lane * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0 && row0 < M) {
-            ptx::tma_store_2d(tm, buf, col, row0);
-            ptx::tma_commit_group();
-          }
-          ebuf ^= 1;
-        };
-        auto load_pack = [&](uint32_t tcol, int bias_col, uint32_t* packed) {  // 64 fp32 columns (+ bias) -> 32 packed bf16 pairs
-#pragma unroll
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            uint32_t r[32];
-            ptx::tmem_ld32(taddr + tcol + hlf * 32, r);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
-              if (add_bias) { v0 += __ldg(bias + bias_col + hlf * 32 + i); v1 += __ldg(bias + bias_col + hlf * 32 + i + 1); }
-              packed[hlf * 16 + i / 2] = pack_bf16x2(v0, v1);
-            }
-          }
-        };
-#pragma unroll 1
-        for (int c = 0; c < BNT; c += 64) {
-          const int col0 = tc.n_blk * BNT + c;
-          if (col0 >= N) break;
-          uint32_t pa[32], pg[32];
-          load_pack(c, col0, pa);
-          stage_store(pa, &tmC, col0);
-          load_pack(BNT + c, N + col0, pg);
-          stage_store(pg, &tmC, N + col0);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {  // out = bf16(bf16(silu(a)) * g) on the bf16-rounded pre-activations (autocast numerics)
-            const float2 a = unpack_bf16x2(pa[i]), g = unpack_bf16x2(pg[i]);
-            pa[i] = pack_bf16x2(bf16_round(silu_fast(a.x)) * g.x, bf16_round(silu_fast(a.y)) * g.y);
-          }
-          stage_store(pa, &tmC2, col0);
-        }
-      } else {
-#pragma unroll 1
-      for (int c = 0; c < BN; c += CH) {
-        const int col0 = tc.n_blk * BN + c;
-        if (col0 >= N) break;
-        uint32_t r[CH];
-        ptx::tmem_ld32(taddr + c, r);
-        if constexpr (CH == 64) ptx::tmem_ld32(taddr + c + 32, r + 32);
-        ptx::tmem_ld_wait();
-        if (add_bias) {
-#pragma unroll
-          for (int i = 0; i < CH; ++i) {
-            const float bv = (col0 + i < N) ? __ldg(bias + col0 + i) : 0.f;
-            r[i] = __float_as_uint(__uint_as_float(r[i]) + bv);
-          }
-        }
-        uint8_t* buf = ebase + ebuf * EPI_BUF_BYTES;
-        if (lane == 0) ptx::tma_wait_group_read<1>();  // the store that last read this buffer is done
-        __syncwarp();
-        uint8_t* rowp = buf + lane * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 v;
-          if constexpr (OUT == OUT_BF16) {
-            v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
-            v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
-            v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
-            v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
-          } else {
-            v.x = r[4 * j + 0]; v.y = r[4 * j + 1]; v.z = r[4 * j + 2]; v.w = r[4 * j + 3];
-          }
-          *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = v;  // 128B swizzle: chunk ^= row % 8
-        }
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0 && row0 < M) {
-          if constexpr (OUT == OUT_F32_ADD) ptx::tma_reduce_add_2d(&tmC, buf, col0, row0);
-          else ptx::tma_store_2d(&tmC, buf, col0, row0);
-          ptx::tma_commit_group();
-        }
-        ebuf ^= 1;
-      }
-      }
+      epilogue_tile<BN, OUT, EPI>(tmC, tmC2, bias, add_bias, sE, lbar, ew, lane, M, N, row0, tc.n_blk, taddr, ebuf, hphase);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[as]);
@@ -392,39 +414,48 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //   tfull[a]  (each CTA)  tcgen05.commit multicast: accumulator stage a is complete; every CTA drains its own 128 lanes
 //   tempty[a] (even CTA)  2 x EPI_WARPS arrivals (the odd CTA's epilogue warps arrive remotely)
 // ---------------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int EPIB = EPI_BYTES>
 struct Cfg2 {
   static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_TILE_BYTES + B_HALF_BYTES;  // per CTA
-  static constexpr int STAGES_RAW = (SMEM_LIMIT - 1024 - 256 - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (SMEM_LIMIT - 1024 - 256 - EPIB) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + 256;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPIB + 256;
 };
 
-template <int BN, bool A_MN, bool B_MN, int OUT>
+// The fused SwiGLU epilogues carry over unchanged (every CTA drains its own 128 rows). SWIGLU: the even CTA loads the
+// weight rows of the silu-ed half, the odd CTA the matching rows of the other half — exactly the pair's B split.
+template <int BN, bool A_MN, bool B_MN, int OUT, int EPI = EPI_NONE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K, int split_k) {
+                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+                     const float* __restrict__ bias, int M, int N, int K, int split_k) {
+  constexpr bool SWIGLU = EPI == EPI_SWIGLU, SWIGLU_BWD = EPI == EPI_SWIGLU_BWD;
   static_assert(!B_MN || (BN / 2) % 64 == 0, "MN-major B: each CTA's half must be whole 64-column blocks");
-  using C = Cfg2<BN>;
+  static_assert(!SWIGLU || (!A_MN && !B_MN && OUT == OUT_BF16 && BN == 256), "SWIGLU epilogue: K-major bf16 256-wide tiles only");
+  static_assert(!SWIGLU_BWD || (!A_MN && B_MN && OUT == OUT_BF16 && BN == 128), "SWIGLU_BWD epilogue: dgrad bf16 128-wide tiles only");
+  constexpr int BNT = SWIGLU ? BN / 2 : BN;
+  constexpr int EPIB = SWIGLU_BWD ? EPI_BWD_BYTES : EPI_BYTES;
+  using C = Cfg2<BN, EPIB>;
   constexpr int NST = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = sA + NST * A_TILE_BYTES;
   uint8_t* sE = sB + NST * C::B_HALF_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sE + EPI_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sE + EPIB);
   uint64_t* empty = full + NST;
   uint64_t* tfull = empty + NST;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* lbar = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lbar + 2 * EPI_WARPS);
 
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int rank = (int)ptx::cluster_ctarank();  // 0 = the even ("leader") CTA, which issues the MMAs
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-  const int mb = (M + 2 * BM - 1) / (2 * BM), nb = (N + BN - 1) / BN;
+  const int mb = (M + 2 * BM - 1) / (2 * BM), nb = (N + BNT - 1) / BNT;
   const int kb_total = (K + BK - 1) / BK;
   const int kb_per = (kb_total + split_k - 1) / split_k;
   const int tiles = mb * nb * split_k;
@@ -433,6 +464,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
     ptx::prefetch_tmap(&tmC);
+    if constexpr (SWIGLU || SWIGLU_BWD) ptx::prefetch_tmap(&tmC2);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NST; ++i) {
@@ -443,6 +475,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       ptx::mbar_init(&tfull[i], 1);
       ptx::mbar_init(&tempty[i], 2 * EPI_WARPS);
     }
+    for (int i = 0; i < 2 * EPI_WARPS; ++i) ptx::mbar_init(&lbar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) ptx::tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot);
@@ -458,7 +491,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     for (int t = cluster_id; t < tiles; t += n_clusters) {
       const TileCoord tc = decode_tile(t, mb, nb, kb_total, kb_per);
       const int m0 = (tc.m_blk * 2 + rank) * BM;
-      const int n0 = tc.n_blk * BN + rank * (BN / 2);
+      const int n0 = SWIGLU ? (rank ? N : 0) + tc.n_blk * BNT : tc.n_blk * BN + rank * (BN / 2);
       for (int kb = tc.kb0; kb < tc.kb1; ++kb) {
         ptx::mbar_wait(&empty[stage], phase ^ 1);
         if (ptx::elect_one()) {
@@ -519,11 +552,19 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own 128 rows): TMEM -> registers -> swizzled smem -> TMA store =====================
     const int ew = warp - 4;
-    constexpr int CH = (OUT == OUT_BF16) ? 64 : 32;
-    uint8_t* ebase = sE + ew * (2 * EPI_BUF_BYTES);
     int ebuf = 0;
     int as = 0;
     uint32_t aphase = 0;
+    [[maybe_unused]] uint32_t hphase = 0;
+    [[maybe_unused]] auto issue_h_loads = [&](int tn, bool wait_stores) {
+      if constexpr (SWIGLU_BWD) {
+        const TileCoord tcn = decode_tile(tn, mb, nb, kb_total, kb_per);
+        issue_h_tile_loads<BN>(tmC2, sE, lbar, ew, lane, M, N, (tcn.m_blk * 2 + rank) * BM + ew * 32, tcn.n_blk, wait_stores);
+      }
+    };
+    if constexpr (SWIGLU_BWD) {
+      if (cluster_id < tiles) issue_h_loads(cluster_id, false);
+    }
     for (int t = cluster_id; t < tiles; t += n_clusters) {
       const TileCoord tc = decode_tile(t, mb, nb, kb_total, kb_per);
       ptx::mbar_wait(&tfull[as], aphase);
@@ -531,52 +572,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int row0 = (tc.m_blk * 2 + rank) * BM + ew * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
       const bool add_bias = (bias != nullptr) && (tc.ks == 0);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += CH) {
-        const int col0 = tc.n_blk * BN + c;
-        if (col0 >= N) break;
-        uint32_t r[CH];
-        ptx::tmem_ld32(taddr + c, r);
-        if constexpr (CH == 64) ptx::tmem_ld32(taddr + c + 32, r + 32);
-        ptx::tmem_ld_wait();
-        if (add_bias) {
-#pragma unroll
-          for (int i = 0; i < CH; ++i) {
-            const float bv = (col0 + i < N) ? __ldg(bias + col0 + i) : 0.f;
-            r[i] = __float_as_uint(__uint_as_float(r[i]) + bv);
-          }
-        }
-        uint8_t* buf = ebase + ebuf * EPI_BUF_BYTES;
-        if (lane == 0) ptx::tma_wait_group_read<1>();
-        __syncwarp();
-        uint8_t* rowp = buf + lane * 128;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 v;
-          if constexpr (OUT == OUT_BF16) {
-            v.x = pack_bf16x2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
-            v.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
-            v.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
-            v.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
-          } else {
-            v.x = r[4 * j + 0]; v.y = r[4 * j + 1]; v.z = r[4 * j + 2]; v.w = r[4 * j + 3];
-          }
-          *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) = v;
-        }
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0 && row0 < M) {
-          if constexpr (OUT == OUT_F32_ADD) ptx::tma_reduce_add_2d(&tmC, buf, col0, row0);
-          else ptx::tma_store_2d(&tmC, buf, col0, row0);
-          ptx::tma_commit_group();
-        }
-        ebuf ^= 1;
-      }
+      epilogue_tile<BN, OUT, EPI>(tmC, tmC2, bias, add_bias, sE, lbar, ew, lane, M, N, row0, tc.n_blk, taddr, ebuf, hphase);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(&tempty[as], 0);  // the even CTA's MMA warp owns the accumulator hand-off
       as ^= 1;
       if (as == 0) aphase ^= 1;
+      if constexpr (SWIGLU_BWD) {
+        if (t + n_clusters < tiles) issue_h_loads(t + n_clusters, true);
+      }
     }
     if (lane == 0) ptx::tma_wait_group<0>();
   }
@@ -783,6 +787,21 @@ DLB_EXPORT int dlb_gemm_swiglu_bf16(const void* A, const void* W, const float* b
   if (rc) return rc;
   rc = encode2d(&tc2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ACT, F, M, ldact, 64, 32);
   if (rc) return rc;
+  if (M > BM) {  // CTA-pair kernel: the even CTA stages the silu-ed half of the weight rows, the odd CTA the other half
+    using C2 = Cfg2<256>;
+    auto kern2 = gemm2_tcgen05_kernel<256, false, false, OUT_BF16, EPI_SWIGLU>;
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM_BYTES);
+      DLB_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(smem=%d): %s", C2::SMEM_BYTES, cudaGetErrorString(e));
+      attr2_set = true;
+    }
+    const int tiles2 = (int)(((M + 2 * BM - 1) / (2 * BM)) * (F / 128));
+    const int maxc = dlb_num_sms() / 2;
+    kern2<<<2 * (tiles2 < maxc ? tiles2 : maxc), 256, C2::SMEM_BYTES, stream>>>(ta, tb, tc, tc2, bias, (int)M, (int)F, (int)K, 1);
+    dlb_count_launch();
+    return dlb_check_launch("gemm2_swiglu");
+  }
   using C = Cfg<256>;
   auto kern = gemm_tcgen05_kernel<256, false, false, OUT_BF16, EPI_SWIGLU>;
   static bool attr_set = false;
@@ -820,6 +839,24 @@ DLB_EXPORT int dlb_gemm_swiglu_bwd_bf16(const void* dY, const void* W2, const vo
   if (rc) return rc;
   rc = encode2d(&tc2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, H, 2 * F, M, ldh, 64, 32);
   if (rc) return rc;
+  // The CTA-pair instantiation exists (and is parity-tested through DLB_SWIGLU_BWD_PAIR=1) but measured slower in the
+  // train step (12.4 vs 10.7 ms / step): this epilogue is the bottleneck and a pair does not shorten it.
+  static const bool use_pair = getenv("DLB_SWIGLU_BWD_PAIR") != nullptr;
+  if (use_pair && M > BM) {
+    using C2 = Cfg2<128, EPI_BWD_BYTES>;
+    auto kern2 = gemm2_tcgen05_kernel<128, false, true, OUT_BF16, EPI_SWIGLU_BWD>;
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      cudaError_t e = cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, C2::SMEM_BYTES);
+      DLB_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(smem=%d): %s", C2::SMEM_BYTES, cudaGetErrorString(e));
+      attr2_set = true;
+    }
+    const int tiles2 = (int)(((M + 2 * BM - 1) / (2 * BM)) * (F / 128));
+    const int maxc = dlb_num_sms() / 2;
+    kern2<<<2 * (tiles2 < maxc ? tiles2 : maxc), 256, C2::SMEM_BYTES, stream>>>(ta, tb, tc, tc2, nullptr, (int)M, (int)F, (int)D, 1);
+    dlb_count_launch();
+    return dlb_check_launch("gemm2_swiglu_bwd");
+  }
   using C = Cfg<128, EPI_BWD_BYTES>;
   auto kern = gemm_tcgen05_kernel<128, false, true, OUT_BF16, EPI_SWIGLU_BWD>;
   static bool attr_set = false;
@@ -852,7 +889,7 @@ int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
   const int tiles = mb * nb * split_k;
   const int max_clusters = dlb_num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  kern<<<2 * clusters, 256, C::SMEM_BYTES, stream>>>(ta, tb, tc, bias, M, N, K, split_k);
+  kern<<<2 * clusters, 256, C::SMEM_BYTES, stream>>>(ta, tb, tc, tc, bias, M, N, K, split_k);
   dlb_count_launch();
   return dlb_check_launch("gemm2_tcgen05");
 }

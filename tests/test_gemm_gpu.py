@@ -122,7 +122,7 @@ def test_gemm_bad_args(cuda_device):
         ops.gemm(a, b)  # K=12 rows are 24 bytes: violates the 16-byte stride rule, must fail loudly
 
 
-@pytest.mark.parametrize("M,F,K,with_bias", [(256, 128, 64, False), (300, 256, 192, True), (1024, 1152, 288, False), (4096, 4608, 1152, False)])
+@pytest.mark.parametrize("M,F,K,with_bias", [(128, 128, 64, True), (100, 256, 128, False), (256, 128, 64, False), (300, 256, 192, True), (1024, 1152, 288, False), (4096, 4608, 1152, False)])
 def test_gemm_swiglu_fused_matches_unfused(cuda_device, M, F, K, with_bias):
     """fc1 + SwiGLU epilogue == gemm followed by the standalone swiglu kernel, bit for bit (same bf16 rounding points)."""
     from diffulab_b200 import ops
@@ -142,7 +142,7 @@ def test_gemm_swiglu_fused_matches_unfused(cuda_device, M, F, K, with_bias):
     assert ((act.float() - ref).norm() / ref.norm()).item() < 1e-2
 
 
-@pytest.mark.parametrize("M,F,D", [(128, 128, 64), (300, 256, 192), (1000, 1152, 288), (4096, 4608, 1152)])
+@pytest.mark.parametrize("M,F,D", [(128, 128, 64), (100, 128, 192), (129, 256, 64), (300, 256, 192), (1000, 1152, 288), (4096, 4608, 1152)])
 def test_gemm_swiglu_bwd_fused_matches_unfused(cuda_device, M, F, D):
     """fc2 dgrad + SwiGLU backward in the epilogue vs the two separate kernels (relL2: the unfused kernel uses the exact
     sigmoid, the epilogue tanh.approx) and vs an fp32 torch restatement."""
