@@ -14,6 +14,8 @@
 //   stream kernels: grid-stride over vectors, one vector per thread-iteration, <= 42 registers (occupancy beats ILP
 //                  here: measured, profiles/elementwise_microbench_r1.jsonl).
 #include "common.cuh"
+#include "ptx.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -93,6 +95,193 @@ ln_modulate_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w, 
       st8(yr + v * 8, pack8(o));
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Tiled LayerNorm + modulate forward (per-sample modulation): the streaming structure that replaces "one warp loads its
+// own row". A producer lane moves 4-row tiles (one contiguous 4*d*2-byte block) global -> shared with cp.async.bulk into
+// a 3-stage ring (four CTAs per SM); four compute warps take one row each from shared memory, and a finished output tile leaves with one
+// cp.async.bulk store. The SM keeps ~150 KB of loads in flight with no thread ever waiting on its own global load; the
+// per-sample vectors P = w*(1+scale), Q = b*(1+scale)+shift are rebuilt in shared memory only when the sample changes,
+// so a row costs 2 FMA-class ops per element after the statistics. Measured (profiles/elementwise_microbench_r1.jsonl):
+// 0.049 ms per XL/2 call vs 0.056-0.061 for the row-per-warp kernel; a copy-only run of the same pipeline takes 0.037 ms,
+// the arithmetic adds ~110 SM-cycles per row = its instruction-issue cost (~440 warp instructions per row over 4 schedulers).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LT_ROWS = 4, LT_STAGES = 3, LT_WARPS = 4;
+template <int VPL>
+__global__ void __launch_bounds__((LT_WARPS + 1) * 32, 4)
+ln_modulate_fwd_tile_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                            const bf16* __restrict__ scale, const bf16* __restrict__ shift, int64_t mod_ld, int rows_per_mod,
+                            bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t R, int d,
+                            float eps, int tiles_per_cta, int dbg_mode) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tile_bytes = LT_ROWS * d * 2;
+  bf16* sIn = reinterpret_cast<bf16*>(smem);                                   // [LT_STAGES][LT_ROWS][d]
+  bf16* sOut = reinterpret_cast<bf16*>(smem + LT_STAGES * tile_bytes);        // [2][LT_ROWS][d]
+  float* sP = reinterpret_cast<float*>(smem + (LT_STAGES + 2) * tile_bytes);  // [d]
+  float* sQ = sP + d;
+  __shared__ uint64_t full[LT_STAGES], empty[LT_STAGES];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int64_t ntiles = (R + LT_ROWS - 1) / LT_ROWS;
+  const int64_t t0 = (int64_t)blockIdx.x * tiles_per_cta;
+  const int64_t t1 = t0 + tiles_per_cta < ntiles ? t0 + tiles_per_cta : ntiles;
+  if (tid == 0) {
+    for (int i = 0; i < LT_STAGES; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], LT_WARPS); }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == LT_WARPS) {
+    // ---------------- producer ----------------
+    int st = 0;
+    uint32_t ph = 0;
+    for (int64_t t = t0; t < t1; ++t) {
+      ptx::mbar_wait(&empty[st], ph ^ 1);
+      if (ptx::elect_one()) {
+        const int64_t r0 = t * LT_ROWS;
+        const int rows = (int)(R - r0 < LT_ROWS ? R - r0 : LT_ROWS);
+        const uint32_t bytes = (uint32_t)rows * d * 2;
+        ptx::mbar_expect_tx(&full[st], bytes);
+        ptx::bulk_load_1d(reinterpret_cast<uint8_t*>(sIn) + st * tile_bytes, x + r0 * d, bytes, &full[st]);
+      }
+      __syncwarp();
+      if (++st == LT_STAGES) { st = 0; ph ^= 1; }
+    }
+    return;
+  }
+  // ---------------- compute warps ----------------
+  const int nv = d >> 3;
+  int st = 0, ob = 0;
+  uint32_t ph = 0;
+  int64_t cur_sample = -1;
+  for (int64_t t = t0; t < t1; ++t) {
+    const int64_t r0 = t * LT_ROWS;
+    const int64_t sample = r0 / rows_per_mod;
+    if (sample != cur_sample) {  // rebuild P, Q for this sample (uniform over the compute warps)
+      asm volatile("bar.sync 1, %0;\n" ::"n"(LT_WARPS * 32) : "memory");
+      const bf16* sc = scale + sample * mod_ld;
+      const bf16* sh = shift + sample * mod_ld;
+      for (int j = tid; j < d; j += LT_WARPS * 32) {
+        const float s1 = bf16_round(1.f + __bfloat162float(sc[j]));  // `1 + scale` is evaluated in bf16 (autocast)
+        sP[j] = w ? w[j] * s1 : s1;
+        sQ[j] = (w ? b[j] * s1 : 0.f) + __bfloat162float(sh[j]);
+      }
+      asm volatile("bar.sync 1, %0;\n" ::"n"(LT_WARPS * 32) : "memory");
+      cur_sample = sample;
+    }
+    // the output staging buffer `ob` was handed to a bulk store two tiles ago: wait until that store has read it
+    if (tid == 0) ptx::tma_wait_group_read<1>();
+    asm volatile("bar.sync 1, %0;\n" ::"n"(LT_WARPS * 32) : "memory");
+    ptx::mbar_wait(&full[st], ph);
+    const bf16* tin = sIn + (size_t)st * LT_ROWS * d;
+    bf16* tout = sOut + (size_t)ob * LT_ROWS * d;
+    if (dbg_mode == 1) {  // development probe: pure shared-memory copy of my rows (no arithmetic)
+      for (int rr = 0; rr < LT_ROWS / LT_WARPS; ++rr)
+        for (int v = lane; v < nv; v += 32)
+          *reinterpret_cast<bf16x8*>(tout + (size_t)(warp + rr * LT_WARPS) * d + v * 8) = *reinterpret_cast<const bf16x8*>(tin + (size_t)(warp + rr * LT_WARPS) * d + v * 8);
+    } else {
+      // this warp's two rows are processed together, every reduction as independent partial sums: the dependent chain
+      // per row is ~10 operations deep instead of ~80 (with two warps per scheduler, chain latency is what binds)
+      constexpr int RPW = LT_ROWS / LT_WARPS;
+      bf16x8 xp[RPW][VPL];
+      float mean[RPW], rstd[RPW];
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) {
+        const bf16* xr = tin + (size_t)(warp + rr * LT_WARPS) * d;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          if (v < nv) xp[rr][i] = *reinterpret_cast<const bf16x8*>(xr + v * 8);
+        }
+      }
+      float part[RPW][VPL];
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr)
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          part[rr][i] = 0.f;
+          if (lane + 32 * i < nv) {
+            float f[8];
+            unpack8(xp[rr][i], f);
+            part[rr][i] = ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
+          }
+        }
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) {
+        float sum = part[rr][0];
+#pragma unroll
+        for (int i = 1; i < VPL; ++i) sum += part[rr][i];
+        mean[rr] = sum;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) mean[rr] += __shfl_xor_sync(0xffffffffu, mean[rr], o);
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) mean[rr] /= d;
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr)
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          part[rr][i] = 0.f;
+          if (lane + 32 * i < nv) {
+            float f[8];
+            unpack8(xp[rr][i], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] -= mean[rr];
+            part[rr][i] = ((f[0] * f[0] + f[1] * f[1]) + (f[2] * f[2] + f[3] * f[3])) + ((f[4] * f[4] + f[5] * f[5]) + (f[6] * f[6] + f[7] * f[7]));
+          }
+        }
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) {
+        float sq = part[rr][0];
+#pragma unroll
+        for (int i = 1; i < VPL; ++i) sq += part[rr][i];
+        rstd[rr] = sq;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int rr = 0; rr < RPW; ++rr) rstd[rr] += __shfl_xor_sync(0xffffffffu, rstd[rr], o);
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) {
+        rstd[rr] = rsqrtf(rstd[rr] / d + eps);
+        const int64_t row = r0 + warp + rr * LT_WARPS;
+        if (lane == 0 && mean_out && row < R) { mean_out[row] = mean[rr]; rstd_out[row] = rstd[rr]; }
+      }
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nv) {
+          float pv[8], qv[8];
+          *reinterpret_cast<float4*>(pv) = *reinterpret_cast<const float4*>(sP + v * 8);
+          *reinterpret_cast<float4*>(pv + 4) = *reinterpret_cast<const float4*>(sP + v * 8 + 4);
+          *reinterpret_cast<float4*>(qv) = *reinterpret_cast<const float4*>(sQ + v * 8);
+          *reinterpret_cast<float4*>(qv + 4) = *reinterpret_cast<const float4*>(sQ + v * 8 + 4);
+#pragma unroll
+          for (int rr = 0; rr < RPW; ++rr) {
+            float f[8], o[8];
+            unpack8(xp[rr][i], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf((f[j] - mean[rr]) * rstd[rr], pv[j], qv[j]);
+            *reinterpret_cast<bf16x8*>(tout + (size_t)(warp + rr * LT_WARPS) * d + v * 8) = pack8(o);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&empty[st]);  // this warp is done with the input stage
+    ptx::fence_proxy_async_smem();
+    asm volatile("bar.sync 1, %0;\n" ::"n"(LT_WARPS * 32) : "memory");
+    if (tid == 0) {
+      const int rows = (int)(R - r0 < LT_ROWS ? R - r0 : LT_ROWS);
+      ptx::bulk_store_1d(y + r0 * d, tout, (uint32_t)rows * d * 2);
+      ptx::tma_commit_group();
+    }
+    ob ^= 1;
+    if (++st == LT_STAGES) { st = 0; ph ^= 1; }
+  }
+  if (tid == 0) ptx::tma_wait_group<0>();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -461,6 +650,30 @@ DLB_EXPORT int dlb_ln_modulate_fwd(const void* x, const float* w, const float* b
               (long long)R, d, (long long)mod_ld);
   DLB_REQUIRE((w == nullptr) == (b == nullptr), DLB_ERR_SHAPE, "ln_modulate_fwd: weight and bias must both be set or null");
   DLB_REQUIRE(rows_per_mod >= 1 && (mean == nullptr) == (rstd == nullptr), DLB_ERR_SHAPE, "ln_modulate_fwd: bad args");
+  // tiled bulk-async kernel: per-sample modulation whose groups are whole 8-row tiles, contiguous 16-byte aligned rows
+  if (rows_per_mod % LT_ROWS == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0) {  // (no size threshold: the kernel choice must not depend on the batch size)
+    const int64_t ntiles = (R + LT_ROWS - 1) / LT_ROWS;
+    const int max_ctas = dlb_num_sms() * 4;
+    const int tiles_per_cta = (int)((ntiles + max_ctas - 1) / max_ctas);
+    const int grid_t = (int)((ntiles + tiles_per_cta - 1) / tiles_per_cta);
+    const size_t smem = (size_t)(LT_STAGES + 2) * LT_ROWS * d * 2 + 2 * (size_t)d * 4;
+    static const int dbg_mode = getenv("DLB_LN_DBG") ? atoi(getenv("DLB_LN_DBG")) : 0;  // 1 = copy-only probe (development)
+    VPL_SWITCH(d, {
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(ln_modulate_fwd_tile_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+        DLB_REQUIRE(e == cudaSuccess, (int)e, "ln_modulate_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+      }
+      if (smem <= 56 * 1024) {
+        ln_modulate_fwd_tile_kernel<VPL><<<grid_t, (LT_WARPS + 1) * 32, smem, stream>>>(
+            (const bf16*)x, w, b, (const bf16*)scale, (const bf16*)shift, mod_ld, (int)rows_per_mod, (bf16*)y, mean, rstd, R, d, eps, tiles_per_cta,
+            dbg_mode);
+        dlb_count_launch();
+        return dlb_check_launch("ln_modulate_fwd_tile");
+      }
+    });
+  }
   const int warps = 4;
   const int grid = (int)((R + warps - 1) / warps);
   VPL_SWITCH(d, (ln_modulate_fwd_kernel<VPL><<<grid, warps * 32, 0, stream>>>(
