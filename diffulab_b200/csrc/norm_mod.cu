@@ -374,6 +374,203 @@ ln_modulate_bwd_rows_kernel(const bf16* __restrict__ dy, const bf16* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Tiled LayerNorm + modulate backward (per-sample modulation): ONE pass over dy / x produces dx AND the per-sample
+// column sums S1 = sum dy, S2 = sum dy*xhat (the separate column kernel re-read both tensors). Same cp.async.bulk ring as
+// the forward tile kernel; because no thread waits on its own global loads, the kernel can afford 80 registers of
+// per-lane column accumulators (2 CTAs / SM) — the reason the row-per-warp version could not be fused. Accumulators are
+// flushed (warp -> shared -> one atomicAdd per column per CTA) when the sample changes and at the end.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LB_ROWS = 4, LB_STAGES = 3, LB_WARPS = 4;
+template <int VPL, bool HAS_RES>
+__global__ void __launch_bounds__((LB_WARPS + 1) * 32, 2)
+ln_modulate_bwd_tile_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean_in,
+                            const float* __restrict__ rstd_in, const float* __restrict__ w, const bf16* __restrict__ scale,
+                            int64_t mod_ld, int rows_per_mod, const bf16* __restrict__ dres, bf16* __restrict__ dx,
+                            float* __restrict__ acc1, float* __restrict__ acc2, int64_t acc_ld, int64_t R, int d, int tiles_per_cta) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int NIN = HAS_RES ? 3 : 2;
+  const int tile_bytes = LB_ROWS * d * 2;
+  const int stage_bytes = NIN * tile_bytes + 32;  // {dy, x, [dres]} tiles + mean[4] + rstd[4]
+  uint8_t* sOut = smem + LB_STAGES * stage_bytes;                       // [2][LB_ROWS][d] bf16
+  float* sG = reinterpret_cast<float*>(sOut + 2 * tile_bytes);          // [d]  (1 + scale) * w of the current sample
+  float* sAcc = sG + d;                                                  // [2][d] flush buffer
+  __shared__ uint64_t full[LB_STAGES], empty[LB_STAGES];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int64_t ntiles = (R + LB_ROWS - 1) / LB_ROWS;
+  const int64_t t0 = (int64_t)blockIdx.x * tiles_per_cta;
+  const int64_t t1 = t0 + tiles_per_cta < ntiles ? t0 + tiles_per_cta : ntiles;
+  if (tid == 0) {
+    for (int i = 0; i < LB_STAGES; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], LB_WARPS); }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == LB_WARPS) {
+    // ---------------- producer ----------------
+    int st = 0;
+    uint32_t ph = 0;
+    for (int64_t t = t0; t < t1; ++t) {
+      ptx::mbar_wait(&empty[st], ph ^ 1);
+      if (ptx::elect_one()) {
+        const int64_t r0 = t * LB_ROWS;
+        const int rows = (int)(R - r0 < LB_ROWS ? R - r0 : LB_ROWS);
+        const uint32_t bytes = (uint32_t)rows * d * 2;
+        uint8_t* sb = smem + st * stage_bytes;
+        // the statistics ride along: 16 bytes each when the whole tile exists (R % 4 == 0 is required by the launcher)
+        ptx::mbar_expect_tx(&full[st], NIN * bytes + 32);
+        ptx::bulk_load_1d(sb, dy + r0 * d, bytes, &full[st]);
+        ptx::bulk_load_1d(sb + tile_bytes, x + r0 * d, bytes, &full[st]);
+        if constexpr (HAS_RES) ptx::bulk_load_1d(sb + 2 * tile_bytes, dres + r0 * d, bytes, &full[st]);
+        ptx::bulk_load_1d(sb + NIN * tile_bytes, mean_in + r0, 16, &full[st]);
+        ptx::bulk_load_1d(sb + NIN * tile_bytes + 16, rstd_in + r0, 16, &full[st]);
+      }
+      __syncwarp();
+      if (++st == LB_STAGES) { st = 0; ph ^= 1; }
+    }
+    return;
+  }
+  // ---------------- compute warps: one row of the tile each ----------------
+  const int nv = d >> 3;
+  int st = 0, ob = 0;
+  uint32_t ph = 0;
+  int64_t cur_sample = -1;
+  float S1[VPL][8], S2[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { S1[i][j] = 0.f; S2[i][j] = 0.f; }
+  auto flush = [&](int64_t sample) {  // compute-warp collective: column sums of `sample` -> global accumulators
+    for (int wv = 0; wv < LB_WARPS; ++wv) {
+      if (warp == wv) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          if (v < nv) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float* a = sAcc + v * 8 + j;
+              if (wv == 0) { a[0] = S1[i][j]; a[d] = S2[i][j]; }
+              else { a[0] += S1[i][j]; a[d] += S2[i][j]; }
+              S1[i][j] = 0.f;
+              S2[i][j] = 0.f;
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, %0;\n" ::"n"(LB_WARPS * 32) : "memory");
+    }
+    for (int c = tid; c < d; c += LB_WARPS * 32) {
+      atomicAdd(acc1 + sample * acc_ld + c, sAcc[c]);
+      atomicAdd(acc2 + sample * acc_ld + c, sAcc[d + c]);
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(LB_WARPS * 32) : "memory");
+  };
+  for (int64_t t = t0; t < t1; ++t) {
+    const int64_t r0 = t * LB_ROWS;
+    const int64_t sample = r0 / rows_per_mod;
+    if (sample != cur_sample) {
+      if (cur_sample >= 0) flush(cur_sample);
+      else asm volatile("bar.sync 1, %0;\n" ::"n"(LB_WARPS * 32) : "memory");
+      const bf16* sc = scale + sample * mod_ld;
+      for (int j = tid; j < d; j += LB_WARPS * 32) {
+        const float s1 = bf16_round(1.f + __bfloat162float(sc[j]));
+        sG[j] = w ? w[j] * s1 : s1;
+      }
+      asm volatile("bar.sync 1, %0;\n" ::"n"(LB_WARPS * 32) : "memory");
+      cur_sample = sample;
+    }
+    if (tid == 0) ptx::tma_wait_group_read<1>();
+    asm volatile("bar.sync 1, %0;\n" ::"n"(LB_WARPS * 32) : "memory");
+    ptx::mbar_wait(&full[st], ph);
+    const uint8_t* sb = smem + st * stage_bytes;
+    bf16* tout = reinterpret_cast<bf16*>(sOut + ob * tile_bytes);
+    const int64_t row = r0 + warp;
+    if (row < R) {
+      const bf16* gr = reinterpret_cast<const bf16*>(sb) + (size_t)warp * d;
+      const bf16* xr = reinterpret_cast<const bf16*>(sb + tile_bytes) + (size_t)warp * d;
+      const float mean = reinterpret_cast<const float*>(sb + NIN * tile_bytes)[warp];
+      const float rstd = reinterpret_cast<const float*>(sb + NIN * tile_bytes + 16)[warp];
+      const float nmr = -mean * rstd;
+      bf16x8 xp[VPL], gp[VPL];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nv) {
+          xp[i] = *reinterpret_cast<const bf16x8*>(xr + v * 8);
+          gp[i] = *reinterpret_cast<const bf16x8*>(gr + v * 8);
+        }
+      }
+      float p1[VPL], p2[VPL];
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        p1[i] = 0.f;
+        p2[i] = 0.f;
+        const int v = lane + 32 * i;
+        if (v < nv) {
+          float xf[8], g[8], G[8], q[8], qx[8];
+          unpack8(xp[i], xf);
+          unpack8(gp[i], g);
+          *reinterpret_cast<float4*>(G) = *reinterpret_cast<const float4*>(sG + v * 8);
+          *reinterpret_cast<float4*>(G + 4) = *reinterpret_cast<const float4*>(sG + v * 8 + 4);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xh = fmaf(xf[j], rstd, nmr);
+            S1[i][j] += g[j];
+            S2[i][j] = fmaf(g[j], xh, S2[i][j]);
+            q[j] = g[j] * G[j];
+            qx[j] = q[j] * xh;
+          }
+          p1[i] = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+          p2[i] = ((qx[0] + qx[1]) + (qx[2] + qx[3])) + ((qx[4] + qx[5]) + (qx[6] + qx[7]));
+        }
+      }
+      float m1 = p1[0], m2 = p2[0];
+#pragma unroll
+      for (int i = 1; i < VPL; ++i) { m1 += p1[i]; m2 += p2[i]; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+        m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+      }
+      m1 /= d;
+      m2 /= d;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nv) {
+          float xf[8], g[8], G[8], o[8];
+          unpack8(xp[i], xf);
+          unpack8(gp[i], g);
+          *reinterpret_cast<float4*>(G) = *reinterpret_cast<const float4*>(sG + v * 8);
+          *reinterpret_cast<float4*>(G + 4) = *reinterpret_cast<const float4*>(sG + v * 8 + 4);
+          if constexpr (HAS_RES) unpack8(*reinterpret_cast<const bf16x8*>(reinterpret_cast<const bf16*>(sb + 2 * tile_bytes) + (size_t)warp * d + v * 8), o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xh = fmaf(xf[j], rstd, nmr);
+            const float tt = rstd * (g[j] * G[j] - m1 - xh * m2);
+            o[j] = HAS_RES ? o[j] + tt : tt;
+          }
+          *reinterpret_cast<bf16x8*>(tout + (size_t)warp * d + v * 8) = pack8(o);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&empty[st]);
+    ptx::fence_proxy_async_smem();
+    asm volatile("bar.sync 1, %0;\n" ::"n"(LB_WARPS * 32) : "memory");
+    if (tid == 0) {
+      const int rows = (int)(R - r0 < LB_ROWS ? R - r0 : LB_ROWS);
+      ptx::bulk_store_1d(dx + r0 * d, tout, (uint32_t)rows * d * 2);
+      ptx::tma_commit_group();
+    }
+    ob ^= 1;
+    if (++st == LB_STAGES) { st = 0; ph ^= 1; }
+  }
+  if (cur_sample >= 0) flush(cur_sample);
+  if (tid == 0) ptx::tma_wait_group<0>();
+}
+
 // grid (col chunks, row chunks, groups); block = one thread per 8-channel vector
 template <bool PER_TOKEN>
 __global__ void __launch_bounds__(256, 3)
@@ -698,6 +895,39 @@ DLB_EXPORT int dlb_ln_modulate_bwd(const void* dy, const void* x, const float* m
   DLB_REQUIRE(!per_token || groups == 1, DLB_ERR_SHAPE, "ln_modulate_bwd: per-token mode takes a single group");
   const int64_t R = groups * rows_per_group;
   const int64_t rows_per_mod = per_token ? 1 : rows_per_group;
+  // one-pass tiled kernel (dx + column sums), then the finalize kernel
+  if (!per_token && rows_per_group % LB_ROWS == 0 && ((uintptr_t)dy % 16) == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)dx % 16) == 0 &&
+      (dres == nullptr || ((uintptr_t)dres % 16) == 0) && ((uintptr_t)mean % 16) == 0 && ((uintptr_t)rstd % 16) == 0) {
+    const int nin = dres ? 3 : 2;
+    const size_t smem_t = (size_t)LB_STAGES * (nin * LB_ROWS * d * 2 + 32) + 2 * (size_t)LB_ROWS * d * 2 + 3 * (size_t)d * 4;
+    if (smem_t <= 113 * 1024) {
+      const int64_t ntiles = R / LB_ROWS;
+      const int max_ctas = dlb_num_sms() * 2;
+      const int tiles_per_cta = (int)((ntiles + max_ctas - 1) / max_ctas);
+      const int grid_t = (int)((ntiles + tiles_per_cta - 1) / tiles_per_cta);
+      VPL_SWITCH(d, {
+        if (dres) {
+          cudaFuncSetAttribute(ln_modulate_bwd_tile_kernel<VPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+          ln_modulate_bwd_tile_kernel<VPL, true><<<grid_t, (LB_WARPS + 1) * 32, smem_t, stream>>>(
+              (const bf16*)dy, (const bf16*)x, mean, rstd, w, (const bf16*)scale, mod_ld, (int)rows_per_group, (const bf16*)dres, (bf16*)dx,
+              dshift, dscale, dmod_ld, R, d, tiles_per_cta);
+        } else {
+          cudaFuncSetAttribute(ln_modulate_bwd_tile_kernel<VPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+          ln_modulate_bwd_tile_kernel<VPL, false><<<grid_t, (LB_WARPS + 1) * 32, smem_t, stream>>>(
+              (const bf16*)dy, (const bf16*)x, mean, rstd, w, (const bf16*)scale, mod_ld, (int)rows_per_group, nullptr, (bf16*)dx,
+              dshift, dscale, dmod_ld, R, d, tiles_per_cta);
+        }
+      });
+      dlb_count_launch();
+      int rcl = dlb_check_launch("ln_modulate_bwd_tile");
+      if (rcl) return rcl;
+      const int gpb = 8;
+      dim3 fgrid((d + 255) / 256, (unsigned)((groups + gpb - 1) / gpb));
+      ln_modulate_bwd_finalize_kernel<<<fgrid, 256, 0, stream>>>(w, b, (const bf16*)scale, mod_ld, dscale, dshift, dmod_ld, dw, db, d, groups, gpb);
+      dlb_count_launch();
+      return dlb_check_launch("ln_modulate_bwd_finalize");
+    }
+  }
   const int warps = 4;
   const int grid_rows = (int)((R + warps - 1) / warps);
   if (per_token) {
