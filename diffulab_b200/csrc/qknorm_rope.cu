@@ -5,6 +5,7 @@
 // back, learnable scale, cast to v's dtype) and RotaryPositionalEmbeddingNDim nn.py:331-400 (cos/sin cast to the
 // activation dtype, rotation evaluated in that dtype) as called from DiTAttention.forward mmdit.py:81-89.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace {
 typedef __nv_bfloat16 bf16;
@@ -174,6 +175,169 @@ qknorm_rope_bwd_rows_kernel(const bf16* __restrict__ dqk, int64_t ld_dqk, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// One-pass tiled backward: a cp.async.bulk ring feeds 2-row tiles {dqk rows, qkv rows, rrms}; warp (row, q|k) owns one
+// half-row, produces the raw-projection gradient AND accumulates the gradient of the learnable RMS scale for its fixed
+// columns in registers (the separate column kernel re-read both tensors: 302 MB per call). Flushed once per CTA.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int QB_ROWS = 2, QB_STAGES = 3, QB_WARPS = 4;
+template <int VPL>
+__global__ void __launch_bounds__((QB_WARPS + 1) * 32, 2)
+qknorm_rope_bwd_tile_kernel(const bf16* __restrict__ dqk, int64_t ld_dqk, const bf16* __restrict__ qkv, int64_t ld_in,
+                            const float* __restrict__ sq, const float* __restrict__ sk, RopeArgs ra, const float* __restrict__ rrms_in,
+                            bf16* __restrict__ dqkv, int64_t ld_out, float* __restrict__ dsq, float* __restrict__ dsk, int64_t R, int d,
+                            int tiles_per_cta) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int row_bytes = 2 * d * 2;                          // q | k halves of one token
+  const int stage_bytes = 2 * QB_ROWS * row_bytes + 16;    // {dqk rows, qkv rows} + rrms[QB_ROWS][2]
+  uint8_t* sOut = smem + QB_STAGES * stage_bytes;          // [2][QB_ROWS][2d] bf16
+  float* sScale = reinterpret_cast<float*>(sOut + 2 * QB_ROWS * row_bytes);  // [2][d] learnable scales (q, k)
+  float* sAcc = sScale + 2 * d;                             // [2][d] flush buffer
+  __shared__ uint64_t full[QB_STAGES], empty[QB_STAGES];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int64_t ntiles = (R + QB_ROWS - 1) / QB_ROWS;
+  const int64_t t0 = (int64_t)blockIdx.x * tiles_per_cta;
+  const int64_t t1 = t0 + tiles_per_cta < ntiles ? t0 + tiles_per_cta : ntiles;
+  if (tid == 0) {
+    for (int i = 0; i < QB_STAGES; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], QB_WARPS); }
+    ptx::fence_mbar_init();
+  }
+  if (tid < QB_WARPS * 32)
+    for (int c = tid; c < 2 * d; c += QB_WARPS * 32) sScale[c] = c < d ? sq[c] : sk[c - d];
+  __syncthreads();
+  if (warp == QB_WARPS) {
+    // ---------------- producer ----------------
+    int st = 0;
+    uint32_t ph = 0;
+    for (int64_t t = t0; t < t1; ++t) {
+      ptx::mbar_wait(&empty[st], ph ^ 1);
+      if (ptx::elect_one()) {
+        const int64_t r0 = t * QB_ROWS;  // R % QB_ROWS == 0 (launcher)
+        uint8_t* sb = smem + st * stage_bytes;
+        ptx::mbar_expect_tx(&full[st], 2 * QB_ROWS * row_bytes + 16);
+#pragma unroll
+        for (int rr = 0; rr < QB_ROWS; ++rr) {
+          ptx::bulk_load_1d(sb + rr * row_bytes, dqk + (r0 + rr) * ld_dqk, row_bytes, &full[st]);
+          ptx::bulk_load_1d(sb + (QB_ROWS + rr) * row_bytes, qkv + (r0 + rr) * ld_in, row_bytes, &full[st]);
+        }
+        ptx::bulk_load_1d(sb + 2 * QB_ROWS * row_bytes, rrms_in + r0 * 2, 16, &full[st]);
+      }
+      __syncwarp();
+      if (++st == QB_STAGES) { st = 0; ph ^= 1; }
+    }
+    return;
+  }
+  // ---------------- compute warps: warp = (row of the tile, q | k) ----------------
+  const int nv = d >> 3;
+  const int rr = warp >> 1, which = warp & 1;
+  const float* scl = sScale + which * d;
+  int st = 0, ob = 0;
+  uint32_t ph = 0;
+  float S[VPL][8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) S[i][j] = 0.f;
+  for (int64_t t = t0; t < t1; ++t) {
+    const int64_t row = t * QB_ROWS + rr;
+    const uint32_t* csr = ra.cs_t + (int64_t)rope_pos(ra, row) * ra.rot_half;
+    if (tid == 0) ptx::tma_wait_group_read<1>();
+    asm volatile("bar.sync 1, %0;\n" ::"n"(QB_WARPS * 32) : "memory");
+    ptx::mbar_wait(&full[st], ph);
+    const uint8_t* sb = smem + st * stage_bytes;
+    const bf16* gsrc = reinterpret_cast<const bf16*>(sb + rr * row_bytes) + which * d;
+    const bf16* src = reinterpret_cast<const bf16*>(sb + (QB_ROWS + rr) * row_bytes) + which * d;
+    const float rrms = reinterpret_cast<const float*>(sb + 2 * QB_ROWS * row_bytes)[rr * 2 + which];
+    bf16* dst = reinterpret_cast<bf16*>(sOut + (ob * QB_ROWS + rr) * row_bytes) + which * d;
+    float gn[VPL][8];  // grad wrt the normalised value (rotation transposed, times the learnable scale)
+    bf16x8 xp[VPL];
+    float part[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      part[i] = 0.f;
+      const int v = lane + 32 * i;
+      if (v < nv) {
+        const int c = v * 8, cl = c % ra.hd;
+        xp[i] = *reinterpret_cast<const bf16x8*>(src + c);
+        float xn[8], scv[8];
+        unpack8(xp[i], xn);
+        unpack8(*reinterpret_cast<const bf16x8*>(gsrc + c), gn[i]);
+        *reinterpret_cast<float4*>(scv) = *reinterpret_cast<const float4*>(scl + c);
+        *reinterpret_cast<float4*>(scv + 4) = *reinterpret_cast<const float4*>(scl + c + 4);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const int pj = (cl + j) >> 1;
+          if (pj < ra.rot_half) {
+            const float2 cs = cs_unpack(__ldg(csr + pj));
+            const float ge = gn[i][j], go = gn[i][j + 1];
+            gn[i][j] = ge * cs.x + go * cs.y;
+            gn[i][j + 1] = go * cs.x - ge * cs.y;
+          }
+        }
+        float q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xr = xn[j] * rrms;
+          S[i][j] = fmaf(gn[i][j], bf16_round(xr), S[i][j]);  // the reference multiplies the bf16-rounded normalised value
+          gn[i][j] *= scv[j];
+          q[j] = gn[i][j] * xr;
+        }
+        part[i] = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+      }
+    }
+    float dot = part[0];
+#pragma unroll
+    for (int i = 1; i < VPL; ++i) dot += part[i];
+    dot = warp_sum(dot) / d;
+    const float rd = rrms * dot;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nv) {
+        float xn[8], o[8];
+        unpack8(xp[i], xn);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rrms * (gn[i][j] - xn[j] * rd);
+        *reinterpret_cast<bf16x8*>(dst + v * 8) = pack8(o);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&empty[st]);
+    ptx::fence_proxy_async_smem();
+    asm volatile("bar.sync 1, %0;\n" ::"n"(QB_WARPS * 32) : "memory");
+    if (tid == 0) {
+#pragma unroll
+      for (int r2 = 0; r2 < QB_ROWS; ++r2) ptx::bulk_store_1d(dqkv + (t * QB_ROWS + r2) * ld_out, sOut + (ob * QB_ROWS + r2) * row_bytes, row_bytes);
+      ptx::tma_commit_group();
+    }
+    ob ^= 1;
+    if (++st == QB_STAGES) { st = 0; ph ^= 1; }
+  }
+  // flush the scale gradients: rows 0 / 1 of the tile held by warps (0,1) / (2,3)
+  if (dsq != nullptr) {
+    for (int round = 0; round < 2; ++round) {
+      if (rr == round) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          if (v < nv) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float* a = sAcc + which * d + v * 8 + j;
+              if (round == 0) *a = S[i][j];
+              else *a += S[i][j];
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, %0;\n" ::"n"(QB_WARPS * 32) : "memory");
+    }
+    for (int c = tid; c < 2 * d; c += QB_WARPS * 32) atomicAdd((c < d ? dsq : dsk) + (c < d ? c : c - d), sAcc[c]);
+  }
+  if (tid == 0) ptx::tma_wait_group<0>();
+}
+
 // grid (col chunks, row chunks, 2 = q/k); thread = one 8-channel vector marching down rows in batches of 4
 __global__ void __launch_bounds__(256, 3)
 qknorm_rope_bwd_cols_kernel(const bf16* __restrict__ dqk, int64_t ld_dqk, const bf16* __restrict__ qkv, int64_t ld_in,
@@ -280,6 +444,23 @@ DLB_EXPORT int dlb_qknorm_rope_bwd(const void* dqk, int64_t ld_dqk, const void* 
   DLB_REQUIRE(R > 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && ld_dqk % 8 == 0, DLB_ERR_SHAPE, "qknorm_rope_bwd: bad strides");
   DLB_REQUIRE(rrms != nullptr, DLB_ERR_SHAPE, "qknorm_rope_bwd: the rrms buffer saved by the forward pass is required");
   RopeArgs ra{cs_t, pos_idx, rot_half, pos_offset, tokens_per_sample > 0 ? tokens_per_sample : 1, hd};
+  {  // one-pass tiled kernel (raw gradient + scale gradients from a single read)
+    const size_t smem_t = (size_t)QB_STAGES * (2 * QB_ROWS * 4 * d + 16) + 2 * (size_t)QB_ROWS * 4 * d + 4 * (size_t)d * 4;
+    const bool aligned = ((uintptr_t)dqk % 16) == 0 && ((uintptr_t)qkv % 16) == 0 && ((uintptr_t)dqkv % 16) == 0 && ((uintptr_t)rrms % 16) == 0;
+    if (R % QB_ROWS == 0 && aligned && smem_t <= 113 * 1024 && (dsq == nullptr) == (dsk == nullptr)) {
+      const int64_t ntiles = R / QB_ROWS;
+      const int max_ctas = dlb_num_sms() * 2;
+      const int tiles_per_cta = (int)((ntiles + max_ctas - 1) / max_ctas);
+      const int grid_t = (int)((ntiles + tiles_per_cta - 1) / tiles_per_cta);
+      VPL_SWITCH(d, {
+        cudaFuncSetAttribute(qknorm_rope_bwd_tile_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        qknorm_rope_bwd_tile_kernel<VPL><<<grid_t, (QB_WARPS + 1) * 32, smem_t, stream>>>(
+            (const bf16*)dqk, ld_dqk, (const bf16*)qkv, ld_in, sq, sk, ra, rrms, (bf16*)dqkv, ld_out, dsq, dsk, R, d, tiles_per_cta);
+      });
+      dlb_count_launch();
+      return dlb_check_launch("qknorm_rope_bwd_tile");
+    }
+  }
   const int warps = 4;
   int64_t grid64 = (R + warps - 1) / warps;
   const int grid = (int)(grid64 < (int64_t)dlb_num_sms() * 5 ? grid64 : (int64_t)dlb_num_sms() * 5);
