@@ -764,6 +764,144 @@ gate_residual_bwd_cols_kernel(const bf16* __restrict__ dout, const bf16* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// One-pass tiled gate-residual backward (per-sample gate): da = dout * gate AND dgate[sample] += sum_rows dout * (a1 [+ a2])
+// from a single read of dout / a1 (the separate column kernel re-read them). Same cp.async.bulk ring + register column
+// accumulators as the LayerNorm backward tile kernel.
+// ---------------------------------------------------------------------------------------------------------
+template <int VPL, bool TWO>
+__global__ void __launch_bounds__((LB_WARPS + 1) * 32, 2)
+gate_residual_bwd_tile_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ a1, const bf16* __restrict__ a2,
+                              const bf16* __restrict__ gate, int64_t gate_ld, int rows_per_mod, bf16* __restrict__ da,
+                              float* __restrict__ dgate, int64_t dgate_ld, int64_t R, int d, int tiles_per_cta) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int NIN = TWO ? 3 : 2;
+  const int tile_bytes = LB_ROWS * d * 2;
+  const int stage_bytes = NIN * tile_bytes;
+  uint8_t* sOut = smem + LB_STAGES * stage_bytes;
+  float* sAcc = reinterpret_cast<float*>(sOut + 2 * tile_bytes);  // [d] flush buffer
+  __shared__ uint64_t full[LB_STAGES], empty[LB_STAGES];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int64_t ntiles = (R + LB_ROWS - 1) / LB_ROWS;
+  const int64_t t0 = (int64_t)blockIdx.x * tiles_per_cta;
+  const int64_t t1 = t0 + tiles_per_cta < ntiles ? t0 + tiles_per_cta : ntiles;
+  if (tid == 0) {
+    for (int i = 0; i < LB_STAGES; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], LB_WARPS); }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  if (warp == LB_WARPS) {
+    int st = 0;
+    uint32_t ph = 0;
+    for (int64_t t = t0; t < t1; ++t) {
+      ptx::mbar_wait(&empty[st], ph ^ 1);
+      if (ptx::elect_one()) {
+        const int64_t r0 = t * LB_ROWS;
+        const int rows = (int)(R - r0 < LB_ROWS ? R - r0 : LB_ROWS);
+        const uint32_t bytes = (uint32_t)rows * d * 2;
+        uint8_t* sb = smem + st * stage_bytes;
+        ptx::mbar_expect_tx(&full[st], NIN * bytes);
+        ptx::bulk_load_1d(sb, dout + r0 * d, bytes, &full[st]);
+        ptx::bulk_load_1d(sb + tile_bytes, a1 + r0 * d, bytes, &full[st]);
+        if constexpr (TWO) ptx::bulk_load_1d(sb + 2 * tile_bytes, a2 + r0 * d, bytes, &full[st]);
+      }
+      __syncwarp();
+      if (++st == LB_STAGES) { st = 0; ph ^= 1; }
+    }
+    return;
+  }
+  const int nv = d >> 3;
+  int st = 0, ob = 0;
+  uint32_t ph = 0;
+  int64_t cur_sample = -1;
+  float S[VPL][8];
+  bf16x8 gv[VPL];  // this lane's slice of the current sample's gate
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) S[i][j] = 0.f;
+  auto flush = [&](int64_t sample) {
+    for (int wv = 0; wv < LB_WARPS; ++wv) {
+      if (warp == wv) {
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          const int v = lane + 32 * i;
+          if (v < nv) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float* a = sAcc + v * 8 + j;
+              if (wv == 0) *a = S[i][j];
+              else *a += S[i][j];
+              S[i][j] = 0.f;
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, %0;\n" ::"n"(LB_WARPS * 32) : "memory");
+    }
+    for (int c = tid; c < d; c += LB_WARPS * 32) atomicAdd(dgate + sample * dgate_ld + c, sAcc[c]);
+    asm volatile("bar.sync 1, %0;\n" ::"n"(LB_WARPS * 32) : "memory");
+  };
+  for (int64_t t = t0; t < t1; ++t) {
+    const int64_t r0 = t * LB_ROWS;
+    const int64_t sample = r0 / rows_per_mod;
+    if (sample != cur_sample) {
+      if (cur_sample >= 0) flush(cur_sample);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nv) gv[i] = ld8(gate + sample * gate_ld + v * 8);
+      }
+      cur_sample = sample;
+    }
+    if (tid == 0) ptx::tma_wait_group_read<1>();
+    asm volatile("bar.sync 1, %0;\n" ::"n"(LB_WARPS * 32) : "memory");
+    ptx::mbar_wait(&full[st], ph);
+    const uint8_t* sb = smem + st * stage_bytes;
+    bf16* tout = reinterpret_cast<bf16*>(sOut + ob * tile_bytes);
+    if (r0 + warp < R) {
+      const bf16* dr = reinterpret_cast<const bf16*>(sb) + (size_t)warp * d;
+      const bf16* ar = reinterpret_cast<const bf16*>(sb + tile_bytes) + (size_t)warp * d;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nv) {
+          float dd[8], a[8], g[8], o[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(dr + v * 8), dd);
+          unpack8(*reinterpret_cast<const bf16x8*>(ar + v * 8), a);
+          unpack8(gv[i], g);
+          if constexpr (TWO) {
+            float b2[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(reinterpret_cast<const bf16*>(sb + 2 * tile_bytes) + (size_t)warp * d + v * 8), b2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = bf16_round(a[j] + b2[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            o[j] = dd[j] * g[j];
+            S[i][j] = fmaf(dd[j], a[j], S[i][j]);
+          }
+          *reinterpret_cast<bf16x8*>(tout + (size_t)warp * d + v * 8) = pack8(o);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&empty[st]);
+    ptx::fence_proxy_async_smem();
+    asm volatile("bar.sync 1, %0;\n" ::"n"(LB_WARPS * 32) : "memory");
+    if (tid == 0) {
+      const int rows = (int)(R - r0 < LB_ROWS ? R - r0 : LB_ROWS);
+      ptx::bulk_store_1d(da + r0 * d, tout, (uint32_t)rows * d * 2);
+      ptx::tma_commit_group();
+    }
+    ob ^= 1;
+    if (++st == LB_STAGES) { st = 0; ph ^= 1; }
+  }
+  if (cur_sample >= 0) flush(cur_sample);
+  if (tid == 0) ptx::tma_wait_group<0>();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // packed SwiGLU (one vector per thread-iteration; <= 40 registers so 6+ CTAs of 256 threads stay resident)
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 6)
@@ -985,6 +1123,30 @@ DLB_EXPORT int dlb_gate_residual_bwd(const void* dout, const void* a1, const voi
   DLB_REQUIRE(!per_token || groups == 1, DLB_ERR_SHAPE, "gate_residual_bwd: per-token mode takes a single group");
   const int64_t R = groups * rows_per_group;
   const int64_t rows_per_mod = per_token ? 1 : rows_per_group;
+  if (!per_token && rows_per_group % LB_ROWS == 0 && ((uintptr_t)dout % 16) == 0 && ((uintptr_t)a1 % 16) == 0 &&
+      (a2 == nullptr || ((uintptr_t)a2 % 16) == 0) && ((uintptr_t)da % 16) == 0) {
+    const int nin = a2 ? 3 : 2;
+    const size_t smem_t = (size_t)LB_STAGES * nin * LB_ROWS * d * 2 + 2 * (size_t)LB_ROWS * d * 2 + (size_t)d * 4;
+    if (smem_t <= 113 * 1024) {
+      const int64_t ntiles = R / LB_ROWS;
+      const int max_ctas = dlb_num_sms() * 2;
+      const int tiles_per_cta = (int)((ntiles + max_ctas - 1) / max_ctas);
+      const int grid_t = (int)((ntiles + tiles_per_cta - 1) / tiles_per_cta);
+      VPL_SWITCH(d, {
+        if (a2) {
+          cudaFuncSetAttribute(gate_residual_bwd_tile_kernel<VPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+          gate_residual_bwd_tile_kernel<VPL, true><<<grid_t, (LB_WARPS + 1) * 32, smem_t, stream>>>(
+              (const bf16*)dout, (const bf16*)a1, (const bf16*)a2, (const bf16*)gate, gate_ld, (int)rows_per_group, (bf16*)da, dgate, dgate_ld, R, d, tiles_per_cta);
+        } else {
+          cudaFuncSetAttribute(gate_residual_bwd_tile_kernel<VPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+          gate_residual_bwd_tile_kernel<VPL, false><<<grid_t, (LB_WARPS + 1) * 32, smem_t, stream>>>(
+              (const bf16*)dout, (const bf16*)a1, nullptr, (const bf16*)gate, gate_ld, (int)rows_per_group, (bf16*)da, dgate, dgate_ld, R, d, tiles_per_cta);
+        }
+      });
+      dlb_count_launch();
+      return dlb_check_launch("gate_residual_bwd_tile");
+    }
+  }
   const int g = stream_grid(R * (d / 8), 1);
 #define GATE_BWD_STREAM(TWO, PT)                                                                                         \
   gate_residual_bwd_stream_kernel<TWO, PT><<<g, 256, 0, stream>>>((const bf16*)dout, (const bf16*)a1, (const bf16*)a2,  \
