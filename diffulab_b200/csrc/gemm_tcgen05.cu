@@ -56,6 +56,26 @@ __device__ __forceinline__ TileCoord decode_tile(int t, int mb, int nb, int kb_t
   return c;
 }
 
+// SWIGLU_BWD: TMA-prefetch the (a, g) tiles of H that this warp's rows of the given output tile will need
+template <int BN>
+__device__ __forceinline__ void issue_h_tile_loads(const CUtensorMap& tmC2, uint8_t* sE, uint64_t* lbar, int ew, int lane, int M, int N,
+                                                   int r0, int n_blk, bool wait_stores, int slot_mask = 3) {
+  if (lane == 0 && r0 >= 0 && r0 < M) {
+    if (wait_stores) ptx::tma_wait_group_read<0>();  // my committed staged stores have been read: their slots are free
+    uint8_t* wb_ = sE + ew * (4 * EPI_BUF_BYTES);
+#pragma unroll
+    for (int slot = 0; slot < 2; ++slot) {
+      if (!((slot_mask >> slot) & 1)) continue;
+      const int col = n_blk * BN + slot * 64;
+      uint64_t* b = &lbar[ew * 2 + slot];
+      ptx::mbar_expect_tx(b, 2 * EPI_BUF_BYTES);
+      ptx::tma_load_2d(wb_ + slot * 2 * EPI_BUF_BYTES, &tmC2, b, col, r0);
+      ptx::tma_load_2d(wb_ + slot * 2 * EPI_BUF_BYTES + EPI_BUF_BYTES, &tmC2, b, N + col, r0);
+    }
+  }
+  __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Epilogue of one accumulator tile for one epilogue warp (shared by the single-CTA and the CTA-pair kernels):
 // this warp's 32 TMEM lanes x the tile's columns -> registers -> 128B-swizzled staging -> TMA store / reduce-add,
@@ -64,7 +84,8 @@ __device__ __forceinline__ TileCoord decode_tile(int t, int mb, int nb, int kb_t
 template <int BN, int OUT, int EPI>
 __device__ __forceinline__ void epilogue_tile(const CUtensorMap& tmC, const CUtensorMap& tmC2, const float* __restrict__ bias,
                                               bool add_bias, uint8_t* sE, uint64_t* lbar, int ew, int lane, int M, int N, int row0,
-                                              int n_blk, uint32_t taddr, int& ebuf, uint32_t& hphase) {
+                                              int n_blk, uint32_t taddr, int& ebuf, uint32_t& hphase, int next_row0 = -1,
+                                              int next_n_blk = 0) {
   constexpr bool SWIGLU = EPI == EPI_SWIGLU, SWIGLU_BWD = EPI == EPI_SWIGLU_BWD;
   constexpr int BNT = SWIGLU ? BN / 2 : BN;
   constexpr int CH = (OUT == OUT_BF16) ? 64 : 32;  // columns per 128-byte staging row
@@ -108,6 +129,9 @@ __device__ __forceinline__ void epilogue_tile(const CUtensorMap& tmC, const CUte
       }
       ptx::fence_proxy_async_smem();
       __syncwarp();
+      // slot 0 of the NEXT tile is requested as soon as this tile's slot-0 stores have been read (they were committed a
+      // whole chunk ago), not after the tile: the main loop of a K = 1152 tile is shorter than the TMA load latency
+      if (slot == 1) issue_h_tile_loads<BN>(tmC2, sE, lbar, ew, lane, M, N, next_row0, next_n_blk, true, 1);
       if (lane == 0 && rows_ok) {
         ptx::tma_store_2d(&tmC, abuf, col0, row0);
         ptx::tma_store_2d(&tmC, gbuf, N + col0, row0);
@@ -206,25 +230,6 @@ __device__ __forceinline__ void epilogue_tile(const CUtensorMap& tmC, const CUte
     ebuf ^= 1;
   }
   }
-}
-
-// SWIGLU_BWD: TMA-prefetch the (a, g) tiles of H that this warp's rows of the given output tile will need
-template <int BN>
-__device__ __forceinline__ void issue_h_tile_loads(const CUtensorMap& tmC2, uint8_t* sE, uint64_t* lbar, int ew, int lane, int M, int N,
-                                                   int r0, int n_blk, bool wait_stores) {
-  if (lane == 0 && r0 < M) {
-    if (wait_stores) ptx::tma_wait_group_read<0>();  // my staged stores have been read: the slots are free
-    uint8_t* wb_ = sE + ew * (4 * EPI_BUF_BYTES);
-#pragma unroll
-    for (int slot = 0; slot < 2; ++slot) {
-      const int col = n_blk * BN + slot * 64;
-      uint64_t* b = &lbar[ew * 2 + slot];
-      ptx::mbar_expect_tx(b, 2 * EPI_BUF_BYTES);
-      ptx::tma_load_2d(wb_ + slot * 2 * EPI_BUF_BYTES, &tmC2, b, col, r0);
-      ptx::tma_load_2d(wb_ + slot * 2 * EPI_BUF_BYTES + EPI_BUF_BYTES, &tmC2, b, N + col, r0);
-    }
-  }
-  __syncwarp();
 }
 
 // SWIGLU variant (fc1 of the packed-SwiGLU MLP, reference nn.py:478-486 + mmdit.py:260-264): the weight is [2F, K]
@@ -369,14 +374,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int as = 0;
     uint32_t aphase = 0;
     [[maybe_unused]] uint32_t hphase = 0;
-    [[maybe_unused]] auto issue_h_loads = [&](int tn, bool wait_stores) {
+    [[maybe_unused]] auto issue_h_loads = [&](int tn, bool wait_stores, int slot_mask) {
       if constexpr (SWIGLU_BWD) {
         const TileCoord tcn = decode_tile(tn, mb, nb, kb_total, kb_per);
-        issue_h_tile_loads<BN>(tmC2, sE, lbar, ew, lane, M, N, tcn.m_blk * BM + ew * 32, tcn.n_blk, wait_stores);
+        issue_h_tile_loads<BN>(tmC2, sE, lbar, ew, lane, M, N, tcn.m_blk * BM + ew * 32, tcn.n_blk, wait_stores, slot_mask);
       }
     };
     if constexpr (SWIGLU_BWD) {
-      if ((int)blockIdx.x < tiles) issue_h_loads(blockIdx.x, false);
+      if ((int)blockIdx.x < tiles) issue_h_loads(blockIdx.x, false, 3);
     }
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(t, mb, nb, kb_total, kb_per);
@@ -385,14 +390,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row0 = tc.m_blk * BM + ew * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
       const bool add_bias = (bias != nullptr) && (tc.ks == 0);
-      epilogue_tile<BN, OUT, EPI>(tmC, tmC2, bias, add_bias, sE, lbar, ew, lane, M, N, row0, tc.n_blk, taddr, ebuf, hphase);
+      int next_row0 = -1, next_n_blk = 0;
+      if constexpr (SWIGLU_BWD) {
+        if (t + (int)gridDim.x < tiles) {
+          const TileCoord tcn = decode_tile(t + gridDim.x, mb, nb, kb_total, kb_per);
+          next_row0 = tcn.m_blk * BM + ew * 32;
+          next_n_blk = tcn.n_blk;
+        }
+      }
+      epilogue_tile<BN, OUT, EPI>(tmC, tmC2, bias, add_bias, sE, lbar, ew, lane, M, N, row0, tc.n_blk, taddr, ebuf, hphase, next_row0, next_n_blk);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[as]);
       as ^= 1;
       if (as == 0) aphase ^= 1;
       if constexpr (SWIGLU_BWD) {  // h tiles of my next output tile: they land while its main loop runs
-        if (t + (int)gridDim.x < tiles) issue_h_loads(t + gridDim.x, true);
+        if (t + (int)gridDim.x < tiles) issue_h_loads(t + gridDim.x, true, 2);  // slot 1 (slot 0 went out inside the epilogue)
       }
     }
     if (lane == 0) ptx::tma_wait_group<0>();
@@ -556,14 +569,14 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int as = 0;
     uint32_t aphase = 0;
     [[maybe_unused]] uint32_t hphase = 0;
-    [[maybe_unused]] auto issue_h_loads = [&](int tn, bool wait_stores) {
+    [[maybe_unused]] auto issue_h_loads = [&](int tn, bool wait_stores, int slot_mask) {
       if constexpr (SWIGLU_BWD) {
         const TileCoord tcn = decode_tile(tn, mb, nb, kb_total, kb_per);
-        issue_h_tile_loads<BN>(tmC2, sE, lbar, ew, lane, M, N, (tcn.m_blk * 2 + rank) * BM + ew * 32, tcn.n_blk, wait_stores);
+        issue_h_tile_loads<BN>(tmC2, sE, lbar, ew, lane, M, N, (tcn.m_blk * 2 + rank) * BM + ew * 32, tcn.n_blk, wait_stores, slot_mask);
       }
     };
     if constexpr (SWIGLU_BWD) {
-      if (cluster_id < tiles) issue_h_loads(cluster_id, false);
+      if (cluster_id < tiles) issue_h_loads(cluster_id, false, 3);
     }
     for (int t = cluster_id; t < tiles; t += n_clusters) {
       const TileCoord tc = decode_tile(t, mb, nb, kb_total, kb_per);
@@ -572,14 +585,22 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int row0 = (tc.m_blk * 2 + rank) * BM + ew * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN;
       const bool add_bias = (bias != nullptr) && (tc.ks == 0);
-      epilogue_tile<BN, OUT, EPI>(tmC, tmC2, bias, add_bias, sE, lbar, ew, lane, M, N, row0, tc.n_blk, taddr, ebuf, hphase);
+      int next_row0 = -1, next_n_blk = 0;
+      if constexpr (SWIGLU_BWD) {
+        if (t + n_clusters < tiles) {
+          const TileCoord tcn = decode_tile(t + n_clusters, mb, nb, kb_total, kb_per);
+          next_row0 = (tcn.m_blk * 2 + rank) * BM + ew * 32;
+          next_n_blk = tcn.n_blk;
+        }
+      }
+      epilogue_tile<BN, OUT, EPI>(tmC, tmC2, bias, add_bias, sE, lbar, ew, lane, M, N, row0, tc.n_blk, taddr, ebuf, hphase, next_row0, next_n_blk);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(&tempty[as], 0);  // the even CTA's MMA warp owns the accumulator hand-off
       as ^= 1;
       if (as == 0) aphase ^= 1;
       if constexpr (SWIGLU_BWD) {
-        if (t + n_clusters < tiles) issue_h_loads(t + n_clusters, true);
+        if (t + n_clusters < tiles) issue_h_loads(t + n_clusters, true, 2);
       }
     }
     if (lane == 0) ptx::tma_wait_group<0>();
