@@ -38,6 +38,9 @@ CONFIG = os.path.join(ROOT, "configs", "train_imagenet_flow_matching_repa.yaml")
 FWD_GFLOP_PER_IMG = 313.33   # matmul FLOPs of one DiT-XL/2 forward
 REPA_GFLOP_PER_IMG = 5.0     # projector 1152 -> 1024 -> 1024 -> 1024, forward + backward
 TRAIN_GFLOP_PER_IMG = 3 * FWD_GFLOP_PER_IMG + REPA_GFLOP_PER_IMG
+# DRAM traffic of the dominant kernel (tcgen05 GEMM), measured once with `ncu --set full` on the bench step (profiles/):
+# mean dram__bytes_read.sum + dram__bytes_write.sum per launch over the captured GEMM launches
+NCU_GEMM_TRAFFIC_BYTES_PER_LAUNCH = 496.8e6
 
 
 def load_peaks() -> tuple[dict, str]:
@@ -300,7 +303,9 @@ def run_gpu_arm(args) -> None:
     achieved = g_fl / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
     peak = float(peaks["bf16_tflops_sustained"])
     roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (fwd + dgrad + wgrad launches)", "achieved": round(achieved, 1),
-                "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": f"bf16_tflops_sustained, {peak_src}",
+                "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": NCU_GEMM_TRAFFIC_BYTES_PER_LAUNCH,
+                "traffic_source": "dram__bytes_read+write per launch, mean over the 10 GEMM launches of profiles/ncu_top_kernels_r1_final.txt (ncu --set full)",
+                "peak_source": f"bf16_tflops_sustained, {peak_src}",
                 "launches": int(g_calls), "gemm_ms_per_step": round(g_ms / args.steps, 3),
                 "gemm_share_of_kernel_time": round(g_ms / all_ms, 4) if all_ms else None,
                 "step_model_flops_frac": round(value / world * TRAIN_GFLOP_PER_IMG * 1e9 / (peak * 1e12), 4)}

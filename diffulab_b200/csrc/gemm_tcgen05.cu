@@ -703,7 +703,7 @@ double pair_cost(int M, int N, int kb_total, int bn, int split_k) {
 }
 
 // tile_n / split_k: > 0 = forced by the caller, else chosen here. pair: -1 = choose, 0 = single-CTA kernel, 1 = CTA pair.
-void pick_config(int M, int N, int K, bool allow_split, int& tile_n, int& split_k, int& pair) {
+void pick_config(int M, int N, int K, bool allow_split, bool b_mn, int& tile_n, int& split_k, int& pair) {
   const int kb_total = (K + BK - 1) / BK;
   const int cands[4] = {256, 192, 128, 64};
   const int splits[6] = {1, 2, 4, 8, 16, 32};
@@ -715,7 +715,7 @@ void pick_config(int M, int N, int K, bool allow_split, int& tile_n, int& split_
     for (int i = 0; i < 4; ++i) {
       const int bn = cands[i];
       if (tile_n > 0 && bn != tile_n) continue;
-      if (pr == 1 && bn != 256 && bn != 128) continue;
+      if (pr == 1 && bn != 256 && bn != 128 && !(bn == 192 && !b_mn)) continue;  // 192: each CTA stages 96 K-major rows of B
       if (tile_n <= 0 && bn == 64 && N > 64) continue;
       if (tile_n <= 0 && bn > 64 && N <= 64) continue;
       for (int j = 0; j < 6; ++j) {
@@ -758,8 +758,8 @@ DLB_EXPORT int dlb_gemm_bf16(const void* A, const void* B, void* Cout, const flo
               "gemm: tile_n %d unsupported", tile_n);
   if (split_k < 0) split_k = 1;
   int bn = tile_n;
-  int pair = (tile_n == 64 || tile_n == 192) ? 0 : -1;
-  pick_config((int)M, (int)N, (int)K, out_mode == OUT_F32_ADD, bn, split_k, pair);
+  int pair = tile_n == 64 ? 0 : -1;
+  pick_config((int)M, (int)N, (int)K, out_mode == OUT_F32_ADD, b_mn_major != 0, bn, split_k, pair);
   if (split_k > kb_total) split_k = kb_total;
   if (split_k > 1) {
     const int kb_per = (kb_total + split_k - 1) / split_k;
@@ -934,6 +934,10 @@ int dispatch_major2(int a_mn, int b_mn, int out_mode, const CUtensorMap& ta, con
 int dispatch_pair(int bn, int a_mn, int b_mn, int out_mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                   const float* bias, int M, int N, int K, int split_k, cudaStream_t s) {
   if (bn == 128) return dispatch_major2<128>(a_mn, b_mn, out_mode, ta, tb, tc, bias, M, N, K, split_k, s);
+  if (bn == 192) {  // K-major B only (checked by the caller): 96-row halves
+    if (!a_mn) return dispatch_out2<192, false, false>(out_mode, ta, tb, tc, bias, M, N, K, split_k, s);
+    return dispatch_out2<192, true, false>(out_mode, ta, tb, tc, bias, M, N, K, split_k, s);
+  }
   return dispatch_major2<256>(a_mn, b_mn, out_mode, ta, tb, tc, bias, M, N, K, split_k, s);
 }
 }  // namespace
@@ -944,7 +948,8 @@ DLB_EXPORT int dlb_gemm2_bf16(const void* A, const void* B, void* Cout, const fl
                               int tile_n, cudaStream_t stream) {
   DLB_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), DLB_ERR_SHAPE, "gemm2: bad problem");
   DLB_REQUIRE(out_mode >= 0 && out_mode <= 2, DLB_ERR_UNSUPPORTED, "gemm2: bad out_mode %d", out_mode);
-  DLB_REQUIRE(tile_n == 128 || tile_n == 256, DLB_ERR_UNSUPPORTED, "gemm2: tile_n must be 128 or 256 (got %d)", tile_n);
+  DLB_REQUIRE(tile_n == 128 || tile_n == 256 || (tile_n == 192 && !b_mn_major), DLB_ERR_UNSUPPORTED,
+              "gemm2: tile_n must be 128 or 256 (or 192 with a K-major B operand), got %d", tile_n);
   DLB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, DLB_ERR_ALIGN, "gemm2: lda/ldb must be multiples of 8 elements");
   const int c_elem = out_mode == OUT_BF16 ? 2 : 4;
   DLB_REQUIRE((ldc * c_elem) % 16 == 0, DLB_ERR_ALIGN, "gemm2: ldc*elem must be a multiple of 16 bytes");
@@ -969,6 +974,5 @@ DLB_EXPORT int dlb_gemm2_bf16(const void* A, const void* B, void* Cout, const fl
   if (out_mode == OUT_BF16) rc = encode2d(&tc, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Cout, N, M, ldc, 64, 32);
   else rc = encode2d(&tc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Cout, N, M, ldc, 32, 32);
   if (rc) return rc;
-  if (bn == 128) return dispatch_major2<128>(a_mn_major, b_mn_major, out_mode, ta, tb, tc, bias, (int)M, (int)N, (int)K, split_k, stream);
-  return dispatch_major2<256>(a_mn_major, b_mn_major, out_mode, ta, tb, tc, bias, (int)M, (int)N, (int)K, split_k, stream);
+  return dispatch_pair(bn, a_mn_major, b_mn_major, out_mode, ta, tb, tc, bias, (int)M, (int)N, (int)K, split_k, stream);
 }

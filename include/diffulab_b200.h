@@ -55,7 +55,7 @@ int dlb_gemm_bf16(const void* A, const void* B, void* C, const float* bias, int6
                   int tile_n, dlb_stream_t stream);
 
 /* CTA-pair (tcgen05 cta_group::2, 256 x tile_n tiles, cluster of two CTAs) version of dlb_gemm_bf16: same contract and
- * results; tile_n in {128, 256}; split_k >= 1 (no automatic choice). dlb_gemm_bf16 dispatches to it where it is faster. */
+ * results; tile_n in {128, 256} (192 as well when B is K-major); split_k >= 1 (no automatic choice). dlb_gemm_bf16 dispatches to it where it is faster. */
 int dlb_gemm2_bf16(const void* A, const void* B, void* C, const float* bias, int64_t M, int64_t N, int64_t K, int64_t lda,
                    int64_t ldb, int64_t ldc, int a_mn_major, int b_mn_major, int out_mode, int split_k, int tile_n,
                    dlb_stream_t stream);

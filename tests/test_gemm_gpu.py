@@ -183,13 +183,15 @@ def test_gemm_cta_pair_matches_single_cta(cuda_device, M, N, K, mode, tile_n):
         sk = 4 if mode == "wgrad_splitk" else 1
         ref = torch.zeros(M, N, device="cuda")
         got = torch.zeros(M, N, device="cuda")
-        ops.gemm(a, b, out=ref, accumulate=True, split_k=1, tile_n=192, **kw)  # tile_n 192 exists only in the single-CTA kernel
+        ops.gemm(a, b, out=ref, accumulate=True, split_k=1, tile_n=64, **kw)  # tile_n 64 exists only in the single-CTA kernel
         ops.gemm(a, b, out=got, accumulate=True, split_k=sk, tile_n=tile_n, pair=True, **kw)
         if sk == 1:
             assert torch.equal(got, ref)
         else:
             torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-3)
     else:
-        ref = ops.gemm(a, b, tile_n=192, **kw)  # single-CTA kernel
+        ref = ops.gemm(a, b, tile_n=64, **kw)  # tile_n 64 exists only in the single-CTA kernel
         got = ops.gemm(a, b, tile_n=tile_n, pair=True, **kw)
         assert torch.equal(got, ref)
+        if mode in ("fwd", "fwd_bias_f32"):  # K-major B: the 256 x 192 pair tile as well
+            assert torch.equal(ops.gemm(a, b, tile_n=192, pair=True, **kw), ref)
