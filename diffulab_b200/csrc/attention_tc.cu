@@ -395,6 +395,214 @@ __device__ __forceinline__ Item decode_item(const Params& p, int w, int nx) {
   } while (0)
 
 // ---------------------------------------------------------------------------------------------------------
+// forward, persistent warp-specialised version (same roles and hand-offs as the backward kernels): resident Q tile
+// (double-buffered), 64-key K / V tiles in a ring fed by the producer warps (TMA or cp.async), S = Q K_j^T double-
+// buffered in TMEM so the MMA warp computes the scores of tile j+1 while the compute warps do the softmax of tile j;
+// O_j = P V_j is read from TMEM one iteration later and accumulated (rescaled) in registers.
+// ---------------------------------------------------------------------------------------------------------
+template <int HDP, int RES, int NST, bool TMA>
+__global__ void __launch_bounds__(NT, 1) attn_fwd_ws_tc_kernel(const Params p, const __grid_constant__ BwdMaps maps) {
+  constexpr int TQ = 128 * HDP * 2, TK = KT * HDP * 2;
+  constexpr int HH = HDP / 2;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sRes = smem;                                     // RES x Q tile, layout L1(128)
+  uint8_t* sKV = sRes + RES * TQ;                           // NST stages of {K tile, V tile}
+  uint8_t* sP = sKV + NST * 2 * TK;                         // [128 q][64 keys] bf16, layout L1(128), 16 KB
+  bf16* sStage = reinterpret_cast<bf16*>(sP + 16384);       // [128][HDP] output staging
+  float* sX = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sStage) + TQ);  // [2][2][128] pair exchange
+  __shared__ uint64_t full[NST], empty[NST], bar_s[2], ps_full, bar_o;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const int T = (p.S + KT - 1) / KT, nx = (p.S + 127) / 128;
+  const int nitems = nx * p.H * p.B;
+  const int n_my = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int G = n_my * T;
+  if (tid == 0) {
+    for (int i = 0; i < NST; ++i) { ptx::mbar_init(&full[i], TMA ? 1 : NPW * 32); ptx::mbar_init(&empty[i], 1); }
+    ptx::mbar_init(&bar_s[0], 1); ptx::mbar_init(&bar_s[1], 1); ptx::mbar_init(&ps_full, NC); ptx::mbar_init(&bar_o, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp_u == 8) ptx::tmem_alloc<256>(&tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, KT, false, false);
+  constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, HDP, false, true);
+
+  if (warp_u > 8) {
+    // ---------------- producer warps ----------------
+    const int pw = warp_u - 9;
+    int uk = 0, uj = 0;
+    for (int u = 0; u < G; ++u) {
+      if (u >= NST) ptx::mbar_wait(&empty[u % NST], ((u / NST) - 1) & 1);
+      const Item it = decode_item(p, blockIdx.x + uk * gridDim.x, nx);
+      uint8_t* st = sKV + (u % NST) * 2 * TK;
+      uint8_t* res = sRes + (uk % RES) * TQ;
+      if constexpr (TMA) {
+        if (pw == 0 && ptx::elect_one()) {
+          uint64_t* bar = &full[u % NST];
+          ptx::mbar_expect_tx(bar, 2 * TK + (uj == 0 ? TQ : 0));
+          if (uj == 0) tma_tile(res, maps, M_Q128, p, it.b, it.h, it.x * 128, bar);
+          tma_tile(st, maps, M_K64, p, it.b, it.h, uj * KT, bar);
+          tma_tile(st + TK, maps, M_V64, p, it.b, it.h, uj * KT, bar);
+        }
+        __syncwarp();
+        if (++uj == T) { uj = 0; ++uk; }
+        continue;
+      }
+      if (uj == 0) load_tile<HDP, T_Q, 128, NPW>(res, p, it.b, it.h, it.x * 128, pw, lane);
+      load_tile<HDP, T_K, KT, NPW>(st, p, it.b, it.h, uj * KT, pw, lane);
+      load_tile<HDP, T_V, KT, NPW>(st + TK, p, it.b, it.h, uj * KT, pw, lane);
+      cp_async_arrive_noinc(&full[u % NST]);
+      if (++uj == T) { uj = 0; ++uk; }
+    }
+    cp_async_wait<0>();
+  } else if (warp_u == 8) {
+    // ---------------- MMA-issue warp ----------------
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
+    const uint32_t resa = ptx::smem_u32(sRes), kva = ptx::smem_u32(sKV);
+    const uint64_t dp0 = desc_k128(ptx::smem_u32(sP));
+    int tk = 0, tj = 0;
+    for (int g = -1; g < G; ++g) {
+      const bool next_ready = g + 1 < G && (g < 0 || __shfl_sync(0xffffffffu, (int)ptx::mbar_test_wait(&full[(g + 1) % NST], ((g + 1) / NST) & 1), 0) != 0);
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        if ((pass == 0) == next_ready && g + 1 < G) {  // S(t) = Q K_t^T into TMEM buffer t & 1
+          const int t = g + 1;
+          ptx::mbar_wait(&full[t % NST], (t / NST) & 1);
+          ptx::fence_proxy_async_smem();
+          ptx::tc_fence_after();
+          const uint64_t dq0 = desc_k128(resa + (tk % RES) * TQ);
+          const uint64_t dk = desc_k64(kva + (t % NST) * 2 * TK);
+#pragma unroll
+          for (int ks = 0; ks < HDP / 16; ++ks) ptx::umma_bf16_elect(tmem + (t & 1) * KT, dq0 + ks * KSTEP_K128, dk + ks * KSTEP_K64, idesc_s, ks > 0);
+          ptx::umma_commit_elect(&bar_s[t & 1]);
+          if (++tj == T) { tj = 0; ++tk; }
+        }
+        if (pass == 0 && g >= 0) {  // O_g = P V_g (fresh tile: the compute warps accumulate in registers)
+          ptx::mbar_wait(&ps_full, g & 1);
+          ptx::tc_fence_after();
+          const uint64_t dv = desc_mn64(kva + (g % NST) * 2 * TK + TK);
+#pragma unroll
+          for (int ks = 0; ks < KT / 16; ++ks) ptx::umma_bf16_elect(tmem + 128, dp0 + ks * KSTEP_K128, dv + ks * KSTEP_MN64, idesc_o, ks > 0);
+          ptx::umma_commit_elect(&empty[g % NST]);
+          ptx::umma_commit_elect(&bar_o);
+        }
+      }
+    }
+  } else {
+    // ---------------- compute warps ----------------
+    const int r = tid & 127, half = tid >> 7;
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tO = tmem + 128 + lane_off;
+    int k = 0, j = 0;
+    Item it = decode_item(p, blockIdx.x, nx);
+    float o[HH];
+    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+    auto add_o_tile = [&]() {  // o = o * alpha + O_tile (my half of the head dim)
+      uint32_t v[HH];
+      const uint32_t a = tO + half * HH;
+      ptx::tmem_ld32(a, v);
+      if constexpr (HH == 40) ptx::tmem_ld8(a + 32, v + 32);
+      if constexpr (HH == 48) ptx::tmem_ld16(a + 32, v + 32);
+      if constexpr (HH == 64) ptx::tmem_ld32(a + 32, v + 32);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < HH; ++i) o[i] = fmaf(o[i], alpha_prev, __uint_as_float(v[i]));
+    };
+    for (int g = 0; g < G; ++g) {
+      if (j == 0) {
+        it = decode_item(p, blockIdx.x + k * gridDim.x, nx);
+#pragma unroll
+        for (int i = 0; i < HH; ++i) o[i] = 0.f;
+        m = -INFINITY;
+        l = 0.f;
+        alpha_prev = 0.f;
+      }
+      ptx::mbar_wait(&bar_s[g & 1], (g >> 1) & 1);
+      ptx::tc_fence_after();
+      if (g >= 1) {
+        ptx::mbar_wait(&bar_o, (g - 1) & 1);  // O_{g-1} finished: sP and the O tile are free
+        ptx::tc_fence_after();
+        if (j > 0) add_o_tile();  // (for j == 0 the previous item's epilogue already consumed it)
+      }
+      float s[32];
+      {
+        uint32_t v[32];
+        ptx::tmem_ld32(tmem + lane_off + (g & 1) * KT + half * 32, v);
+        ptx::tmem_ld_wait();
+        if (tile_may_be_masked(p, j * KT)) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(v[i]) + key_bias(p, it.b, j * KT + half * 32 + i);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(v[i]);
+        }
+      }
+      float mx0 = fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])), mx1 = fmaxf(fmaxf(s[4], s[5]), fmaxf(s[6], s[7]));
+#pragma unroll
+      for (int i = 8; i < 32; i += 8) {
+        mx0 = fmaxf(mx0, fmaxf(fmaxf(s[i], s[i + 1]), fmaxf(s[i + 2], s[i + 3])));
+        mx1 = fmaxf(mx1, fmaxf(fmaxf(s[i + 4], s[i + 5]), fmaxf(s[i + 6], s[i + 7])));
+      }
+      float* sx = sX + (g & 1) * 256;  // double-buffered by tile parity: one pair barrier per tile
+      sx[half * 128 + r] = fmaxf(mx0, mx1);
+      pair_barrier(1 + (warp & 3));
+      const float mx = fmaxf(sx[r], sx[128 + r]);
+      const float m_new = fmaxf(m, mx);
+      const float ms = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
+      alpha_prev = ex2(m * p.scale_log2 - ms);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s[i] = ex2(s[i] * p.scale_log2 - ms);
+      float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        ls0 += (s[i] + s[i + 1]) + (s[i + 2] + s[i + 3]);
+        ls1 += (s[i + 4] + s[i + 5]) + (s[i + 6] + s[i + 7]);
+      }
+      store_bf16x32(sP + r * 16, half * 32, s);
+      l = l * alpha_prev + (ls0 + ls1);
+      m = m_new;
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&ps_full);
+      if (j == T - 1) {  // item epilogue
+        ptx::mbar_wait(&bar_o, g & 1);
+        ptx::tc_fence_after();
+        add_o_tile();
+        float* sl = sX + 512 + (k & 1) * 256;
+        sl[half * 128 + r] = l;
+        pair_barrier(1 + (warp & 3));
+        const float lt = sl[r] + sl[128 + r];
+        const float inv = lt > 0.f ? 1.f / lt : 0.f;
+        const int row = it.x * 128 + r;
+        if (half == 0 && p.lse && row < p.S) p.lse[((int64_t)it.b * p.H + it.h) * p.S + row] = m * p.scale + logf(lt);
+        compute_barrier();  // the previous item's store_tile has finished reading the staging tile
+#pragma unroll
+        for (int c = 0; c < HH; c += 8) {
+          float t8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t8[i] = o[c + i] * inv;
+          st8(sStage + r * HDP + half * HH + c, pack8(t8));
+        }
+        ptx::tc_fence_before();
+        compute_barrier();
+        store_tile<HDP, O_OUT>(sStage, p, it.b, it.h, it.x * 128, tid);
+        j = 0;
+        ++k;
+      } else {
+        ++j;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp_u == 8) ptx::tmem_dealloc<256>(__shfl_sync(0xffffffffu, tmem_slot, 0));
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // backward: dQ (and D = rowsum(dO o O))
 // ---------------------------------------------------------------------------------------------------------
 template <int HDP, int RES, int NST, bool TMA>
@@ -813,6 +1021,7 @@ struct dlb_attn_seg {
 };
 
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <unordered_map>
 
 namespace {
@@ -902,6 +1111,38 @@ DLB_EXPORT int dlb_attn_fwd_tc(const dlb_attn_seg* segs, int nseg, float* lse, c
   Params p{};
   int rc = fill_tc_params(p, "attn_fwd_tc", segs, nseg, lse, nullptr, kmask, mask_len, B, H, hd, scale, false);
   if (rc) return rc;
+  static const bool simple = getenv("DLB_ATTN_FWD_SIMPLE") != nullptr;  // the 256-thread kernel (kept for comparison)
+  if (!simple) {
+    const int nitems = ((p.S + 127) / 128) * H * B, T = (p.S + 63) / 64;
+    const int sms = dlb_num_sms();
+    bool use_tma = true;
+    for (int i = 0; i < nseg; ++i) use_tma = use_tma && segs[i].len > 0 && segs[i].len % 128 == 0;
+    HDP_SWITCH_TC(hd, {
+      constexpr int RES_F = HDPV <= 80 ? 2 : 1, NST_F = HDPV <= 96 ? 4 : 3;
+      const size_t smem = (size_t)RES_F * 128 * HDPV * 2 + (size_t)NST_F * 2 * 64 * HDPV * 2 + 16384 + (size_t)128 * HDPV * 2 + 1024 * 4;
+      const int grid_f = (RES_F == 2 && T >= NST_F && nitems > sms) ? sms : nitems;
+      static BwdMaps maps;
+      if (use_tma) {
+        for (int i = 0; i < nseg; ++i) {
+          const dlb_attn_seg& g = segs[i];
+          const int64_t rows = (int64_t)B * g.len;
+          rc = head_map(&maps.m[i][M_Q128], g.q, rows, g.ldq, H, hd, 128, HDPV / 8);
+          if (!rc) rc = head_map(&maps.m[i][M_K64], g.k, rows, g.ldk, H, hd, 64, HDPV / 8);
+          if (!rc) rc = head_map(&maps.m[i][M_V64], g.v, rows, g.ldv, H, hd, 64, HDPV / 8);
+          if (rc) return rc;
+        }
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_ws_tc_kernel<HDPV, RES_F, NST_F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        DLB_REQUIRE(e == cudaSuccess, (int)e, "attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attn_fwd_ws_tc_kernel<HDPV, RES_F, NST_F, true><<<grid_f, NT, smem, stream>>>(p, maps);
+      } else {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_ws_tc_kernel<HDPV, RES_F, NST_F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        DLB_REQUIRE(e == cudaSuccess, (int)e, "attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attn_fwd_ws_tc_kernel<HDPV, RES_F, NST_F, false><<<grid_f, NT, smem, stream>>>(p, maps);
+      }
+    });
+    dlb_count_launch();
+    return dlb_check_launch("attn_fwd_ws_tc");
+  }
   dim3 grid((p.S + 127) / 128, H, B);
   HDP_SWITCH_TC(hd, {
     const size_t smem = (size_t)3 * 128 * HDPV * 2 + 32768 + 3 * 128 * 4;
