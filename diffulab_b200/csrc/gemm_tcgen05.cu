@@ -85,7 +85,7 @@ template <int BN, int OUT, int EPI>
 __device__ __forceinline__ void epilogue_tile(const CUtensorMap& tmC, const CUtensorMap& tmC2, const float* __restrict__ bias,
                                               bool add_bias, uint8_t* sE, uint64_t* lbar, int ew, int lane, int M, int N, int row0,
                                               int n_blk, uint32_t taddr, int& ebuf, uint32_t& hphase, int next_row0 = -1,
-                                              int next_n_blk = 0) {
+                                              int next_n_blk = 0, int my_slot = -1) {
   constexpr bool SWIGLU = EPI == EPI_SWIGLU, SWIGLU_BWD = EPI == EPI_SWIGLU_BWD;
   constexpr int BNT = SWIGLU ? BN / 2 : BN;
   constexpr int CH = (OUT == OUT_BF16) ? 64 : 32;  // columns per 128-byte staging row
@@ -97,6 +97,7 @@ __device__ __forceinline__ void epilogue_tile(const CUtensorMap& tmC, const CUte
     const bool rows_ok = row0 < M;
 #pragma unroll 1
     for (int slot = 0; slot < 2; ++slot) {
+      if (my_slot >= 0 && slot != my_slot) continue;  // 8-warp epilogue: this warp owns one 64-column slot of its 32 rows
       const int col0 = n_blk * BN + slot * 64;
       uint8_t* abuf = wbase + slot * 2 * EPI_BUF_BYTES;
       uint8_t* gbuf = abuf + EPI_BUF_BYTES;
@@ -131,7 +132,7 @@ __device__ __forceinline__ void epilogue_tile(const CUtensorMap& tmC, const CUte
       __syncwarp();
       // slot 0 of the NEXT tile is requested as soon as this tile's slot-0 stores have been read (they were committed a
       // whole chunk ago), not after the tile: the main loop of a K = 1152 tile is shorter than the TMA load latency
-      if (slot == 1) issue_h_tile_loads<BN>(tmC2, sE, lbar, ew, lane, M, N, next_row0, next_n_blk, true, 1);
+      if (slot == 1 && my_slot < 0) issue_h_tile_loads<BN>(tmC2, sE, lbar, ew, lane, M, N, next_row0, next_n_blk, true, 1);
       if (lane == 0 && rows_ok) {
         ptx::tma_store_2d(&tmC, abuf, col0, row0);
         ptx::tma_store_2d(&tmC, gbuf, N + col0, row0);
@@ -241,8 +242,11 @@ __device__ __forceinline__ void epilogue_tile(const CUtensorMap& tmC, const CUte
 // epilogue warps TMA-load the matching (a, g) tiles of the saved pre-activation H (prefetched during the tile's
 // main loop), compute da = dact * g * silu'(a), dg = dact * silu(a) in place and TMA-store them to dH[:, n] / dH[:, F+n].
 // d(act) is never written to memory. N = F here.
+// (The SWIGLU_BWD variant runs EIGHT epilogue warps, 384 threads: its epilogue does ~22 instructions per element and with
+//  four warps took 2.4x the main loop of a K = 1152 tile; warps 8-11 share the TMEM lane quarters of warps 4-7 and take the
+//  second 64-column slot.)
 template <int BN, bool A_MN, bool B_MN, int OUT, int EPI = EPI_NONE>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(EPI == EPI_SWIGLU_BWD ? 384 : 256, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
                     const float* __restrict__ bias, int M, int N, int K, int split_k) {
@@ -285,7 +289,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull[i], 1);
-      ptx::mbar_init(&tempty[i], EPI_WARPS);
+      ptx::mbar_init(&tempty[i], SWIGLU_BWD ? 2 * EPI_WARPS : EPI_WARPS);
     }
     for (int i = 0; i < 2 * EPI_WARPS; ++i) ptx::mbar_init(&lbar[i], 1);
     ptx::fence_mbar_init();
@@ -369,7 +373,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue: TMEM -> registers -> swizzled smem -> TMA store =====================
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
+    const int ew = (warp - 4) & 3;  // == warp % 4: the TMEM lane quarter this warp may access
+    const int my_slot = SWIGLU_BWD ? (warp - 4) >> 2 : -1;
+    const int slot_mask = SWIGLU_BWD ? 1 << ((warp - 4) >> 2) : 3;
     int ebuf = 0;
     int as = 0;
     uint32_t aphase = 0;
@@ -381,7 +387,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     };
     if constexpr (SWIGLU_BWD) {
-      if ((int)blockIdx.x < tiles) issue_h_loads(blockIdx.x, false, 3);
+      if ((int)blockIdx.x < tiles) issue_h_loads(blockIdx.x, false, slot_mask);
     }
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(t, mb, nb, kb_total, kb_per);
@@ -398,14 +404,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           next_n_blk = tcn.n_blk;
         }
       }
-      epilogue_tile<BN, OUT, EPI>(tmC, tmC2, bias, add_bias, sE, lbar, ew, lane, M, N, row0, tc.n_blk, taddr, ebuf, hphase, next_row0, next_n_blk);
+      epilogue_tile<BN, OUT, EPI>(tmC, tmC2, bias, add_bias, sE, lbar, ew, lane, M, N, row0, tc.n_blk, taddr, ebuf, hphase, next_row0, next_n_blk, my_slot);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[as]);
       as ^= 1;
       if (as == 0) aphase ^= 1;
       if constexpr (SWIGLU_BWD) {  // h tiles of my next output tile: they land while its main loop runs
-        if (t + (int)gridDim.x < tiles) issue_h_loads(t + gridDim.x, true, 2);  // slot 1 (slot 0 went out inside the epilogue)
+        if (t + (int)gridDim.x < tiles) issue_h_loads(t + gridDim.x, true, slot_mask);
       }
     }
     if (lane == 0) ptx::tma_wait_group<0>();
@@ -888,7 +894,7 @@ DLB_EXPORT int dlb_gemm_swiglu_bwd_bf16(const void* dY, const void* W2, const vo
   }
   const int tiles = (int)(((M + BM - 1) / BM) * (F / 128));
   const int grid = tiles < dlb_num_sms() ? tiles : dlb_num_sms();
-  kern<<<grid, 256, C::SMEM_BYTES, stream>>>(ta, tb, tc, tc2, nullptr, (int)M, (int)F, (int)D, 1);
+  kern<<<grid, 384, C::SMEM_BYTES, stream>>>(ta, tb, tc, tc2, nullptr, (int)M, (int)F, (int)D, 1);
   dlb_count_launch();
   return dlb_check_launch("gemm_swiglu_bwd");
 }
