@@ -1117,6 +1117,7 @@ DLB_EXPORT int dlb_attn_fwd_tc(const dlb_attn_seg* segs, int nseg, float* lse, c
     const int sms = dlb_num_sms();
     bool use_tma = true;
     for (int i = 0; i < nseg; ++i) use_tma = use_tma && segs[i].len > 0 && segs[i].len % 128 == 0;
+    if (getenv("DLB_ATTN_NO_TMA") != nullptr) use_tma = false;  // tests: force the cp.async producers on TMA-eligible shapes
     HDP_SWITCH_TC(hd, {
       constexpr int RES_F = HDPV <= 80 ? 2 : 1, NST_F = HDPV <= 96 ? 4 : 3;
       const size_t smem = (size_t)RES_F * 128 * HDPV * 2 + (size_t)NST_F * 2 * 64 * HDPV * 2 + 16384 + (size_t)128 * HDPV * 2 + 1024 * 4;
@@ -1167,6 +1168,7 @@ DLB_EXPORT int dlb_attn_bwd_tc(const dlb_attn_seg* segs, int nseg, const float* 
   const int sms = dlb_num_sms();
   bool use_tma = true;  // TMA producer: every tile lies inside one segment and lse / dsum rows are 16-byte aligned
   for (int i = 0; i < nseg; ++i) use_tma = use_tma && segs[i].len > 0 && segs[i].len % 128 == 0;
+    if (getenv("DLB_ATTN_NO_TMA") != nullptr) use_tma = false;  // tests: force the cp.async producers on TMA-eligible shapes
   HDP_SWITCH_TC(hd, {
     // resident double-buffering (persistent CTAs) where shared memory allows; otherwise one item per CTA
     constexpr int RES_DQ = HDPV <= 80 ? 2 : 1, NST_DQ = HDPV <= 96 ? 4 : 3;

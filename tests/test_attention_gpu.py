@@ -84,3 +84,44 @@ def test_attention_fwd_bwd(cuda_device, B, H, hd, L, N, masked, impl, bwd_impl):
     assert rel_l2(dv, v.grad.reshape(B, S, d)) < 2e-2
     for x in dqkvs:
         assert x[:, : 2 * d].abs().max().item() == 0.0  # attention bwd only owns the v columns
+
+
+@pytest.mark.parametrize("B,H,hd,L,N", [(3, 4, 72, 0, 256), (2, 6, 64, 128, 256), (10, 16, 72, 0, 256)])
+def test_tma_and_cp_async_producers_agree_bitwise(cuda_device, B, H, hd, L, N):
+    """The TMA (4-D tensor map) and cp.async producer paths stage identical shared-memory images, so forward and backward
+    results must be bit-identical; run in a subprocess with DLB_ATTN_NO_TMA=1 to force the fallback path."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+
+    code = f"""
+import sys, torch
+sys.path.insert(0, {os.getcwd()!r})
+from diffulab_b200 import ops
+B, H, hd, L, N = {B}, {H}, {hd}, {L}, {N}
+g = torch.Generator(device="cuda").manual_seed(7)
+d = H * hd
+lens = [L, N] if L else [N]
+qks = [torch.randn(B * l, 2 * d, device="cuda", generator=g).bfloat16() for l in lens]
+qkvs = [torch.randn(B * l, 3 * d, device="cuda", generator=g).bfloat16() for l in lens]
+specs = [ops.AttnSegSpec(a, b, l) for a, b, l in zip(qks, qkvs, lens)]
+kmask = None
+if L:
+    kl = torch.randint(1, L + 1, (B,), device="cuda", generator=g)
+    kmask = (torch.arange(L, device="cuda")[None, :] < kl[:, None]).to(torch.uint8).contiguous()
+outs, lse = ops.attn_fwd(specs, B, H, hd, hd ** -0.5, kmask)
+douts = [torch.randn(o.shape, device="cuda", generator=g).bfloat16() for o in outs]
+dqkvs = [torch.zeros_like(q) for q in qkvs]
+ops.attn_bwd(specs, outs, douts, lse, B, H, hd, hd ** -0.5, dqkvs, kmask)
+torch.save({{"outs": [o.cpu() for o in outs], "lse": lse.cpu(), "dqkvs": [t.cpu() for t in dqkvs]}}, sys.argv[1])
+"""
+    res = []
+    for env_extra in ({}, {"DLB_ATTN_NO_TMA": "1"}):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env={**os.environ, **env_extra}, timeout=300)
+            res.append(torch.load(f.name))
+    a, b = res
+    assert torch.equal(a["lse"], b["lse"])
+    for x, y in zip(a["outs"] + a["dqkvs"], b["outs"] + b["dqkvs"]):
+        assert torch.equal(x, y)
