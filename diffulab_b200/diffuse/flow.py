@@ -107,8 +107,28 @@ class Flow(Diffusion):
             return (model_inputs["x"] - prediction) / max(t_curr, 0.05)
         return prediction
 
+    batch_cfg: bool = True  # run the two classifier-free-guidance evaluations as one batched forward where possible
+
+    def _can_batch_cfg(self, model: Denoiser, model_inputs: ModelInput) -> bool:
+        return (self.batch_cfg and model_inputs.get("y") is not None and model_inputs.get("initial_context") is None
+                and model_inputs.get("x_context") is None and getattr(model, "label_embed", None) is not None
+                and getattr(model, "classifier_free", False) and getattr(model, "n_classes", None) is not None)
+
     def one_step_denoise(self, model: Denoiser, model_inputs: ModelInput, t_prev: float, t_curr: float, guidance_scale: float,
                          sampler_args: dict[str, Any] = {}) -> StepResult:
+        if guidance_scale > 0 and self._can_batch_cfg(model, model_inputs):
+            # Label-conditioned classifier-free guidance: the conditional and the unconditional evaluation (reference
+            # flow.py:256-259: p = 0, then p = 1 = every label replaced by the null class) run as ONE forward over
+            # [x; x] with labels [y; null]. Samples do not interact inside the denoiser (tests: batch-slice independence),
+            # so the two halves equal the two separate calls; the label dropout at p = 1 is deterministic.
+            x = model_inputs["x"]
+            y = model_inputs["y"]
+            both = {**model_inputs, "x": torch.cat([x, x], 0), "y": torch.cat([y, torch.full_like(y, model.n_classes)], 0), "p": 0}
+            v, v_dropped = self.get_v(model, ModelInput(both), t_curr).chunk(2, 0)
+            if isinstance(self.sampler, Euler) and not sampler_args:
+                return self.sampler.step_cfg(x, v, v_dropped, guidance_scale, t_curr, t_prev)
+            v = v_dropped + guidance_scale * (v - v_dropped)
+            return self.sampler.step(x, v, t_curr, t_prev, **sampler_args)
         v = self.get_v(model, ModelInput({**model_inputs, "p": 0}), t_curr)
         if guidance_scale > 0:
             v_dropped = self.get_v(model, {**model_inputs, "p": 1}, t_curr)

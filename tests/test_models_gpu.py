@@ -169,6 +169,10 @@ def test_golden_euler_trajectory(cuda_device, name):
     assert out["x"].dtype == torch.float32
     assert rel_l2(out["x"], e["x_final"]) < 5e-2
     assert rel_l2(out["xt"], e["xt"]) < 5e-2
+    # the batched conditional + unconditional evaluation (one forward over [x; x]) equals the two separate calls
+    flow.batch_cfg = False
+    out2 = flow.denoise(model, {"x": e["x_init"].cuda(), **inputs_for(fx)}, use_tqdm=False, guidance_scale=e["guidance"], return_intermediates=True)
+    assert torch.equal(out["x"], out2["x"]) and torch.equal(out["xt"], out2["xt"])
 
 
 def _rand_sd(model, seed):
