@@ -5,7 +5,8 @@
 // first, then image rows), bf16 operands, fp32 softmax. Q / K arrive RMS-normalised and rotated (qknorm_rope.cu), V is
 // read in place from the packed qkv projection.
 //
-// Structure (all three kernels): one CTA owns one 128-row tile of one (sample, head) — the "resident" tile, TMEM lane =
+// Structure (forward attn_fwd_ws_tc_kernel, backward attn_bwd_dq/dkv_tc_kernel; attn_fwd_tc_kernel is the earlier 256-thread
+// forward kept for comparison): one CTA owns one 128-row tile of one (sample, head) — the "resident" tile, TMEM lane =
 // resident row — and streams the other sequence axis past it in 64-row tiles through a ring of shared-memory stages.
 // 288 threads: warps 0-7 are compute warps (two threads per resident row, each owning 32 of the 64 columns of a score
 // tile; they also stage all operands with cp.async, 8 rows x 64 bytes per warp instruction), warp 8 only issues

@@ -5,7 +5,10 @@
 //   gate_res    : x + branch * gate                            mmdit.py:296-307
 //   swiglu      : silu(x1) * x3 on the packed up-projection    nn.py:478-486
 //
-// Shapes of the kernels (all accesses are 128-bit, coalesced):
+// Shapes of the kernels (all accesses are 128-bit, coalesced). The per-sample-modulation hot path uses the TILE kernels
+// (cp.async.bulk ring -> shared memory -> compute warps -> bulk store; backward = one pass with per-lane register column
+// accumulators); the row / col / stream kernels below remain for per-token modulation (DDT decoder), ragged group sizes
+// and unaligned views:
 //   row kernels  : one warp owns one token row (d <= 2048); the row is kept PACKED (bf16x8 vectors) in registers so
 //                  the kernels stay at <= 64-80 registers (6-8 CTAs of 4 warps per SM); statistics via warp shuffles.
 //   col kernels  : one thread owns one 8-channel vector and marches down a chunk of rows in batches of 4 rows (8+
