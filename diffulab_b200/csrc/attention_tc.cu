@@ -8,14 +8,18 @@
 // Structure (forward attn_fwd_ws_tc_kernel, backward attn_bwd_dq/dkv_tc_kernel; attn_fwd_tc_kernel is the earlier 256-thread
 // forward kept for comparison): one CTA owns one 128-row tile of one (sample, head) — the "resident" tile, TMEM lane =
 // resident row — and streams the other sequence axis past it in 64-row tiles through a ring of shared-memory stages.
-// 288 threads: warps 0-7 are compute warps (two threads per resident row, each owning 32 of the 64 columns of a score
-// tile; they also stage all operands with cp.async, 8 rows x 64 bytes per warp instruction), warp 8 only issues
-// tcgen05.mma (warp-uniform code, elect.sync) so that instruction issue never sits on the softmax threads' path.
+// 352 threads: warps 0-7 are compute warps (two threads per resident row, each owning 32 of the 64 columns of a score
+// tile), warp 8 only issues tcgen05.mma (warp-uniform code, elect.sync) so that instruction issue never sits on the
+// softmax threads' path, warps 9-10 are producers: one elected lane issues TMA loads through 4-D tensor maps whose
+// boxes land directly in the operand layout (segment lengths that are multiples of 128), otherwise both warps stage with
+// cp.async (8 rows x 64 bytes per warp instruction) and arrive asynchronously (cp.async.mbarrier.arrive.noinc).
+// CTAs are persistent over (tile, head, sample) work items and the load ring runs ahead across item boundaries.
 // No CTA-wide barrier inside the loop; the hand-offs are mbarriers:
-//   full[s]  (256 arrivals) tile in stage s has landed            compute -> MMA warp
-//   bar1[b]  (tcgen05.commit) score tiles in TMEM buffer b ready   MMA warp -> compute
-//   ps_full  (256 arrivals) P / dS operand tile written, TMEM buffer drained   compute -> MMA warp
-//   bar2     (tcgen05.commit) accumulating products of tile j done: stage, operand tile (and O tile) free
+//   full[s]  (TMA bytes / producer arrivals) tile in stage s has landed       producers -> MMA warp
+//   bar1[b]  (tcgen05.commit) score tiles in TMEM buffer b ready              MMA warp -> compute
+//   ps_full  (256 arrivals) P / dS operand tile written, TMEM buffer drained  compute -> MMA warp
+//   bar2     (tcgen05.commit) accumulating products of tile j done: operand tile (and O tile) free
+//   empty[s] (tcgen05.commit) stage s may be refilled                          MMA warp -> producers
 // The MMA warp issues the score products of tile j+1 before the accumulating products of tile j, so the tensor core
 // computes scores while the compute warps do the exponentials of the previous tile; loads run NST-1 tiles ahead.
 // Every operand tile uses ONE shared-memory layout ("L1(R)": 16-byte chunk (row r, chunk c) of an R-row tile at
