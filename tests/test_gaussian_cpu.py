@@ -69,3 +69,45 @@ def test_no_cpu_fallback():
     gd = GaussianDiffusion(n_steps=10)
     with pytest.raises((ValueError, RuntimeError)):
         gd.add_noise(torch.zeros(2, 1, 4, 4), torch.tensor([1, 2], dtype=torch.int32), torch.zeros(2, 1, 4, 4))
+
+
+def test_cfg_batching_is_only_used_for_label_conditioned_models():
+    """Flow batches the conditional / unconditional evaluation into one forward only when the unconditional branch is
+    'every label -> null class' (label-conditioned, classifier-free, no text context); host logic, no kernels involved."""
+    from diffulab_b200 import Flow
+
+    class M:
+        label_embed = object()
+        classifier_free = True
+        n_classes = 10
+
+    class NoCF(M):
+        classifier_free = False
+
+    class Ctx(M):
+        label_embed = None
+
+    f = Flow(n_steps=4)
+    y = torch.zeros(2, dtype=torch.long)
+    assert f._can_batch_cfg(M(), {"x": None, "y": y})
+    assert not f._can_batch_cfg(M(), {"x": None})
+    assert not f._can_batch_cfg(M(), {"x": None, "y": y, "initial_context": {"embeddings": None}})
+    assert not f._can_batch_cfg(M(), {"x": None, "y": y, "x_context": torch.zeros(1)})
+    assert not f._can_batch_cfg(NoCF(), {"x": None, "y": y})
+    assert not f._can_batch_cfg(Ctx(), {"x": None, "y": y})
+    f.batch_cfg = False
+    assert not f._can_batch_cfg(M(), {"x": None, "y": y})
+
+
+def test_euler_maruyama_schedule_scalars():
+    """sigma / std of the stochastic flow sampler are evaluated in Python floats exactly like the reference
+    (samplers/flow/euler_meruyama.py:38-40); tmax = timesteps[1]."""
+    from diffulab_b200 import Flow
+
+    f = Flow(n_steps=10, sampling_method="euler_maruyama", sampler_parameters={"eta": 0.7})
+    assert f.sampler.name == "euler_maruyama" and f.sampler.tmax == f.timesteps[1]
+    t_curr, t_prev = f.timesteps[0], f.timesteps[1]
+    sigma = ((t_curr / (1 - min(t_curr, f.sampler.tmax))) ** 0.5) * 0.7
+    assert sigma > 0 and (t_curr - t_prev) > 0
+    with pytest.raises((ValueError, RuntimeError)):
+        f.sampler.step(torch.zeros(1, 1, 4, 4), torch.zeros(1, 1, 4, 4), t_curr, t_prev)  # CPU tensors: no fallback
