@@ -9,11 +9,11 @@ Everything on the device runs in libdiffulab_b200.so (hand-written CUDA behind a
 __version__ = "0.1.0"
 
 from .denoisers import DDT, Denoiser, MMDiT, ModelInput, ModelOutput, SprintDiT
-from .diffuse import DDIM, DDPM, Diffuser, Diffusion, Euler, EulerMaruyama, Flow, GaussianDiffusion, SamplingOutput, StepResult
+from .diffuse import DDIM, DDPM, Diffuser, Diffusion, Euler, EulerMaruyama, Flow, Heun, GaussianDiffusion, SamplingOutput, StepResult
 from .embedders import ContextEmbedder, PrecomputedEmbedder
 from .losses import LossFunction, RepaLoss
 
 __all__ = [
-    "MMDiT", "SprintDiT", "DDT", "Denoiser", "ModelInput", "ModelOutput", "Diffuser", "Diffusion", "Flow", "GaussianDiffusion", "Euler", "EulerMaruyama", "DDPM", "DDIM",
+    "MMDiT", "SprintDiT", "DDT", "Denoiser", "ModelInput", "ModelOutput", "Diffuser", "Diffusion", "Flow", "GaussianDiffusion", "Euler", "EulerMaruyama", "Heun", "DDPM", "DDIM",
     "SamplingOutput", "StepResult", "ContextEmbedder", "PrecomputedEmbedder", "LossFunction", "RepaLoss",
 ]

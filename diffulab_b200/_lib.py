@@ -17,6 +17,7 @@ p = C.c_void_p
 i64 = C.c_int64
 i32 = C.c_int
 f32 = C.c_float
+f64 = C.c_double
 
 # name -> argtypes (restype is always int unless listed in _RESTYPES). Mirrors include/diffulab_b200.h.
 _SIGNATURES: dict[str, list] = {
@@ -89,8 +90,10 @@ _SIGNATURES: dict[str, list] = {
     "dlb_restore_rows_bwd": [p, p, p, p, p, p, i32, i32, i32, i32, p],
     # x, vc, vu, v_dtype, guidance, t_curr, t_prev, x_prev, x0_est, v_out, n, stream
     "dlb_euler_step": [p, p, p, i32, f32, f32, f32, p, p, p, i64, p],
-    # p, g, m, v, shadow, ema, ema_decay, n, lr, b1, b2, eps, wd, step, grad_scale, stream
-    "dlb_adamw_step": [p, p, p, p, p, p, f32, i64, f32, f32, f32, f32, f32, i64, f32, p],
+    # p, g, m, v, shadow, ema, ema_decay, chunk_active, n, lr, b1, b2, eps, wd, step, grad_scale, stream
+    "dlb_adamw_step": [p, p, p, p, p, p, f32, p, i64, f64, f64, f64, f64, f64, i64, f32, p],
+    # ema, p, decay, n, stream
+    "dlb_ema_lerp": [p, p, f32, i64, p],
 }
 
 

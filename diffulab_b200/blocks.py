@@ -73,8 +73,18 @@ def wb(p: Tensor, pad_cols: int | None = None) -> Tensor:
     return s
 
 
+# ids of the parameters whose gradient buffer was handed to a kernel since the last `clear_touched()` (= the parameters
+# whose .grad would be non-None in the reference after this backward; the optimizer skips the others like torch does)
+_touched: set[int] = set()
+
+
+def clear_touched() -> None:
+    _touched.clear()
+
+
 def gbuf(p: Tensor) -> Tensor:
     """fp32 gradient accumulator of a parameter (allocated zeroed on first use)."""
+    _touched.add(id(p))
     if p.grad is None:
         p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
     return p.grad

@@ -324,29 +324,32 @@ __global__ void euler_maruyama_kernel(const float* __restrict__ x, const TV* __r
 
 // torch.optim.AdamW (no amsgrad, no maximize): p *= 1 - lr*wd; m,v update; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).
 // Also refreshes the bf16 shadow copy used by the GEMMs and (optionally) the EMA copy.
-__device__ __forceinline__ void adamw_one(float& pi, float gi, float& mi, float& vi, float lr, float beta1, float beta2,
-                                          float eps, float wd, float bc1, float bc2_sqrt) {
-  pi *= (1.f - lr * wd);
+__device__ __forceinline__ void adamw_one(float& pi, float gi, float& mi, float& vi, float decay, float beta1, float beta2,
+                                          float eps, float step_size, float bc2_sqrt) {
+  pi *= decay;  // decoupled weight decay: p *= 1 - lr * wd
   mi = beta1 * mi + (1.f - beta1) * gi;
   vi = beta2 * vi + (1.f - beta2) * gi * gi;
-  pi -= (lr / bc1) * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+  pi -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
 }
-// 4 parameters per thread per iteration (128-bit loads / stores; n4 = n / 4), scalar tail handled by the last block
+// 4 parameters per thread per iteration (128-bit loads / stores; n4 = n / 4), scalar tail handled by the last block.
+// chunk_active (nullable): one byte per 64-element chunk of the flat buffer; a zero byte skips the chunk entirely —
+// torch.optim.AdamW skips parameters whose .grad is None (no decay, no moment update, no step).
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-             bf16* __restrict__ shadow, float* __restrict__ ema, float ema_decay, int64_t n, float lr, float beta1,
-             float beta2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+             bf16* __restrict__ shadow, float* __restrict__ ema, float ema_decay, const uint8_t* __restrict__ chunk_active,
+             int64_t n, float decay, float beta1, float beta2, float eps, float step_size, float bc2_sqrt, float grad_scale) {
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    if (chunk_active != nullptr && chunk_active[i >> 4] == 0) continue;
     float4 pv = reinterpret_cast<float4*>(p)[i];
     const float4 gv = reinterpret_cast<const float4*>(g)[i];
     float4 mv = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
-    adamw_one(pv.x, gv.x * grad_scale, mv.x, vv.x, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
-    adamw_one(pv.y, gv.y * grad_scale, mv.y, vv.y, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
-    adamw_one(pv.z, gv.z * grad_scale, mv.z, vv.z, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
-    adamw_one(pv.w, gv.w * grad_scale, mv.w, vv.w, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
+    adamw_one(pv.x, gv.x * grad_scale, mv.x, vv.x, decay, beta1, beta2, eps, step_size, bc2_sqrt);
+    adamw_one(pv.y, gv.y * grad_scale, mv.y, vv.y, decay, beta1, beta2, eps, step_size, bc2_sqrt);
+    adamw_one(pv.z, gv.z * grad_scale, mv.z, vv.z, decay, beta1, beta2, eps, step_size, bc2_sqrt);
+    adamw_one(pv.w, gv.w * grad_scale, mv.w, vv.w, decay, beta1, beta2, eps, step_size, bc2_sqrt);
     reinterpret_cast<float4*>(p)[i] = pv;
     reinterpret_cast<float4*>(m)[i] = mv;
     reinterpret_cast<float4*>(v)[i] = vv;
@@ -356,7 +359,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
       s2.y = pack_bf16x2(pv.z, pv.w);
       reinterpret_cast<uint2*>(shadow)[i] = s2;
     }
-    if (ema) {
+    if (ema) {  // ema.lerp_(p, 1 - decay) (ema_pytorch update_moving_average); decay 0 = copy
       float4 ev = reinterpret_cast<float4*>(ema)[i];
       ev.x = ev.x * ema_decay + pv.x * (1.f - ema_decay);
       ev.y = ev.y * ema_decay + pv.y * (1.f - ema_decay);
@@ -367,13 +370,31 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
   }
   if (blockIdx.x == gridDim.x - 1) {
     for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
+      if (chunk_active != nullptr && chunk_active[i >> 6] == 0) continue;
       float pi = p[i], mi = m[i], vi = v[i];
-      adamw_one(pi, g[i] * grad_scale, mi, vi, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt);
+      adamw_one(pi, g[i] * grad_scale, mi, vi, decay, beta1, beta2, eps, step_size, bc2_sqrt);
       p[i] = pi; m[i] = mi; v[i] = vi;
       if (shadow) shadow[i] = __float2bfloat16_rn(pi);
       if (ema) ema[i] = ema[i] * ema_decay + pi * (1.f - ema_decay);
     }
   }
+}
+
+// ema = ema * decay + p * (1 - decay) over a flat buffer (EMA updates that do not coincide with an optimizer step)
+__global__ void __launch_bounds__(256) ema_lerp_kernel(float* __restrict__ ema, const float* __restrict__ p, float decay, int64_t n) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 ev = reinterpret_cast<float4*>(ema)[i];
+    const float4 pv = reinterpret_cast<const float4*>(p)[i];
+    ev.x = ev.x * decay + pv.x * (1.f - decay);
+    ev.y = ev.y * decay + pv.y * (1.f - decay);
+    ev.z = ev.z * decay + pv.z * (1.f - decay);
+    ev.w = ev.w * decay + pv.w * (1.f - decay);
+    reinterpret_cast<float4*>(ema)[i] = ev;
+  }
+  if (blockIdx.x == gridDim.x - 1)
+    for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) ema[i] = ema[i] * decay + p[i] * (1.f - decay);
 }
 
 }  // namespace
@@ -505,16 +526,26 @@ DLB_EXPORT int dlb_euler_maruyama_step(const float* x, const void* v, int v_dtyp
   return dlb_check_launch("euler_maruyama_step");
 }
 
+// Hyper-parameters arrive as doubles (python floats) and the bias corrections are evaluated in double exactly as
+// torch.optim.AdamW's single-tensor path does (step_size = lr / (1 - beta1^step), sqrt(1 - beta2^step)).
 DLB_EXPORT int dlb_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, float* ema, float ema_decay,
-                              int64_t n, float lr, float beta1, float beta2, float eps, float wd, int64_t step,
-                              float grad_scale, cudaStream_t stream) {
+                              const uint8_t* chunk_active, int64_t n, double lr, double beta1, double beta2, double eps, double wd,
+                              int64_t step, float grad_scale, cudaStream_t stream) {
   DLB_REQUIRE(n > 0 && step >= 1, DLB_ERR_SHAPE, "adamw_step: bad args");
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2_sqrt = sqrt(1.0 - pow(beta2, (double)step));
   DLB_REQUIRE(((uintptr_t)p % 16) == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)m % 16) == 0 && ((uintptr_t)v % 16) == 0 &&
                   ((uintptr_t)shadow % 8) == 0 && ((uintptr_t)ema % 16) == 0,
               DLB_ERR_ALIGN, "adamw_step: buffers must be 16-byte aligned");
-  adamw_kernel<<<grid_for((n + 3) / 4), 256, 0, stream>>>(p, g, m, v, (bf16*)shadow, ema, ema_decay, n, lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, grad_scale);
+  adamw_kernel<<<grid_for((n + 3) / 4), 256, 0, stream>>>(p, g, m, v, (bf16*)shadow, ema, ema_decay, chunk_active, n, (float)(1.0 - lr * wd),
+                                                          (float)beta1, (float)beta2, (float)eps, (float)(lr / bc1), (float)bc2_sqrt, grad_scale);
   dlb_count_launch();
   return dlb_check_launch("adamw_step");
+}
+
+DLB_EXPORT int dlb_ema_lerp(float* ema, const float* p, float decay, int64_t n, cudaStream_t stream) {
+  DLB_REQUIRE(n > 0 && ((uintptr_t)ema % 16) == 0 && ((uintptr_t)p % 16) == 0, DLB_ERR_ALIGN, "ema_lerp: bad args");
+  ema_lerp_kernel<<<grid_for((n + 3) / 4), 256, 0, stream>>>(ema, p, decay, n);
+  dlb_count_launch();
+  return dlb_check_launch("ema_lerp");
 }

@@ -29,6 +29,9 @@ class _DenoiserBase(Denoiser):
     rope_axes_dim: list[int]
     label_embed: LabelEmbed | None
     context_embedder: ContextEmbedder | None
+    # True when the drop probability `p` touches nothing but the label / context (so Flow may batch the conditional and
+    # unconditional guidance passes into one forward); SprintDiT's p also drives path-drop and opts out.
+    cfg_batchable: bool = True
 
     def _conditioning(self, timesteps: Tensor, y: Tensor | None, p: float) -> tuple[Tensor, Tensor]:
         labels, table = None, None

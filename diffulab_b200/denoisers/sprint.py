@@ -21,6 +21,8 @@ from .mmdit import _DenoiserBase, _default_axes
 
 
 class SprintDiT(_DenoiserBase):
+    cfg_batchable = False  # p = 1 also skips the deep layers (path-drop guidance, sprint.py:474-475)
+
     def __init__(
         self,
         simple_dit: bool = False,
@@ -164,5 +166,9 @@ class SprintDiT(_DenoiserBase):
         out = self.last_layer(fused, cond_silu, (H, W))
         model_output: ModelOutput = {"x": out}
         if features is not None:
+            # the reference appends the post-last_layer token tensor [B, N, p*p*C] as the final feature (sprint.py:492-494,
+            # 574-576); the fused last layer returns the image, so the token view is rebuilt (layout plumbing only)
+            C_out = self.output_channels
+            features.append(out.view(B, C_out, hp, ps, wp, ps).permute(0, 2, 4, 3, 5, 1).reshape(B, hp * wp, ps * ps * C_out))
             model_output["features"] = features
         return model_output

@@ -682,18 +682,32 @@ def restore_rows_bwd(dy: Tensor, idx: Tensor, inv: Tensor, drop: Tensor | None, 
 
 
 def euler_step(x: Tensor, vc: Tensor, vu: Tensor | None, guidance: float, t_curr: float, t_prev: float,
-               want_x0: bool = True) -> tuple[Tensor, Tensor | None]:
+               want_x0: bool = True, want_v: bool = False):
+    """x_prev = x - v dt (dt = t_curr - t_prev), estimated_x0 = x - v t_curr with v = vc, or vu + guidance (vc - vu)
+    when vu is given, in one launch. Returns (x_prev, x0 | None) and, with want_v, also the combined v (fp32)."""
     _req(x, F32, "x")
     _req(vc, vc.dtype, "vc")
     x_prev = torch.empty_like(x)
     x0 = torch.empty_like(x) if want_x0 else None
+    v_out = torch.empty_like(x) if want_v else None
     _lib_call("dlb_euler_step", x.data_ptr(), vc.data_ptr(), _ptr(vu), _dt(vc), guidance, t_curr, t_prev, x_prev.data_ptr(),
-              _ptr(x0), None, x.numel(), _stream())
+              _ptr(x0), _ptr(v_out), x.numel(), _stream())
+    if want_v:
+        return x_prev, x0, v_out
     return x_prev, x0
 
 
 def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, shadow: Tensor | None, *, lr: float, beta1: float, beta2: float,
                eps: float, weight_decay: float, step: int, grad_scale: float = 1.0, ema: Tensor | None = None,
-               ema_decay: float = 0.0) -> None:
+               ema_decay: float = 0.0, chunk_active: Tensor | None = None) -> None:
+    """chunk_active: uint8 [ceil(n / 64)], 0 = leave that 64-element chunk untouched (torch skips grad-less parameters)."""
     _lib_call("dlb_adamw_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(shadow), _ptr(ema), ema_decay,
-              p.numel(), lr, beta1, beta2, eps, weight_decay, step, grad_scale, _stream())
+              _ptr(chunk_active), p.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), step, grad_scale,
+              _stream())
+
+
+def ema_lerp_(ema: Tensor, p: Tensor, decay: float) -> None:
+    """ema = ema * decay + p * (1 - decay), flat fp32 buffers."""
+    _req(ema, F32, "ema")
+    _req(p, F32, "p")
+    _lib_call("dlb_ema_lerp", ema.data_ptr(), p.data_ptr(), float(decay), ema.numel(), _stream())

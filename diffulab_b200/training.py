@@ -72,10 +72,12 @@ class FlatParams:
 
 
 class FusedAdamW(torch.optim.Optimizer):
-    """torch.optim.AdamW semantics (decoupled weight decay, bias correction; no amsgrad) as ONE kernel over the flat
-    parameter buffer; the same pass writes the bf16 shadow consumed by the next forward and, optionally, an EMA
-    copy (reference: torch.optim.AdamW built from configs/optimizer/adamw.yaml + ema_pytorch, base_trainer.py:149-153).
-    `state_dict()` keeps torch's per-parameter layout (step / exp_avg / exp_avg_sq)."""
+    """torch.optim.AdamW semantics (decoupled weight decay, bias correction in double; no amsgrad) as ONE kernel over the
+    flat parameter buffer; the same pass writes the bf16 shadow consumed by the next forward and, when an `EMA` is
+    attached and due, its moving average (reference: torch.optim.AdamW built from configs/optimizer/adamw.yaml +
+    ema_pytorch, base_trainer.py:149-153). Parameters that received no gradient since `zero_grad()` are skipped exactly as
+    torch skips `p.grad is None` (no decay, no moment update). `state_dict()` / `load_state_dict()` keep torch's
+    per-parameter layout (step / exp_avg / exp_avg_sq)."""
 
     def __init__(self, params, lr: float = 1e-3, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-2, grad_scale: float = 1.0):
@@ -86,22 +88,75 @@ class FusedAdamW(torch.optim.Optimizer):
         self._steps: list[int] = []
         self._m: list[Tensor] = []
         self._v: list[Tensor] = []
+        self._step_t: list[Tensor] = []
+        self._mask_key: list[frozenset | None] = []
+        self._mask: list[Tensor | None] = []
+        self.ema: "EMA | None" = None
         for group in self.param_groups:
             st = FlatParams(group["params"])
             self.stores.append(st)
             self._steps.append(0)
-            m, v = torch.zeros_like(st.flat_p), torch.zeros_like(st.flat_p)
-            step_t = torch.tensor(0.0)  # one shared counter tensor per group (torch keeps one per parameter)
-            self._step_t = getattr(self, "_step_t", []) + [step_t]
-            self._m.append(m)
-            self._v.append(v)
+            self._m.append(torch.zeros_like(st.flat_p))
+            self._v.append(torch.zeros_like(st.flat_p))
+            self._step_t.append(torch.tensor(0.0))  # one shared counter tensor per group (torch keeps one per parameter)
+            self._mask_key.append(None)
+            self._mask.append(None)
+        self._point_state()
+
+    def _point_state(self) -> None:
+        """self.state[p] = views of the flat moment buffers (what state_dict() serialises)."""
+        for gi, st in enumerate(self.stores):
+            m, v = self._m[gi], self._v[gi]
             for p, o in zip(st.params, st.offsets):
                 n = p.numel()
-                self.state[p] = {"step": step_t, "exp_avg": m[o : o + n].view(p.shape), "exp_avg_sq": v[o : o + n].view(p.shape)}
+                self.state[p] = {"step": self._step_t[gi], "exp_avg": m[o : o + n].view(p.shape), "exp_avg_sq": v[o : o + n].view(p.shape)}
+
+    def load_state_dict(self, state_dict: dict) -> None:
+        """torch's loader replaces self.state[p] with fresh tensors; copy them back into the flat buffers the kernel reads,
+        restore the step counters and re-point the state at the flat views (a resumed run continues bit-identically)."""
+        super().load_state_dict(state_dict)
+        with torch.no_grad():
+            for gi, st in enumerate(self.stores):
+                steps = set()
+                for p, o in zip(st.params, st.offsets):
+                    ent = self.state.get(p, {})
+                    n = p.numel()
+                    if "exp_avg" in ent:
+                        self._m[gi][o : o + n].copy_(ent["exp_avg"].reshape(-1))
+                        self._v[gi][o : o + n].copy_(ent["exp_avg_sq"].reshape(-1))
+                    if "step" in ent:
+                        steps.add(int(float(ent["step"])))
+                step = max(steps) if steps else 0
+                self._steps[gi] = step
+                self._step_t[gi] = torch.tensor(float(step))
+        self._point_state()
 
     def zero_grad(self, set_to_none: bool = True) -> None:  # noqa: ARG002 - gradients live in the flat buffer
         for st in self.stores:
             st.zero_grad()
+        K.clear_touched()
+
+    def _active_mask(self, gi: int) -> Tensor | None:
+        """uint8 per 64-element chunk: 0 for parameters that received no gradient this step (torch: .grad is None).
+        Rebuilt only when the set of gradient-receiving parameters changes (normally once)."""
+        st = self.stores[gi]
+        touched = frozenset(i for i, p in enumerate(st.params) if id(p) in K._touched)
+        if touched == self._mask_key[gi]:
+            return self._mask[gi]
+        self._mask_key[gi] = touched
+        idle = [i for i in range(len(st.params)) if i not in touched]
+        # a gradient may also have arrived through plain autograd (accumulated into the flat view): only all-zero slices
+        # of untouched parameters count as "no gradient"
+        idle = [i for i in idle if not bool(st.params[i].grad.any().item())] if idle else []
+        if not idle:
+            self._mask[gi] = None
+            return None
+        mask = torch.ones(st.total // _ALIGN, dtype=torch.uint8)
+        for i in idle:
+            o, n = st.offsets[i], st.params[i].numel()
+            mask[o // _ALIGN : (o + n + _ALIGN - 1) // _ALIGN] = 0
+        self._mask[gi] = mask.to(st.flat_p.device)
+        return self._mask[gi]
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -109,15 +164,98 @@ class FusedAdamW(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        ema_plan = self.ema.plan() if self.ema is not None else None  # ("skip" | "copy" | "lerp", decay)
         for gi, (group, st) in enumerate(zip(self.param_groups, self.stores)):
             st.check_versions()
             self._steps[gi] += 1
             b1, b2 = group["betas"]
+            mask = self._active_mask(gi)
+            # the EMA rides in the same pass only when every parameter is written (no skipped chunks)
+            fuse_ema = ema_plan is not None and ema_plan[0] != "skip" and mask is None
             ops.adamw_step(st.flat_p, st.flat_g, self._m[gi], self._v[gi], st.flat_shadow, lr=float(group["lr"]), beta1=b1, beta2=b2,
-                           eps=group["eps"], weight_decay=group["weight_decay"], step=self._steps[gi], grad_scale=self.grad_scale)
+                           eps=group["eps"], weight_decay=group["weight_decay"], step=self._steps[gi], grad_scale=self.grad_scale,
+                           ema=self.ema.flat[gi] if fuse_ema else None, ema_decay=ema_plan[1] if fuse_ema else 0.0, chunk_active=mask)
+            if ema_plan is not None and ema_plan[0] != "skip" and not fuse_ema:
+                ops.ema_lerp_(self.ema.flat[gi], st.flat_p, ema_plan[1])
             self._step_t[gi] += 1
+        if self.ema is not None:
+            self.ema.advance()
         K.bump_shadow_epoch()  # version-cached (padded) shadows must be rebuilt; installed flat shadows stay valid
         return loss
+
+
+class EMA:
+    """Exponential moving average of the optimised parameters, fused into the AdamW pass.
+
+    Reference: `ema_pytorch.EMA(model, beta, update_after_step, update_every)` built in base_trainer.py:247-253 and
+    advanced by `ema_denoiser.update()` right after `optimizer.step()` (base_trainer.py:152-153). ema-pytorch 0.7.7 is a
+    third-party dependency (uv.lock) that is NOT present in this container, so its published algorithm is restated here
+    ("parity unpinned" for this class; tests compare with a torch restatement of the same rule):
+      update(): step = self.step; self.step += 1
+                first call            -> copy the online parameters (initted)
+                step % update_every   != 0 -> nothing
+                step <= update_after_step  -> copy the online parameters
+                else                  -> ema.lerp_(online, 1 - decay(step+1))
+      decay(s): e = max(s - update_after_step - 1, 0); 0 if e <= 0 else clamp(1 - (1 + e / inv_gamma) ** -power, min_value, beta)
+    with the package defaults inv_gamma = 1.0, power = 2/3, min_value = 0.0.
+    Only trainable parameters are averaged (the denoisers on this path have no buffers)."""
+
+    def __init__(self, optimizer: FusedAdamW, beta: float = 0.9999, update_after_step: int = 100, update_every: int = 10,
+                 inv_gamma: float = 1.0, power: float = 2.0 / 3.0, min_value: float = 0.0):
+        self.beta, self.update_after_step, self.update_every = beta, update_after_step, update_every
+        self.inv_gamma, self.power, self.min_value = inv_gamma, power, min_value
+        self.step = 0
+        self.initted = False
+        self.opt = optimizer
+        self.flat = [st.flat_p.clone() for st in optimizer.stores]
+        optimizer.ema = self
+
+    def get_current_decay(self, step: int | None = None) -> float:
+        s = self.step if step is None else step
+        epoch = max(s - self.update_after_step - 1, 0)
+        if epoch <= 0:
+            return 0.0
+        value = 1.0 - (1.0 + epoch / self.inv_gamma) ** (-self.power)
+        return min(max(value, self.min_value), self.beta)
+
+    def plan(self) -> tuple[str, float]:
+        """What the update following the current optimizer step does: ('skip' | 'copy' | 'lerp', decay)."""
+        step = self.step
+        if not self.initted:
+            return ("copy", 0.0)
+        if step % self.update_every != 0:
+            return ("skip", 0.0)
+        if step <= self.update_after_step:
+            return ("copy", 0.0)
+        return ("lerp", self.get_current_decay(step + 1))
+
+    def advance(self) -> None:
+        self.step += 1
+        self.initted = True
+
+    def update(self) -> None:
+        """Stand-alone update (when the optimizer step was not the fused one): same rule, separate launch."""
+        kind, decay = self.plan()
+        if kind != "skip":
+            for e, st in zip(self.flat, self.opt.stores):
+                ops.ema_lerp_(e, st.flat_p, decay)
+        self.advance()
+
+    def state_dict(self) -> dict[str, Tensor]:
+        """EMA weights under the model's parameter names order (list index -> tensor), fp32."""
+        out = {}
+        for gi, st in enumerate(self.opt.stores):
+            for i, (p, o) in enumerate(zip(st.params, st.offsets)):
+                out[f"{gi}.{i}"] = self.flat[gi][o : o + p.numel()].view(p.shape)
+        return out
+
+    def parameters_like(self, model: nn.Module) -> dict[str, Tensor]:
+        """EMA tensors keyed by `model`'s parameter names (what `ema_model.state_dict()` holds in the reference)."""
+        by_id = {}
+        for gi, st in enumerate(self.opt.stores):
+            for p, o in zip(st.params, st.offsets):
+                by_id[id(p)] = self.flat[gi][o : o + p.numel()].view(p.shape)
+        return {n: by_id[id(p)] for n, p in model.named_parameters() if id(p) in by_id}
 
 
 class GradReducer:
@@ -174,6 +312,7 @@ class GradReducer:
         self.pending = list(self.pending_init)
         self.launched = [False] * len(self.buckets)
         self.works = []
+        self.seen: set[int] = set()
         self.active = True
         K.set_grad_ready_hook(self._ready)
 
@@ -196,6 +335,15 @@ class GradReducer:
         bi = self.bucket_of.get(id(p))
         if bi is None:
             return
+        # `_ready` fires once per USE of a parameter; a parameter used twice in one forward (shared module, tied weight)
+        # would release its bucket before the second wgrad was enqueued. Count each parameter once and refuse reuse after
+        # its bucket is in flight (ranks would silently diverge otherwise).
+        if id(p) in self.seen:
+            if self.launched[bi]:
+                raise RuntimeError("GradReducer: a parameter received a second gradient after its bucket was all-reduced "
+                                   "(shared / tied weights are not supported by the overlapped reducer)")
+            return
+        self.seen.add(id(p))
         self.pending[bi] -= 1
         if self.pending[bi] == 0:
             self._launch(bi)
@@ -216,9 +364,13 @@ class GradReducer:
 
 
 def training_step(diffuser, optimizer: torch.optim.Optimizer, batch: dict[str, Any], p_classifier_free_guidance: float = 0.0,
-                  reducer: GradReducer | None = None, scheduler: Any | None = None) -> dict[str, Tensor]:
-    """One optimisation step with the reference's order of operations (base_trainer.py:138-153). Returns the loss
-    dict as DEVICE tensors: the reference's per-step `loss.item()` host sync is left to the caller."""
+                  reducer: GradReducer | None = None, scheduler: Any | None = None, per_batch_scheduler: bool = False,
+                  ema: EMA | None = None) -> dict[str, Tensor]:
+    """One optimisation step with the reference's order of operations (base_trainer.py:138-153): zero_grad -> draw t ->
+    set p -> compute_loss -> backward (+ bucketed all-reduce) -> optimizer.step -> scheduler.step if per_batch_scheduler ->
+    EMA update. An `EMA` attached to a `FusedAdamW` is advanced inside `optimizer.step()` (same kernel pass); any other
+    combination calls `ema.update()` here. Returns the loss dict as DEVICE tensors: the reference's per-step
+    `loss.item()` host sync is left to the caller."""
     optimizer.zero_grad()
     model_inputs = batch["model_inputs"]
     device = next(diffuser.denoiser.parameters()).device
@@ -232,6 +384,8 @@ def training_step(diffuser, optimizer: torch.optim.Optimizer, batch: dict[str, A
     if reducer is not None:
         reducer.finish()
     optimizer.step()
-    if scheduler is not None:
+    if scheduler is not None and per_batch_scheduler:
         scheduler.step()
+    if ema is not None and getattr(optimizer, "ema", None) is not ema:
+        ema.update()
     return {k: v.detach() for k, v in losses.items()}

@@ -223,10 +223,14 @@ int dlb_gaussian_step(const void* pred, int pred_dtype, const float* xt, const f
 int dlb_euler_maruyama_step(const float* x, const void* v, int v_dtype, const float* noise, const float* x_prev_in, float c,
                             float one_minus_t, float dt, float t_curr, float stdv, float* x_prev, float* mean,
                             float* x0_est, float* logprob, int64_t n, dlb_stream_t stream);
-/* torch.optim.AdamW step over a flat buffer (+ bf16 shadow, + optional EMA) (base_trainer.py:149-153) */
+/* torch.optim.AdamW step over a flat buffer (+ bf16 shadow, + optional EMA lerp ema = ema*decay + p*(1-decay))
+ * (base_trainer.py:149-153). Hyper-parameters are doubles (python floats); bias corrections are evaluated in double as
+ * torch does. chunk_active (nullable): one byte per 64 elements, 0 = skip (parameters whose .grad is None in torch). */
 int dlb_adamw_step(float* p, const float* g, float* m, float* v, void* shadow, float* ema, float ema_decay,
-                   int64_t n, float lr, float beta1, float beta2, float eps, float wd, int64_t step, float grad_scale,
-                   dlb_stream_t stream);
+                   const uint8_t* chunk_active, int64_t n, double lr, double beta1, double beta2, double eps, double wd,
+                   int64_t step, float grad_scale, dlb_stream_t stream);
+/* ema_pytorch EMA.update_moving_average over a flat buffer: ema.lerp_(p, 1 - decay) (base_trainer.py:152-153) */
+int dlb_ema_lerp(float* ema, const float* p, float decay, int64_t n, dlb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -47,10 +47,7 @@ def r(x: Tensor) -> Tensor:
 
 def linear(x: Tensor, w: Tensor, b: Tensor | None = None) -> Tensor:
     """nn.Linear under autocast: operands rounded to bf16, fp32 accumulate, bf16 result."""
-    y = r(x) @ r(w).t()
-    if b is not None:
-        y = y + r(b)
-    return r(y)
+    return r(F.linear(r(x), r(w), r(b) if b is not None else None))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -59,7 +56,7 @@ def linear(x: Tensor, w: Tensor, b: Tensor | None = None) -> Tensor:
 def timestep_embedding(t: Tensor, dim: int, max_period: int = 10000) -> Tensor:
     """networks/utils/nn.py:91-114"""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = t[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
@@ -78,7 +75,7 @@ def label_embed(sd: SD, y: Tensor, n_classes: int, p: float, drop_u: Tensor | No
     """nn.py:135-164: labels replaced by the extra class where rand < p"""
     if p > 0:
         assert drop_u is not None, "label dropout needs the uniform draw"
-        y = torch.where(drop_u < p, torch.full_like(y, n_classes), y)
+        y = torch.where(drop_u.to(y.device) < p, torch.full_like(y, n_classes), y)
     return sd["label_embed.embedding.weight"][y]
 
 
@@ -87,7 +84,7 @@ def rope_tables(pos_ids: Tensor, axes_dim: list[int], base: float) -> tuple[Tens
     cs, sn = [], []
     for i, ad in enumerate(axes_dim):
         pos = pos_ids[..., i].to(torch.float64)
-        freqs = 1.0 / (base ** (torch.arange(0, ad, 2, dtype=torch.float64) / ad))
+        freqs = 1.0 / (base ** (torch.arange(0, ad, 2, dtype=torch.float64, device=pos_ids.device) / ad))
         ang = pos[..., None] * freqs
         cs.append(ang.cos().float())
         sn.append(ang.sin().float())
@@ -129,13 +126,15 @@ def modulation(sd: SD, prefix: str, vec: Tensor, n: int) -> list[Tensor]:
 
 def rms_norm(x: Tensor, scale: Tensor) -> Tensor:
     """nn.py:427-431, 473-475"""
-    rr = torch.rsqrt(torch.mean(x * x, dim=-1, keepdim=True) + 1e-6)
-    return r(r(x * rr) * scale)
+    xf = x.float()  # RMSNorm.forward upcasts, casts back to the input dtype, then multiplies by the fp32 scale
+    rr = torch.rsqrt(torch.mean(xf * xf, dim=-1, keepdim=True) + 1e-6)
+    return r(r((xf * rr).to(x.dtype)) * scale)
 
 
 def apply_rope(x: Tensor, cos: Tensor, sin: Tensor) -> Tensor:
     """nn.py:331-353, 377-400. x [B,S,H,hd]; cos/sin [S,R/2] or [B,S,R/2] (cast to the activation dtype)."""
     R = cos.shape[-1] * 2
+    cos, sin = cos.to(x.dtype), sin.to(x.dtype)  # nn.py:377-378
     c = r(cos)[..., None, :] if cos.dim() == 3 else r(cos)[None, :, None, :]
     s = r(sin)[..., None, :] if sin.dim() == 3 else r(sin)[None, :, None, :]
     xr, xp = x[..., :R], x[..., R:]
@@ -146,9 +145,24 @@ def apply_rope(x: Tensor, cos: Tensor, sin: Tensor) -> Tensor:
     return torch.cat([rot, xp], -1)
 
 
+_fused_sdpa = False
+
+
+def set_fused_sdpa(on: bool) -> None:
+    """True: call F.scaled_dot_product_attention exactly as the reference does (mmdit.py:92-98) instead of the explicit
+    softmax(QK^T)V restatement — used by bench.py's reference-GPU arm so that the timed attention is the library kernel
+    the reference would run (flash / cuDNN / math backend chosen by torch)."""
+    global _fused_sdpa
+    _fused_sdpa = bool(on)
+
+
 def sdpa(q: Tensor, k: Tensor, v: Tensor, key_mask: Tensor | None) -> Tensor:
     """F.scaled_dot_product_attention(scale=hd^-0.5, attn_mask=key padding) mmdit.py:92-98. q,k,v [B,S,H,hd]"""
     hd = q.shape[-1]
+    if _fused_sdpa:
+        mask = key_mask[:, None, None, :].bool() if key_mask is not None else None
+        o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), attn_mask=mask, scale=hd**-0.5)
+        return o.transpose(1, 2)
     s = torch.einsum("bqhd,bkhd->bhqk", q, k) * hd**-0.5
     if key_mask is not None:
         s = s.masked_fill(~key_mask[:, None, None, :].bool(), float("-inf"))
@@ -159,8 +173,8 @@ def sdpa(q: Tensor, k: Tensor, v: Tensor, key_mask: Tensor | None) -> Tensor:
 def qkv_heads(sd: SD, wkey: str, nkey: str, x: Tensor, H: int) -> tuple[Tensor, Tensor, Tensor]:
     B, S, d = x.shape
     q, k, v = linear(x, sd[f"{wkey}.weight"]).chunk(3, dim=-1)
-    q = rms_norm(q, sd[f"{nkey}.query_norm.scale"])
-    k = rms_norm(k, sd[f"{nkey}.key_norm.scale"])
+    q = rms_norm(q, sd[f"{nkey}.query_norm.scale"]).to(v.dtype)  # QKNorm.forward: q.to(v), k.to(v) (nn.py:475)
+    k = rms_norm(k, sd[f"{nkey}.key_norm.scale"]).to(v.dtype)
     return q.view(B, S, H, -1), k.view(B, S, H, -1), v.view(B, S, H, -1)
 
 
@@ -181,7 +195,7 @@ def mmdit_attention(sd: SD, prefix: str, x: Tensor, ctx: Tensor, cos: Tensor, si
     q, k, v = torch.cat([qc, qi], 1), torch.cat([kc, ki], 1), torch.cat([vc, vi], 1)
     mask = None
     if ctx_mask is not None:
-        mask = torch.cat([ctx_mask.bool(), torch.ones(B, N, dtype=torch.bool)], 1)
+        mask = torch.cat([ctx_mask.bool(), torch.ones(B, N, dtype=torch.bool, device=ctx_mask.device)], 1)
     o = sdpa(apply_rope(q, cos, sin), apply_rope(k, cos, sin), v, mask).reshape(B, L + N, d)
     return linear(o[:, L:], sd[f"{prefix}.input_proj_out.weight"]), linear(o[:, :L], sd[f"{prefix}.context_proj_out.weight"])
 
@@ -228,7 +242,7 @@ def single_stream_block(sd: SD, p: str, x: Tensor, cond: Tensor, ctx: Tensor, co
     z = torch.cat([ctx, x], 1)
     mask = None
     if ctx_mask is not None:
-        mask = torch.cat([ctx_mask.bool(), torch.ones(x.shape[0], x.shape[1], dtype=torch.bool)], 1)
+        mask = torch.cat([ctx_mask.bool(), torch.ones(x.shape[0], x.shape[1], dtype=torch.bool, device=x.device)], 1)
     a, b, g = modulation(sd, f"{p}.modulation", cond, 3)
     h = modulate(layer_norm(z, sd[f"{p}.norm.weight"], sd[f"{p}.norm.bias"], 1e-5), a, b)
     branch = r(dit_attention(sd, f"{p}.attention", h, cos, sin, H, mask) + swiglu_mlp(sd, f"{p}.mlp", h))
@@ -286,10 +300,10 @@ def drop_context(context: dict[str, Tensor], null_emb: Tensor, null_mask: Tensor
     """PrecomputedEmbedder.drop_conditions embedders/precomputed.py:20-39"""
     emb, mask = context["embeddings"], context["attn_mask"]
     if drop_u is None:
-        drop_u = torch.ones(emb.shape[0])  # rand < 0 never true; p == 0 path
-    dm = drop_u < p
-    emb = torch.where(dm[:, None, None], null_emb[None].expand_as(emb), emb)
-    mask = torch.where(dm[:, None], null_mask[None].expand_as(mask), mask)
+        drop_u = torch.ones(emb.shape[0], device=emb.device)  # rand < 0 never true; p == 0 path
+    dm = drop_u.to(emb.device) < p
+    emb = torch.where(dm[:, None, None], null_emb.to(emb.device)[None].expand_as(emb), emb)
+    mask = torch.where(dm[:, None], null_mask.to(mask.device)[None].expand_as(mask), mask)
     return emb, mask
 
 
@@ -309,11 +323,11 @@ def mmdit_forward(sd: SD, cfg: dict[str, Any], x: Tensor, t: Tensor, y: Tensor |
     if context is None:
         if "label_embed.embedding.weight" in sd:
             emb = emb + label_embed(sd, y, cfg["n_classes"], p, draws.get("label"))
-        cos, sin = rope_tables(pos_ids_2d(hp, wp), cfg["rope_axes_dim"], cfg.get("rope_base", 10000))
+        cos, sin = rope_tables(pos_ids_2d(hp, wp).to(x.device), cfg["rope_axes_dim"], cfg.get("rope_base", 10000))
     else:
         ce, ctx_mask = drop_context(context, cfg["null_embedding"], cfg["null_mask"], p, draws.get("context"))
         ctx = linear(ce, sd["context_embed.weight"])
-        cos, sin = rope_tables(pos_ids_joint(ctx.shape[1], hp, wp), cfg["rope_axes_dim"], cfg.get("rope_base", 10000))
+        cos, sin = rope_tables(pos_ids_joint(ctx.shape[1], hp, wp).to(x.device), cfg["rope_axes_dim"], cfg.get("rope_base", 10000))
     for i in range(n_blocks(sd, "layers")):
         tok, ctx = run_block(sd, f"layers.{i}", tok, emb, ctx, cos, sin, H, ctx_mask)
         if capture is not None:
@@ -337,11 +351,10 @@ def sprint_select(scores: Tensor, k: int) -> Tensor:
 def sprint_restore(xk: Tensor, kept: Tensor, S: int, mask_token: Tensor, path_drop: Tensor | None) -> Tensor:
     """sprint.py:371-387"""
     B, k, d = xk.shape
-    full = r(mask_token).reshape(1, 1, d).expand(B, S, d).clone()
-    for b in range(B):
-        full[b, kept[b]] = xk[b]
-        if path_drop is not None and bool(path_drop[b]):
-            full[b] = r(mask_token).reshape(1, d)
+    full = r(mask_token).to(xk.dtype).reshape(1, 1, d).expand(B, S, d).clone()
+    full = full.scatter(1, kept.unsqueeze(-1).expand(-1, -1, d), xk)
+    if path_drop is not None:
+        full = torch.where(path_drop.to(xk.device).bool()[:, None, None], r(mask_token).to(xk.dtype).reshape(1, 1, d).expand(B, S, d), full)
     return full
 
 
@@ -363,7 +376,7 @@ def sprint_forward(sd: SD, cfg: dict[str, Any], x: Tensor, t: Tensor, y: Tensor 
         ctx = linear(ce, sd["context_embed.weight"])
         L = ctx.shape[1]
         pos = pos_ids_joint(L, hp, wp)
-    cos, sin = rope_tables(pos, cfg["rope_axes_dim"], cfg.get("rope_base", 10000))
+    cos, sin = rope_tables(pos.to(x.device), cfg["rope_axes_dim"], cfg.get("rope_base", 10000))
     for i in range(n_blocks(sd, "layers")):
         tok, ctx = run_block(sd, f"layers.{i}", tok, emb, ctx, cos, sin, H, ctx_mask)
         if capture is not None:
@@ -371,9 +384,9 @@ def sprint_forward(sd: SD, cfg: dict[str, Any], x: Tensor, t: Tensor, y: Tensor 
     enc_ctx = ctx
     if training:
         k = max(1, int(S * (1.0 - float(cfg["drop_rate"]))))
-        kept = sprint_select(draws["scores"], k)
+        kept = sprint_select(draws["scores"].cpu(), k).to(x.device)
     else:
-        kept = torch.arange(S).expand(B, S)
+        kept = torch.arange(S, device=x.device).expand(B, S)
     if capture is not None:
         capture["kept_indices"] = kept
     xk = torch.gather(tok, 1, kept.unsqueeze(-1).expand(-1, -1, d))
@@ -383,7 +396,7 @@ def sprint_forward(sd: SD, cfg: dict[str, Any], x: Tensor, t: Tensor, y: Tensor 
     if p < 1:
         for i in range(n_blocks(sd, "deep_layers")):
             xk, ctx = run_block(sd, f"deep_layers.{i}", xk, emb, ctx, cos_b, sin_b, H, ctx_mask)
-        path = (draws["path"] < p) if p > 0 else None
+        path = (draws["path"].cpu() < p) if p > 0 else None
         restored = sprint_restore(xk, kept, S, sd["mask_token"], path)
     else:
         restored = r(sd["mask_token"]).expand(B, S, d).clone()
@@ -407,13 +420,13 @@ def ddt_forward(sd: SD, cfg: dict[str, Any], x: Tensor, t: Tensor, y: Tensor | N
     if context is None:
         if "label_embed.embedding.weight" in sd:
             emb = emb + label_embed(sd, y, cfg["n_classes"], p, draws.get("label"))
-        cos, sin = rope_tables(pos_ids_2d(hp, wp), cfg["rope_axes_dim"], cfg.get("rope_base", 10000))
+        cos, sin = rope_tables(pos_ids_2d(hp, wp).to(x.device), cfg["rope_axes_dim"], cfg.get("rope_base", 10000))
         cos_d, sin_d = cos, sin
     else:
         ce, ctx_mask = drop_context(context, cfg["null_embedding"], cfg["null_mask"], p, draws.get("context"))
         ctx = linear(ce, sd["context_embed.weight"])
         L = ctx.shape[1]
-        cos, sin = rope_tables(pos_ids_joint(L, hp, wp), cfg["rope_axes_dim"], cfg.get("rope_base", 10000))
+        cos, sin = rope_tables(pos_ids_joint(L, hp, wp).to(x.device), cfg["rope_axes_dim"], cfg.get("rope_base", 10000))
         cos_d, sin_d = cos[L:], sin[L:]  # decoder: image positions (0,h,w) only (ddt.py:425-449)
     for i in range(n_blocks(sd, "layers")):
         tok, ctx = run_block(sd, f"layers.{i}", tok, emb, ctx, cos, sin, H, ctx_mask)
@@ -462,7 +475,7 @@ def repa_loss(sd_repa: SD, feats: Tensor, dst: Tensor, coeff: float) -> Tensor:
     """RepaLoss.forward training/losses/repa.py:176-186 (projector proj.{0,2,4})"""
     h = r(F.silu(linear(feats, sd_repa["proj.0.weight"], sd_repa["proj.0.bias"])))
     h = r(F.silu(linear(h, sd_repa["proj.2.weight"], sd_repa["proj.2.bias"])))
-    s = linear(h, sd_repa["proj.4.weight"], sd_repa["proj.4.bias"])
+    s = linear(h, sd_repa["proj.4.weight"], sd_repa["proj.4.bias"]).float()  # F.cosine_similarity runs in fp32 under autocast
     dot = (s * dst).sum(-1)
     ns = s.norm(dim=-1).clamp_min(1e-8)
     nz = dst.norm(dim=-1).clamp_min(1e-8)
@@ -480,12 +493,22 @@ def cfg_combine(v: Tensor, v_dropped: Tensor, g: float) -> Tensor:
 
 
 def flow_denoise(velocity: Callable[[Tensor, float, float], Tensor], x: Tensor, n_steps: int, shift: float | None,
-                 guidance_scale: float = 0.0) -> Tensor:
-    """Flow.denoise flow.py:484-499. velocity(x, t, p) -> model(x, t, p)['x'] (v-prediction)."""
+                 guidance_scale: float = 0.0, method: str = "euler") -> Tensor:
+    """Flow.denoise flow.py:484-499. velocity(x, t, p) -> model(x, t, p)['x'] (v-prediction).
+    method 'heun' has no reference counterpart: the textbook trapezoidal predictor-corrector built from two
+    reference-style velocity evaluations (each with the reference's CFG combine), last step (t_prev = 0) plain Euler."""
+
+    def guided(xx: Tensor, t: float) -> Tensor:
+        v = velocity(xx, t, 0.0)
+        if guidance_scale > 0:
+            v = cfg_combine(v, velocity(xx, t, 1.0), guidance_scale)
+        return v
+
     ts = flow_timesteps(n_steps, shift)
     for t_curr, t_prev in zip(ts[:-1], ts[1:]):
-        v = velocity(x, t_curr, 0.0)
-        if guidance_scale > 0:
-            v = cfg_combine(v, velocity(x, t_curr, 1.0), guidance_scale)
+        v = guided(x, t_curr)
+        if method == "heun" and t_prev > 0:
+            x_pred, _ = euler_step(x, v, t_curr, t_prev)
+            v = 0.5 * (v + guided(x_pred, t_prev))
         x, _ = euler_step(x, v, t_curr, t_prev)
     return x

@@ -68,6 +68,8 @@ def capture_blocks(model, names):
 
 def run_case(name: str, build, kwargs: dict, B: int, C: int, HW: int, mm: bool, train_mode: bool, p: float, seed: int,
              repa: dict | None = None, euler: dict | None = None):
+    if _ONLY and name not in _ONLY:
+        return
     ref = import_reference()
     from diffulab.diffuse.modelizations.flow import Flow
 
@@ -168,6 +170,9 @@ def run_case(name: str, build, kwargs: dict, B: int, C: int, HW: int, mm: bool, 
     print(name, {k: float(v) for k, v in fixture["losses"].items()}, f"{os.path.getsize(os.path.join(OUT, name + '.pt')) / 1e6:.2f} MB")
 
 
+_ONLY: set[str] = set(sys.argv[1:])  # optional fixture-name filter: python oracle/make_golden.py sprint_dit_cfg
+
+
 def main():
     import_reference()
     from diffulab.networks.denoisers.ddt import DDT
@@ -202,6 +207,13 @@ def main():
                                                   deep_layers_depth=2, decoder_depth=1, n_classes=10, classifier_free=True,
                                                   drop_rate=0.5),
              B=3, C=4, HW=8, mm=False, train_mode=True, p=0.0, seed=5)
+    # label-conditioned SprintDiT sampled with classifier-free guidance: the p = 1 pass skips the deep layers (path-drop
+    # guidance, sprint.py:474-475), which a batched [y; null] evaluation must NOT be substituted for
+    run_case("sprint_dit_cfg", SprintDiT, dict(simple_dit=True, input_channels=4, output_channels=4, inner_dim=64,
+                                                embedding_dim=64, num_heads=2, mlp_ratio=4, patch_size=2, encoder_depth=1,
+                                                deep_layers_depth=2, decoder_depth=1, n_classes=10, classifier_free=True,
+                                                drop_rate=0.5),
+             B=3, C=4, HW=8, mm=False, train_mode=True, p=0.3, seed=8, euler=dict(n_steps=3, guidance=4.0, shift=6.93))
     ddt_kw = dict(simple_ddt=False, input_channels=8, output_channels=8, inner_dim=64, num_heads=2, mlp_ratio=4, patch_size=1,
                   encoder_depth=3, n_single_stream_blocks=1, decoder_depth=2, rope_axes_dim=[8, 12, 12], rope_base=1000,
                   classifier_free=True)

@@ -2,6 +2,7 @@
 import os
 
 import pytest
+import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -49,3 +50,19 @@ def test_reference_yaml_drives_the_drop_in_classes():
     assert cfg["dataloader"]["batch_size"] == 32 and cfg["diffuser"]["n_steps"] == 100
     model = instantiate(cfg["model"])
     assert isinstance(model, dl.MMDiT) and model.simple_dit
+
+
+def test_bench_workload_shapes():
+    """The synthetic workloads have the shapes SURVEY.md 8(d) specifies (no GPU work: host generation only)."""
+    from diffulab_b200.config import load_config
+    from diffulab_b200.synthetic import Workload, config_path
+
+    for name, shape, L in (("cifar10", (3, 32, 32), 0), ("imagenet_repa", (4, 32, 32), 0), ("txt_to_img", (128, 16, 16), 128), ("sprint", (128, 16, 16), 128)):
+        cfg = load_config(config_path(name))
+        wl = Workload(cfg, None, object() if "repa" in cfg else None, None)
+        b = wl.batch(5, torch.Generator().manual_seed(0))
+        assert tuple(b["x"].shape) == (5, *shape)
+        if L:
+            assert tuple(b["context"]["embeddings"].shape) == (5, L, 2048) and b["context"]["attn_mask"].dtype == torch.bool
+            assert int(b["context"]["attn_mask"].sum(1).min()) >= 8
+    assert abs(Workload(load_config(config_path("imagenet_repa")), None, None, None).flops_per_image(False) / 1e9 - 313.33) < 0.01

@@ -80,6 +80,10 @@ def test_cfg_batching_is_only_used_for_label_conditioned_models():
         label_embed = object()
         classifier_free = True
         n_classes = 10
+        cfg_batchable = True
+
+    class PathDrop(M):  # SprintDiT: p = 1 also skips the deep layers, so [y; null] batching would change the result
+        cfg_batchable = False
 
     class NoCF(M):
         classifier_free = False
@@ -95,6 +99,10 @@ def test_cfg_batching_is_only_used_for_label_conditioned_models():
     assert not f._can_batch_cfg(M(), {"x": None, "y": y, "x_context": torch.zeros(1)})
     assert not f._can_batch_cfg(NoCF(), {"x": None, "y": y})
     assert not f._can_batch_cfg(Ctx(), {"x": None, "y": y})
+    assert not f._can_batch_cfg(PathDrop(), {"x": None, "y": y})
+    import diffulab_b200 as dl
+
+    assert dl.SprintDiT.cfg_batchable is False and dl.MMDiT.cfg_batchable is True and dl.DDT.cfg_batchable is True
     f.batch_cfg = False
     assert not f._can_batch_cfg(M(), {"x": None, "y": y})
 
