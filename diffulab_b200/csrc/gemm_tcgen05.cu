@@ -12,6 +12,8 @@
 #include "ptx.cuh"
 #include <cudaTypedefs.h>
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 namespace {
 
@@ -632,9 +634,32 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   return fn;
 }
 
-// 2-D row-major tensor [outer][inner] with `ld` elements between rows.
+// 2-D row-major tensor [outer][inner] with `ld` elements between rows. Descriptors are cached per
+// (dtype, pointer, extents, pitch, box): the training loop and the sampling loop reuse their buffers (caching allocator),
+// so after the first step a GEMM call costs three hash look-ups instead of three driver encodes (~1500 per train step).
+struct TmapKey {
+  const void* ptr; uint64_t inner, outer, ld; uint32_t box_inner, box_outer; int dt;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner && box_outer == o.box_outer && dt == o.dt;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    for (uint64_t v : {k.inner, k.outer, k.ld, (uint64_t)k.box_inner << 32 | k.box_outer, (uint64_t)k.dt}) h = (h ^ v) * 0x100000001B3ull + (h >> 29);
+    return (size_t)h;
+  }
+};
 int encode2d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void* ptr, uint64_t inner, uint64_t outer,
              uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  static std::mutex mu;
+  const TmapKey key{ptr, inner, outer, ld, box_inner, box_outer, (int)dt};
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *m = it->second; return DLB_OK; }
+  }
   auto enc = get_encode();
   DLB_REQUIRE(enc != nullptr, DLB_ERR_DRIVER, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {inner, outer};
@@ -646,6 +671,9 @@ int encode2d(CUtensorMap* m, CUtensorMapDataType dt, int elem_bytes, const void*
   DLB_REQUIRE(r == CUDA_SUCCESS, DLB_ERR_DRIVER,
               "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu ld=%llu box=%ux%u ptr=%p", (int)r,
               (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer, ptr);
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache.size() > 16384) cache.clear();
+  cache.emplace(key, *m);
   return DLB_OK;
 }
 

@@ -340,6 +340,8 @@ def sprint_select(scores: Tensor, k: int) -> Tensor:
     """sprint.py:343-346: indices of the k largest scores, ascending. Plain loops, tie -> larger index
     (the build's documented tie rule; exactness vs torch.topk is defined on tie-free draws)."""
     B, S = scores.shape
+    if scores.is_cuda:  # the reference's own device expression (bench timing arm only; tie order is implementation-defined)
+        return torch.topk(scores, k=k, dim=1, largest=True, sorted=False).indices.sort(dim=1).values
     out = torch.empty(B, k, dtype=torch.long)
     for b in range(B):
         row = scores[b].tolist()
@@ -384,7 +386,8 @@ def sprint_forward(sd: SD, cfg: dict[str, Any], x: Tensor, t: Tensor, y: Tensor 
     enc_ctx = ctx
     if training:
         k = max(1, int(S * (1.0 - float(cfg["drop_rate"]))))
-        kept = sprint_select(draws["scores"].cpu(), k).to(x.device)
+        sc = draws["scores"] if cfg.get("device_select") else draws["scores"].cpu()  # parity: documented tie rule on the host
+        kept = sprint_select(sc, k).to(x.device)
     else:
         kept = torch.arange(S, device=x.device).expand(B, S)
     if capture is not None:
