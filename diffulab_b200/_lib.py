@@ -53,7 +53,6 @@ _SIGNATURES: dict[str, list] = {
     "dlb_attn_bwd_tc": [p, i32, p, p, p, i32, i32, i32, i32, f32, p],
     "dlb_cast_f32_bf16": [p, p, i64, i64, i64, p],
     "dlb_cast_bf16_f32": [p, p, i64, p],
-    "dlb_umma_probe": [p, p, p, i32, i32, i32, i32, i32, p],
     "dlb_attn_set_trace": [p],
     "dlb_gemm2_bf16": [p, p, p, p, i64, i64, i64, i64, i64, i64, i32, i32, i32, i32, i32, p],
     # dY, W2, H, dH, M, F, D, lddy, ldw2, ldh, lddh, stream
@@ -64,8 +63,6 @@ _SIGNATURES: dict[str, list] = {
     "dlb_euler_maruyama_step": [p, p, i32, p, p, f32, f32, f32, f32, f32, p, p, p, p, i64, p],
     # pred, pred_dtype, xt, noise, table, t, sampler, mean_type, clamp, eta, B, per_sample, x_prev, x0, mean, logprob, stream
     "dlb_gaussian_step": [p, i32, p, p, p, p, i32, i32, i32, f32, i64, i64, p, p, p, p, p],
-    # base, rows, ld, H, hd, grid, tiles_per_cta, dump, stream
-    "dlb_tma_gather_probe": [p, i64, i64, i32, i32, i32, i32, p, p],
     "dlb_add_bf16": [p, p, p, i64, p],
     "dlb_bias_silu_fwd": [p, p, p, i64, i64, i32, p],
     "dlb_bias_silu_bwd": [p, p, p, p, p, i64, i64, i32, p],
@@ -94,6 +91,18 @@ _SIGNATURES: dict[str, list] = {
     "dlb_adamw_step": [p, p, p, p, p, p, f32, p, i64, f64, f64, f64, f64, f64, i64, f32, p],
     # ema, p, decay, n, stream
     "dlb_ema_lerp": [p, p, f32, i64, p],
+}
+
+
+# development probes (csrc/probes/, libdiffulab_b200_probes.so; include/diffulab_b200_probes.h): tests / scripts only
+_PROBE_SIGNATURES: dict[str, list] = {
+    "dlb_umma_probe": [p, p, p, i32, i32, i32, i32, i32, p],
+    # base, rows, ld, H, hd, grid, tiles_per_cta, dump, stream
+    "dlb_tma_gather_probe": [p, i64, i64, i32, i32, i32, i32, p, p],
+    # X, Y, P, D1, D2, rows, ld, H, hd, h, xrow, yrow, dump, stream
+    "dlb_attn_sw_probe": [p, p, p, p, p, i64, i64, i32, i32, i32, i32, i32, p, p],
+    # X, rows, ld, H, hd, grid, tiles_per_cta, stream
+    "dlb_attn_sw_stream_probe": [p, i64, i64, i32, i32, i32, i32, p],
 }
 
 
@@ -133,6 +142,32 @@ def load() -> C.CDLL:
         fn.restype = _RESTYPES.get(name, C.c_int)
     _lib = lib
     return lib
+
+
+_probes: C.CDLL | None = None
+
+
+def load_probes() -> C.CDLL:
+    """The separate development-probe library (hardware layout probes used by tests/ and scripts/ only)."""
+    global _probes
+    if _probes is None:
+        path = _HERE / "libdiffulab_b200_probes.so"
+        if not path.exists():
+            raise RuntimeError(f"{path} is missing: build it with `python -m diffulab_b200.build`")
+        lib = C.CDLL(str(path))
+        for name, argtypes in _PROBE_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        lib.dlb_last_error.restype = C.c_char_p
+        _probes = lib
+    return _probes
+
+
+def check_probe(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_probes().dlb_last_error()
+        raise DlbError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
 
 
 class DlbError(RuntimeError):

@@ -2,6 +2,8 @@
 
 `python -m diffulab_b200.build` compiles every `csrc/*.cu` to an object (in parallel, incremental on
 mtime) and links one C-ABI shared library next to this file. nvcc cross-compiles without a GPU.
+The hardware-layout probes under `csrc/probes/` (used only by tests/ and scripts/) go into a SEPARATE
+library, libdiffulab_b200_probes.so, so that the product ABI (include/diffulab_b200.h) carries no development aids.
 """
 
 from __future__ import annotations
@@ -17,6 +19,8 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 OBJ = HERE / "csrc" / "build"
 LIB = HERE / "libdiffulab_b200.so"
+PROBES = HERE / "csrc" / "probes"
+PROBES_LIB = HERE / "libdiffulab_b200_probes.so"
 
 NVCC_FLAGS = [
     "-gencode",
@@ -44,7 +48,7 @@ def _newest_header_mtime() -> float:
 
 
 def _compile(src: Path, force: bool, verbose: bool) -> Path:
-    obj = OBJ / (src.stem + ".o")
+    obj = OBJ / (("probe_" if src.parent == PROBES else "") + src.stem + ".o")
     stale = force or not obj.exists() or obj.stat().st_mtime < max(src.stat().st_mtime, _newest_header_mtime())
     if stale:
         cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
@@ -65,11 +69,18 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError(f"no CUDA sources under {CSRC}")
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(lambda s: _compile(s, force, verbose), srcs))
-    if force or not LIB.exists() or LIB.stat().st_mtime < max(o.stat().st_mtime for o in objs):
-        cmd = [_nvcc(), "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    psrcs = sorted(PROBES.glob("*.cu"))
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        pobjs = list(ex.map(lambda s: _compile(s, force, verbose), psrcs))
+    common = [o for o in objs if o.stem == "common"]
+    for lib, members in ((LIB, objs), (PROBES_LIB, pobjs + common)):
+        if not members:
+            continue
+        if force or not lib.exists() or lib.stat().st_mtime < max(o.stat().st_mtime for o in members):
+            cmd = [_nvcc(), "-shared", "-o", str(lib), *map(str, members), "-gencode", "arch=compute_100a,code=sm_100a"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB
 
 

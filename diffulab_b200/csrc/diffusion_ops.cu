@@ -324,11 +324,12 @@ __global__ void euler_maruyama_kernel(const float* __restrict__ x, const TV* __r
 
 // torch.optim.AdamW (no amsgrad, no maximize): p *= 1 - lr*wd; m,v update; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).
 // Also refreshes the bf16 shadow copy used by the GEMMs and (optionally) the EMA copy.
-__device__ __forceinline__ void adamw_one(float& pi, float gi, float& mi, float& vi, float decay, float beta1, float beta2,
-                                          float eps, float step_size, float bc2_sqrt) {
+// omb1 / omb2 = 1 - beta evaluated in DOUBLE on the host (1.f - 0.999f is off by 1.3e-5 relative, visible in exp_avg_sq)
+__device__ __forceinline__ void adamw_one(float& pi, float gi, float& mi, float& vi, float decay, float beta1, float beta2, float omb1,
+                                          float omb2, float eps, float step_size, float bc2_sqrt) {
   pi *= decay;  // decoupled weight decay: p *= 1 - lr * wd
-  mi = beta1 * mi + (1.f - beta1) * gi;
-  vi = beta2 * vi + (1.f - beta2) * gi * gi;
+  mi = beta1 * mi + omb1 * gi;
+  vi = beta2 * vi + omb2 * gi * gi;
   pi -= step_size * (mi / (sqrtf(vi) / bc2_sqrt + eps));
 }
 // 4 parameters per thread per iteration (128-bit loads / stores; n4 = n / 4), scalar tail handled by the last block.
@@ -337,7 +338,7 @@ __device__ __forceinline__ void adamw_one(float& pi, float gi, float& mi, float&
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              bf16* __restrict__ shadow, float* __restrict__ ema, float ema_decay, const uint8_t* __restrict__ chunk_active,
-             int64_t n, float decay, float beta1, float beta2, float eps, float step_size, float bc2_sqrt, float grad_scale) {
+             int64_t n, float decay, float beta1, float beta2, float omb1, float omb2, float eps, float step_size, float bc2_sqrt, float grad_scale) {
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -346,10 +347,10 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     const float4 gv = reinterpret_cast<const float4*>(g)[i];
     float4 mv = reinterpret_cast<float4*>(m)[i];
     float4 vv = reinterpret_cast<float4*>(v)[i];
-    adamw_one(pv.x, gv.x * grad_scale, mv.x, vv.x, decay, beta1, beta2, eps, step_size, bc2_sqrt);
-    adamw_one(pv.y, gv.y * grad_scale, mv.y, vv.y, decay, beta1, beta2, eps, step_size, bc2_sqrt);
-    adamw_one(pv.z, gv.z * grad_scale, mv.z, vv.z, decay, beta1, beta2, eps, step_size, bc2_sqrt);
-    adamw_one(pv.w, gv.w * grad_scale, mv.w, vv.w, decay, beta1, beta2, eps, step_size, bc2_sqrt);
+    adamw_one(pv.x, gv.x * grad_scale, mv.x, vv.x, decay, beta1, beta2, omb1, omb2, eps, step_size, bc2_sqrt);
+    adamw_one(pv.y, gv.y * grad_scale, mv.y, vv.y, decay, beta1, beta2, omb1, omb2, eps, step_size, bc2_sqrt);
+    adamw_one(pv.z, gv.z * grad_scale, mv.z, vv.z, decay, beta1, beta2, omb1, omb2, eps, step_size, bc2_sqrt);
+    adamw_one(pv.w, gv.w * grad_scale, mv.w, vv.w, decay, beta1, beta2, omb1, omb2, eps, step_size, bc2_sqrt);
     reinterpret_cast<float4*>(p)[i] = pv;
     reinterpret_cast<float4*>(m)[i] = mv;
     reinterpret_cast<float4*>(v)[i] = vv;
@@ -372,7 +373,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
     for (int64_t i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) {
       if (chunk_active != nullptr && chunk_active[i >> 6] == 0) continue;
       float pi = p[i], mi = m[i], vi = v[i];
-      adamw_one(pi, g[i] * grad_scale, mi, vi, decay, beta1, beta2, eps, step_size, bc2_sqrt);
+      adamw_one(pi, g[i] * grad_scale, mi, vi, decay, beta1, beta2, omb1, omb2, eps, step_size, bc2_sqrt);
       p[i] = pi; m[i] = mi; v[i] = vi;
       if (shadow) shadow[i] = __float2bfloat16_rn(pi);
       if (ema) ema[i] = ema[i] * ema_decay + pi * (1.f - ema_decay);
@@ -538,7 +539,7 @@ DLB_EXPORT int dlb_adamw_step(float* p, const float* g, float* m, float* v, void
                   ((uintptr_t)shadow % 8) == 0 && ((uintptr_t)ema % 16) == 0,
               DLB_ERR_ALIGN, "adamw_step: buffers must be 16-byte aligned");
   adamw_kernel<<<grid_for((n + 3) / 4), 256, 0, stream>>>(p, g, m, v, (bf16*)shadow, ema, ema_decay, chunk_active, n, (float)(1.0 - lr * wd),
-                                                          (float)beta1, (float)beta2, (float)eps, (float)(lr / bc1), (float)bc2_sqrt, grad_scale);
+                                                          (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, (float)(lr / bc1), (float)bc2_sqrt, grad_scale);
   dlb_count_launch();
   return dlb_check_launch("adamw_step");
 }

@@ -1,8 +1,8 @@
 // Development probe: can a 4-D tensor map {8 elements, rows, 16-byte chunks of one head, heads} drop a [64 rows x hd]
 // head slice of a packed [rows, ld] bf16 activation into shared memory directly in the core-matrix layout the attention
 // kernels use (chunk c, row r at c*1024 + r*16), and how fast does TMA stream such 16-byte-inner boxes?
-#include "common.cuh"
-#include "ptx.cuh"
+#include "../common.cuh"
+#include "../ptx.cuh"
 #include <cudaTypedefs.h>
 
 namespace {

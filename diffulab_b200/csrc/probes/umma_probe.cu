@@ -2,8 +2,8 @@
 // by the threads themselves into NON-swizzled canonical UMMA layouts (8x8 "core matrices" of 128 bytes), for
 // K-major or MN-major A/B. Used by tests/test_umma_probe_gpu.py to pin the LBO/SBO descriptor semantics that the
 // tcgen05 attention kernels rely on (their operands are produced by threads, not by TMA).
-#include "common.cuh"
-#include "ptx.cuh"
+#include "../common.cuh"
+#include "../ptx.cuh"
 
 namespace {
 typedef __nv_bfloat16 bf16;

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace ptx {
 

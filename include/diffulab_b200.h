@@ -147,15 +147,6 @@ int dlb_attn_bwd_tc(const dlb_attn_seg* segs, int nseg, const float* lse, float*
  * kernel (slots 0..63 forward, 64..127 dq, 128..191 dkv); NULL switches tracing off (the default) */
 int dlb_attn_set_trace(long long* dev_buf);
 
-/* development probe: stream [64 rows x hd] head slices of a packed bf16 [rows, ld] activation into shared memory with a
- * 4-D tensor map whose box lands in the attention kernels' core-matrix layout; dump (nullable) = CTA 0's first tile */
-int dlb_tma_gather_probe(const void* base, int64_t rows, int64_t ld, int H, int hd, int grid, int tiles_per_cta,
-                         void* dump, dlb_stream_t stream);
-
-/* development probe: D[128,N] = A*B^T from thread-staged non-swizzled UMMA operands (pins LBO/SBO semantics) */
-int dlb_umma_probe(const void* A, const void* B, float* D, int N, int K, int a_mn, int b_mn, int swap_lbo_sbo,
-                   dlb_stream_t stream);
-
 /* ---- glue ------------------------------------------------------------------------------------------------ */
 int dlb_cast_f32_bf16(const float* in, void* out, int64_t rows, int64_t cols, int64_t ld_out, dlb_stream_t stream);
 int dlb_cast_bf16_f32(const void* in, float* out, int64_t n, dlb_stream_t stream);

@@ -6,7 +6,7 @@ import torch
 sys.path.insert(0, ".")
 from diffulab_b200 import _lib  # noqa: E402
 
-lib = _lib.load()
+lib = _lib.load_probes()
 B, S, H, hd = 128, 256, 16, 72
 rows, ld = B * S, 3 * H * hd
 x = torch.randn(rows, ld, device="cuda").bfloat16()

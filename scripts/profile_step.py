@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """One DiT-XL/2 (+REPA) train step at the bench geometry (per-GPU batch 128, N 256, d 1152) with a reduced DEPTH, for ncu:
 every kernel of the real step appears with its real shape, the capture stays short. The step to profile is wrapped in the NVTX
-range `profiled_step` (two warm-up steps run before it):
+step is bracketed by cudaProfilerStart/Stop (two warm-up steps run before it; NVTX ranges are per thread and would miss the
+backward kernels, which the autograd engine launches from its own thread):
 
-    ncu --nvtx --nvtx-include "profiled_step/" --metrics <...> -o gpurun_out/step_light python scripts/profile_step.py
-    ncu --nvtx --nvtx-include "profiled_step/" --set full --import-source on -k regex:'attn|ln_mod|qknorm|gate_res' ...
+    ncu --profile-from-start off --metrics <...> --csv --log-file gpurun_out/step_light.csv python scripts/profile_step.py
+    ncu --profile-from-start off --set full --import-source on -k regex:'attn|ln_mod|qknorm|gate_res' ...
 
 --config picks another BASELINE config (cifar10 | txt_to_img | sprint); --depth overrides the block count where the config has one.
 """
@@ -51,11 +52,11 @@ def main():
     for i in range(2):
         step(i)
     torch.cuda.synchronize()
-    torch.cuda.nvtx.range_push("profiled_step")
+    torch.cuda.profiler.start()
     for i in range(args.steps):
         out = step(i)
     torch.cuda.synchronize()
-    torch.cuda.nvtx.range_pop()
+    torch.cuda.profiler.stop()
     print({k: float(v) for k, v in out.items()})
 
 

@@ -35,6 +35,19 @@ def test_library_exports_every_declared_symbol():
     assert lib.dlb_last_error() is not None
 
 
+def test_probe_library_is_separate_and_matches_its_header():
+    """Development probes live in libdiffulab_b200_probes.so with their own header; the product ABI carries none."""
+    from diffulab_b200 import _lib
+
+    text = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "diffulab_b200_probes.h")).read(), flags=re.S)
+    declared = sorted(set(re.findall(r"\b(dlb_[a-z0-9_]+)\s*\(", text)))
+    lib = _lib.load_probes()
+    assert declared == sorted(_lib._PROBE_SIGNATURES)
+    for s in declared:
+        assert hasattr(lib, s)
+    assert not any("probe" in s for s in header_symbols())
+
+
 def test_attn_seg_struct_layout_matches_header():
     import ctypes as C
 

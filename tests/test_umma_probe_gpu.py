@@ -20,9 +20,9 @@ def test_umma_noswizzle_descriptors(cuda_device, N, K, a_mn, b_mn):
     errs = {}
     for swap in (0, 1):
         D = torch.zeros(128, N, device="cuda")
-        rc = _lib.load().dlb_umma_probe(Ain.data_ptr(), Bin.data_ptr(), D.data_ptr(), N, K, a_mn, b_mn, swap,
+        rc = _lib.load_probes().dlb_umma_probe(Ain.data_ptr(), Bin.data_ptr(), D.data_ptr(), N, K, a_mn, b_mn, swap,
                                         torch.cuda.current_stream().cuda_stream)
-        _lib.check(rc, "dlb_umma_probe")
+        _lib.check_probe(rc, "dlb_umma_probe")
         torch.cuda.synchronize()
         errs[swap] = ((D - ref).norm() / ref.norm()).item()
     print("probe", N, K, a_mn, b_mn, errs)
