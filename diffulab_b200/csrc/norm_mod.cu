@@ -18,6 +18,7 @@
 //                  here: measured, profiles/elementwise_microbench_r1.jsonl).
 #include "common.cuh"
 #include "ptx.cuh"
+#include "rowwise_lean.cuh"
 #include <cstdlib>
 
 namespace {
@@ -988,6 +989,18 @@ DLB_EXPORT int dlb_ln_modulate_fwd(const void* x, const float* w, const float* b
               (long long)R, d, (long long)mod_ld);
   DLB_REQUIRE((w == nullptr) == (b == nullptr), DLB_ERR_SHAPE, "ln_modulate_fwd: weight and bias must both be set or null");
   DLB_REQUIRE(rows_per_mod >= 1 && (mean == nullptr) == (rstd == nullptr), DLB_ERR_SHAPE, "ln_modulate_fwd: bad args");
+  // lean warp-per-row kernel (rowwise_lean.cuh): per-sample modulation, exact per-lane unit split of the channels
+  static const bool no_lean = getenv("DLB_NO_LEAN") != nullptr;  // tests: force the general kernels
+  if (!no_lean && rows_per_mod % lean::WARPS == 0 && R < (1ll << 31) && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0) {
+    const int rpc = lean::rows_per_cta_for((int)R, dlb_num_sms() * 2);
+    const int grid_l = (int)((R + rpc - 1) / rpc);
+    DLB_LEAN_SWITCH(d, {
+      lean::ln_modulate_fwd_lean<U, UPL><<<grid_l, lean::WARPS * 32, 0, stream>>>((const bf16*)x, w, b, (const bf16*)scale, (const bf16*)shift, mod_ld,
+                                                                                  (int)rows_per_mod, (bf16*)y, mean, rstd, (int)R, eps, rpc);
+      dlb_count_launch();
+      return dlb_check_launch("ln_modulate_fwd_lean");
+    });
+  }
   // tiled bulk-async kernel: per-sample modulation whose groups are whole 8-row tiles, contiguous 16-byte aligned rows
   if (rows_per_mod % LT_ROWS == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0) {  // (no size threshold: the kernel choice must not depend on the batch size)
     const int64_t ntiles = (R + LT_ROWS - 1) / LT_ROWS;
@@ -1036,6 +1049,37 @@ DLB_EXPORT int dlb_ln_modulate_bwd(const void* dy, const void* x, const float* m
   DLB_REQUIRE(!per_token || groups == 1, DLB_ERR_SHAPE, "ln_modulate_bwd: per-token mode takes a single group");
   const int64_t R = groups * rows_per_group;
   const int64_t rows_per_mod = per_token ? 1 : rows_per_group;
+  // lean one-pass kernel (rowwise_lean.cuh), then the finalize kernel
+  static const bool no_lean = getenv("DLB_NO_LEAN") != nullptr;
+  if (!no_lean && !per_token && rows_per_group % lean::WARPS == 0 && R < (1ll << 31) && ((uintptr_t)dy % 16) == 0 && ((uintptr_t)x % 16) == 0 &&
+      ((uintptr_t)dx % 16) == 0 && ((uintptr_t)dres % 16) == 0 && ((uintptr_t)dscale % 16) == 0 && ((uintptr_t)dshift % 16) == 0 && dmod_ld % 4 == 0) {
+    const int rpc = lean::rows_per_cta_for((int)R, dlb_num_sms());
+    const int grid_l = (int)((R + rpc - 1) / rpc);
+    const size_t smem_l = (size_t)2 * d * 4 + (size_t)lean::WARPS * 2 * (dres ? 3 : 2) * d * 2;
+    if (smem_l <= 220 * 1024) {
+      DLB_LEAN_SWITCH(d, {
+        if (dres) {
+          cudaFuncSetAttribute(lean::ln_modulate_bwd_lean<U, UPL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
+          lean::ln_modulate_bwd_lean<U, UPL, true><<<grid_l, lean::WARPS * 32, smem_l, stream>>>(
+              (const bf16*)dy, (const bf16*)x, mean, rstd, w, (const bf16*)scale, mod_ld, (int)rows_per_group, (const bf16*)dres, (bf16*)dx, dshift, dscale,
+              dmod_ld, (int)R, rpc);
+        } else {
+          cudaFuncSetAttribute(lean::ln_modulate_bwd_lean<U, UPL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
+          lean::ln_modulate_bwd_lean<U, UPL, false><<<grid_l, lean::WARPS * 32, smem_l, stream>>>(
+              (const bf16*)dy, (const bf16*)x, mean, rstd, w, (const bf16*)scale, mod_ld, (int)rows_per_group, nullptr, (bf16*)dx, dshift, dscale, dmod_ld,
+              (int)R, rpc);
+        }
+        dlb_count_launch();
+        int rcl = dlb_check_launch("ln_modulate_bwd_lean");
+        if (rcl) return rcl;
+        const int gpb = 8;
+        dim3 fgrid((d + 255) / 256, (unsigned)((groups + gpb - 1) / gpb));
+        ln_modulate_bwd_finalize_kernel<<<fgrid, 256, 0, stream>>>(w, b, (const bf16*)scale, mod_ld, dscale, dshift, dmod_ld, dw, db, d, groups, gpb);
+        dlb_count_launch();
+        return dlb_check_launch("ln_modulate_bwd_finalize");
+      });
+    }
+  }
   // one-pass tiled kernel (dx + column sums), then the finalize kernel
   if (!per_token && rows_per_group % LB_ROWS == 0 && ((uintptr_t)dy % 16) == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)dx % 16) == 0 &&
       (dres == nullptr || ((uintptr_t)dres % 16) == 0) && ((uintptr_t)mean % 16) == 0 && ((uintptr_t)rstd % 16) == 0) {
@@ -1107,6 +1151,22 @@ DLB_EXPORT int dlb_gate_residual_fwd(const void* x, const void* a1, const void* 
                                      int64_t rows_per_mod, void* out, int64_t R, int d, cudaStream_t stream) {
   DLB_REQUIRE(R > 0 && d > 0 && d % 8 == 0 && gate_ld % 8 == 0 && rows_per_mod >= 1, DLB_ERR_SHAPE,
               "gate_residual_fwd: bad shape R=%lld d=%d", (long long)R, d);
+  static const bool no_lean = getenv("DLB_NO_LEAN") != nullptr;
+  if (!no_lean && R < (1ll << 31) && ((uintptr_t)x % 16) == 0 && ((uintptr_t)a1 % 16) == 0 && ((uintptr_t)a2 % 16) == 0 && ((uintptr_t)out % 16) == 0 &&
+      ((uintptr_t)gate % 16) == 0 && gate_ld % 8 == 0) {
+    const int rpc = lean::rows_per_cta_for((int)R, dlb_num_sms() * 3);
+    const int grid_l = (int)((R + rpc - 1) / rpc);
+    DLB_LEAN_SWITCH(d, {
+      if (a2)
+        lean::gate_residual_fwd_lean<U, UPL, true><<<grid_l, lean::WARPS * 32, 0, stream>>>((const bf16*)x, (const bf16*)a1, (const bf16*)a2, (const bf16*)gate,
+                                                                                          gate_ld, (int)rows_per_mod, (bf16*)out, (int)R, rpc);
+      else
+        lean::gate_residual_fwd_lean<U, UPL, false><<<grid_l, lean::WARPS * 32, 0, stream>>>((const bf16*)x, (const bf16*)a1, nullptr, (const bf16*)gate,
+                                                                                           gate_ld, (int)rows_per_mod, (bf16*)out, (int)R, rpc);
+      dlb_count_launch();
+      return dlb_check_launch("gate_residual_fwd_lean");
+    });
+  }
   const int g = stream_grid(R * (d / 8), 1);
   if (a2)
     gate_residual_fwd_kernel<true><<<g, 256, 0, stream>>>((const bf16*)x, (const bf16*)a1, (const bf16*)a2, (const bf16*)gate,
@@ -1126,6 +1186,23 @@ DLB_EXPORT int dlb_gate_residual_bwd(const void* dout, const void* a1, const voi
   DLB_REQUIRE(!per_token || groups == 1, DLB_ERR_SHAPE, "gate_residual_bwd: per-token mode takes a single group");
   const int64_t R = groups * rows_per_group;
   const int64_t rows_per_mod = per_token ? 1 : rows_per_group;
+  static const bool no_lean_b = getenv("DLB_NO_LEAN") != nullptr;
+  if (!no_lean_b && !per_token && rows_per_group % lean::WARPS == 0 && R < (1ll << 31) && ((uintptr_t)dout % 16) == 0 && ((uintptr_t)a1 % 16) == 0 &&
+      ((uintptr_t)a2 % 16) == 0 && ((uintptr_t)da % 16) == 0 && ((uintptr_t)gate % 16) == 0 && gate_ld % 8 == 0 && ((uintptr_t)dgate % 16) == 0 &&
+      dgate_ld % 4 == 0) {
+    const int rpc = lean::rows_per_cta_for((int)R, dlb_num_sms() * 2);
+    const int grid_l = (int)((R + rpc - 1) / rpc);
+    DLB_LEAN_SWITCH(d, {
+      if (a2)
+        lean::gate_residual_bwd_lean<U, UPL, true><<<grid_l, lean::WARPS * 32, 0, stream>>>((const bf16*)dout, (const bf16*)a1, (const bf16*)a2, (const bf16*)gate,
+                                                                                          gate_ld, (int)rows_per_group, (bf16*)da, dgate, dgate_ld, (int)R, rpc);
+      else
+        lean::gate_residual_bwd_lean<U, UPL, false><<<grid_l, lean::WARPS * 32, 0, stream>>>((const bf16*)dout, (const bf16*)a1, nullptr, (const bf16*)gate,
+                                                                                           gate_ld, (int)rows_per_group, (bf16*)da, dgate, dgate_ld, (int)R, rpc);
+      dlb_count_launch();
+      return dlb_check_launch("gate_residual_bwd_lean");
+    });
+  }
   if (!per_token && rows_per_group % LB_ROWS == 0 && ((uintptr_t)dout % 16) == 0 && ((uintptr_t)a1 % 16) == 0 &&
       (a2 == nullptr || ((uintptr_t)a2 % 16) == 0) && ((uintptr_t)da % 16) == 0) {
     const int nin = a2 ? 3 : 2;

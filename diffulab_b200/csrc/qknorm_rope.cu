@@ -6,6 +6,8 @@
 // activation dtype, rotation evaluated in that dtype) as called from DiTAttention.forward mmdit.py:81-89.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "rowwise_lean.cuh"
+#include <cstdlib>
 
 namespace {
 typedef __nv_bfloat16 bf16;
@@ -425,6 +427,22 @@ DLB_EXPORT int dlb_qknorm_rope_fwd(const void* qkv, int64_t ld_in, const float* 
   if (rc) return rc;
   DLB_REQUIRE(R > 0 && ld_in % 8 == 0 && ld_out % 8 == 0, DLB_ERR_SHAPE, "qknorm_rope_fwd: bad strides");
   RopeArgs ra{cs_t, pos_idx, rot_half, pos_offset, tokens_per_sample > 0 ? tokens_per_sample : 1, hd};
+  // lean warp-per-half-row kernel (rowwise_lean.cuh): needs an exact per-lane unit split and whole units inside the rotary span
+  static const bool no_lean = getenv("DLB_NO_LEAN") != nullptr;
+  if (!no_lean && R < (1ll << 31) && ((uintptr_t)qkv % 16) == 0 && ((uintptr_t)out % 16) == 0 && ((uintptr_t)cs_t % 16) == 0 && ((uintptr_t)sq % 16) == 0 &&
+      ((uintptr_t)sk % 16) == 0) {
+    int Uc = 0, UPLc = 0;
+    if (lean::pick_units(d, Uc, UPLc) && rot_half % (Uc / 2) == 0 && hd % Uc == 0) {
+      const int rpc = lean::rows_per_cta_for((int)R, dlb_num_sms() * 3);
+      const int grid_l = (int)((R + rpc - 1) / rpc);
+      DLB_LEAN_SWITCH(d, {
+        lean::qknorm_rope_fwd_lean<U, UPL><<<grid_l, lean::QK_WARPS * 32, 0, stream>>>((const bf16*)qkv, ld_in, sq, sk, cs_t, pos_idx, rot_half, pos_offset,
+                                                                                      ra.tokens_per_sample, hd, (bf16*)out, ld_out, rrms, (int)R, eps, rpc);
+        dlb_count_launch();
+        return dlb_check_launch("qknorm_rope_fwd_lean");
+      });
+    }
+  }
   // (a cp.async.bulk tile version of this forward measured SLOWER, 0.100 vs 0.088 ms: its packed-bf16 arithmetic is light
   //  enough that 24 resident row-warps per SM already hide the load latency; the backward kernels are the opposite case)
   const int warps = 4;
@@ -446,6 +464,24 @@ DLB_EXPORT int dlb_qknorm_rope_bwd(const void* dqk, int64_t ld_dqk, const void* 
   DLB_REQUIRE(R > 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && ld_dqk % 8 == 0, DLB_ERR_SHAPE, "qknorm_rope_bwd: bad strides");
   DLB_REQUIRE(rrms != nullptr, DLB_ERR_SHAPE, "qknorm_rope_bwd: the rrms buffer saved by the forward pass is required");
   RopeArgs ra{cs_t, pos_idx, rot_half, pos_offset, tokens_per_sample > 0 ? tokens_per_sample : 1, hd};
+  static const bool no_lean = getenv("DLB_NO_LEAN") != nullptr;
+  if (!no_lean && R < (1ll << 31) && ((uintptr_t)dqk % 16) == 0 && ((uintptr_t)qkv % 16) == 0 && ((uintptr_t)dqkv % 16) == 0 && ((uintptr_t)cs_t % 16) == 0 &&
+      ((uintptr_t)sq % 16) == 0 && ((uintptr_t)sk % 16) == 0 && ((uintptr_t)dsq % 16) == 0 && ((uintptr_t)dsk % 16) == 0 && (dsq == nullptr) == (dsk == nullptr)) {
+    int Uc = 0, UPLc = 0;
+    const size_t smem_l = (size_t)2 * d * 4 + (size_t)lean::WARPS * lean::QB_NS * 2 * d * 2;
+    if (lean::pick_units(d, Uc, UPLc) && rot_half % (Uc / 2) == 0 && hd % Uc == 0 && smem_l <= 220 * 1024) {
+      const int rpc = lean::rows_per_cta_for((int)R, dlb_num_sms());
+      const int grid_l = (int)((R + rpc - 1) / rpc);
+      DLB_LEAN_SWITCH(d, {
+        cudaFuncSetAttribute(lean::qknorm_rope_bwd_lean<U, UPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
+        lean::qknorm_rope_bwd_lean<U, UPL><<<grid_l, lean::WARPS * 32, smem_l, stream>>>(
+            (const bf16*)dqk, ld_dqk, (const bf16*)qkv, ld_in, sq, sk, cs_t, pos_idx, rot_half, pos_offset, ra.tokens_per_sample, hd, rrms, (bf16*)dqkv, ld_out, dsq,
+            dsk, (int)R, rpc);
+        dlb_count_launch();
+        return dlb_check_launch("qknorm_rope_bwd_lean");
+      });
+    }
+  }
   {  // one-pass tiled kernel (raw gradient + scale gradients from a single read)
     const size_t smem_t = (size_t)QB_STAGES * (2 * QB_ROWS * 4 * d + 16) + 2 * (size_t)QB_ROWS * 4 * d + 4 * (size_t)d * 4;
     const bool aligned = ((uintptr_t)dqk % 16) == 0 && ((uintptr_t)qkv % 16) == 0 && ((uintptr_t)dqkv % 16) == 0 && ((uintptr_t)rrms % 16) == 0;

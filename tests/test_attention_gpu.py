@@ -35,6 +35,9 @@ CASES = [
     (11, 8, 72, 0, 256, False),   # 176 work items > 148 SMs: persistent backward CTAs, uneven items per CTA
     (7, 6, 64, 40, 300, True),    # 126 items x ragged S = 340 (6 streamed tiles): one item per CTA, long ring
     (10, 6, 64, 72, 256, True),   # 180 items, S = 328: persistent + mask + partial tiles
+    (2, 4, 128, 0, 256, False),   # swizzled TMA path, head dim 128 (two 128-byte blocks per row)
+    (2, 2, 32, 128, 128, True),   # swizzled TMA path, head dim < 64 (out-of-bounds columns arrive as zeros), masked text segment
+    (5, 16, 72, 128, 256, True),  # swizzled TMA path, hd 72 (32-byte-swizzled tail block), two segments, 240 items
 ]
 
 

@@ -18,7 +18,7 @@ def test_sw_tiles_k_major_and_mn_major(cuda_device, hd, H, packed):
     ld = packed * H * hd
     buf = torch.randn(rows, ld, device="cuda", generator=g).bfloat16()
     X = buf[:, (packed - 1) * H * hd:]  # e.g. the V third of a packed qkv projection (row pitch > H*hd)
-    Y = torch.randn(rows, H * hd, device="cuda", generator=g).bfloat16()
+    Y = torch.randn(rows, ld, device="cuda", generator=g).bfloat16()[:, : H * hd]  # same row pitch as X (the probe takes one ld)
     P = torch.randn(128, 64, device="cuda", generator=g).bfloat16()
     hdp = 64 if hd <= 64 else (80 if hd <= 80 else 128)
     for h, xrow, yrow in ((0, 0, 64), (H - 1, 256, 448), (H // 2, 384, 128)):

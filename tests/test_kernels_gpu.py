@@ -32,7 +32,10 @@ def ref_ln_mod(x, w, b, scale, shift, eps):
     return u * one_s + shift.float()
 
 
-@pytest.mark.parametrize("B,N,d", [(2, 16, 64), (3, 50, 1152), (2, 64, 768), (4, 33, 512), (1, 7, 2048)])
+@pytest.mark.parametrize("B,N,d", [(2, 16, 64), (3, 50, 1152), (2, 64, 768), (4, 33, 512), (1, 7, 2048),
+                                   # lean warp-per-row kernels (rowwise_lean.cuh): exact per-lane unit split, rows_per_mod % 8 == 0;
+                                   # (200, 8, 256): a CTA's row range crosses sample boundaries (accumulator flush + P/Q rebuild)
+                                   (3, 256, 1152), (2, 128, 640), (200, 8, 256), (5, 72, 1152)])
 @pytest.mark.parametrize("affine", [True, False])
 def test_ln_modulate_fwd_bwd(gen, B, N, d, affine):
     from diffulab_b200 import ops
@@ -100,7 +103,8 @@ def test_ln_modulate_per_token(gen):
 
 
 # ---- gated residual (mmdit.py:296-307, 524-531) -----------------------------------------------------------
-@pytest.mark.parametrize("B,N,d,two", [(2, 16, 64, False), (3, 50, 1152, False), (2, 40, 768, True)])
+@pytest.mark.parametrize("B,N,d,two", [(2, 16, 64, False), (3, 50, 1152, False), (2, 40, 768, True),
+                                       (3, 256, 1152, False), (200, 8, 256, True), (2, 128, 640, True), (2, 64, 1152, True)])
 def test_gate_residual(gen, B, N, d, two):
     from diffulab_b200 import ops
 
@@ -162,7 +166,8 @@ def ref_qknorm_rope(x, s, cos, sin, H, hd):
     return torch.cat([rot, yp], -1).reshape(B, S, d)
 
 
-@pytest.mark.parametrize("B,S,H,hd,axes", [(2, 16, 2, 32, [16, 16]), (2, 64, 16, 72, [36, 36]), (2, 40, 12, 64, [16, 24, 24]), (1, 9, 8, 64, [8, 8])])
+@pytest.mark.parametrize("B,S,H,hd,axes", [(2, 16, 2, 32, [16, 16]), (2, 64, 16, 72, [36, 36]), (2, 40, 12, 64, [16, 24, 24]), (1, 9, 8, 64, [8, 8]),
+                                           (3, 256, 16, 72, [36, 36]), (2, 32, 4, 64, [16, 16]), (2, 129, 10, 64, [20, 22, 22])])
 def test_qknorm_rope(gen, B, S, H, hd, axes):
     from diffulab_b200 import ops
 
