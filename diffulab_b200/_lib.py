@@ -64,6 +64,10 @@ _SIGNATURES: dict[str, list] = {
     # pred, pred_dtype, xt, noise, table, t, sampler, mean_type, clamp, eta, B, per_sample, x_prev, x0, mean, logprob, stream
     "dlb_gaussian_step": [p, i32, p, p, p, p, i32, i32, i32, f32, i64, i64, p, p, p, p, p],
     "dlb_add_bf16": [p, p, p, i64, p],
+    "dlb_gelu_fwd": [p, p, i64, p],
+    "dlb_gelu_bwd": [p, p, p, i64, p],
+    # x, ld_in, y, ld_out, cs, rot_half, pos_idx, pos_offset, tokens_per_sample, hd, d, R, inverse, stream
+    "dlb_rope_apply": [p, i64, p, i64, p, i32, p, i32, i32, i32, i32, i64, i32, p],
     "dlb_bias_silu_fwd": [p, p, p, i64, i64, i32, p],
     "dlb_bias_silu_bwd": [p, p, p, p, p, i64, i64, i32, p],
     "dlb_silu_fwd": [p, i32, p, i64, p],

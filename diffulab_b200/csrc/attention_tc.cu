@@ -10,10 +10,9 @@
 // resident row — and streams the other sequence axis past it in 64-row tiles through a ring of shared-memory stages.
 // 352 threads: warps 0-7 are compute warps (two threads per resident row, each owning 32 of the 64 columns of a score
 // tile), warp 8 only issues tcgen05.mma (warp-uniform code, elect.sync) so that instruction issue never sits on the
-// softmax threads' path, warps 9-10 are producers: one elected lane issues TMA loads through 3-D tensor maps {hd, heads,
-// tokens} with 128-byte swizzled boxes (attn_sw.cuh: segment lengths that are multiples of 128, padded head dims 64 / 80 /
-// 128), otherwise both warps stage with cp.async into the unswizzled core-matrix layout (8 rows x 64 bytes per warp
-// instruction) and arrive asynchronously (cp.async.mbarrier.arrive.noinc).
+// softmax threads' path, warps 9-10 are producers: one elected lane issues TMA loads through 4-D tensor maps whose
+// boxes land directly in the operand layout (segment lengths that are multiples of 128), otherwise both warps stage with
+// cp.async (8 rows x 64 bytes per warp instruction) and arrive asynchronously (cp.async.mbarrier.arrive.noinc).
 // CTAs are persistent over (tile, head, sample) work items and the load ring runs ahead across item boundaries.
 // No CTA-wide barrier inside the loop; the hand-offs are mbarriers:
 //   full[s]  (TMA bytes / producer arrivals) tile in stage s has landed       producers -> MMA warp
@@ -34,7 +33,6 @@
 // Head dims that are not a multiple of 16 (DiT-XL/2: 72) are zero-padded in shared memory only.
 #include "common.cuh"
 #include "ptx.cuh"
-#include "attn_sw.cuh"
 
 namespace attn_tc {
 typedef __nv_bfloat16 bf16;
@@ -372,57 +370,16 @@ __global__ void __launch_bounds__(NC, 2) attn_fwd_tc_kernel(const Params p) {
 // current item's epilogue. RES = 1 (large head dims, or fewer than NST streamed tiles per item) = one item per CTA.
 //   empty[s] (tcgen05.commit) accumulating products that read stage s are done        MMA warp -> producers
 // ---------------------------------------------------------------------------------------------------------
-// TMA fast path (every segment length a multiple of 128, padded head dim 64 / 80 / 128): swizzled head-slice tiles
-// (attn_sw.cuh) loaded through 3-D tensor maps {hd, heads, tokens}; one elected producer lane issues them. Otherwise the
-// producer warps use cp.async into the unswizzled layout L1(R) (ragged tiles, arbitrary segment lengths).
-struct BwdMaps { CUtensorMap m[2][5][2]; };  // [segment][T_Q .. T_O][main | tail]
-template <int HDP, int R>
-__device__ __forceinline__ void tma_tile(uint8_t* dst, const BwdMaps& maps, int which, const Params& p, int b, int h, int s0, uint64_t* bar) {
+// TMA fast path (every segment length a multiple of 128): 4-D tensor maps {8 elements, rows, 16-byte chunks of a head,
+// heads} whose boxes land directly in layout L1(64) / L1(128) (pinned by scripts/probe_tma_gather.py); one elected
+// producer lane issues them. Otherwise the producer warps use cp.async (ragged tiles, arbitrary segment lengths).
+enum { M_Q64 = 0, M_Q128, M_K64, M_K128, M_V64, M_V128, M_DO64, M_DO128, M_O128, M_COUNT };
+struct BwdMaps { CUtensorMap m[2][M_COUNT]; };
+__device__ __forceinline__ void tma_tile(void* dst, const BwdMaps& maps, int which, const Params& p, int b, int h, int s0, uint64_t* bar) {
   const int sg = s0 < p.seg[0].len ? 0 : 1;
   const int row = b * p.seg[sg].len + (sg ? s0 - p.seg[0].len : s0);
-  attn_sw::tma_tile<HDP, R>(dst, &maps.m[sg][which][0], &maps.m[sg][which][1], bar, h, row);
+  ptx::tma_load_4d(dst, &maps.m[sg][which], bar, 0, row, 0, h);
 }
-// operand products in either layout. SW: swizzled tiles; else the unswizzled layout L1(R)
-template <int HDP, bool SW>
-__device__ __forceinline__ void mma_scores64(uint32_t d_tmem, uint32_t a_tile128, uint32_t b_tile64) {  // S(128 x 64) = A B^T over the head dim
-  if constexpr (SW) {
-    attn_sw::mma_scores<HDP, 64>(d_tmem, a_tile128, b_tile64);
-  } else {
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, KT, false, false);
-    const uint64_t da = desc_k128(a_tile128), db = desc_k64(b_tile64);
-#pragma unroll
-    for (int ks = 0; ks < HDP / 16; ++ks) ptx::umma_bf16_elect(d_tmem, da + ks * KSTEP_K128, db + ks * KSTEP_K64, idesc, ks > 0);
-  }
-}
-template <int HDP, bool SW>
-__device__ __forceinline__ void mma_accum64(uint32_t d_tmem, uint32_t p_tile, uint32_t b_tile64, bool acc0) {  // D(128 x HDP) (+)= P(128 x 64) B(64 x HDP)
-  if constexpr (SW) {
-    attn_sw::mma_accum<HDP>(d_tmem, p_tile, b_tile64, acc0);
-  } else {
-    constexpr uint32_t idesc = ptx::make_idesc_bf16(128, HDP, false, true);
-    const uint64_t dp = desc_k128(p_tile), db = desc_mn64(b_tile64);
-#pragma unroll
-    for (int ks = 0; ks < KT / 16; ++ks) ptx::umma_bf16_elect(d_tmem, dp + ks * KSTEP_K128, db + ks * KSTEP_MN64, idesc, (acc0 || ks > 0) ? 1u : 0u);
-  }
-}
-// 32 columns starting at column c (a multiple of 32) of row r of a thread-written [128][64] operand tile
-template <bool SW>
-__device__ __forceinline__ void store_p32(uint8_t* tile, int r, int c, const float* v) {
-  if constexpr (SW) {
-#pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-      uint4 u;
-      u.x = pack_bf16x2(v[8 * q4 + 0], v[8 * q4 + 1]);
-      u.y = pack_bf16x2(v[8 * q4 + 2], v[8 * q4 + 3]);
-      u.z = pack_bf16x2(v[8 * q4 + 4], v[8 * q4 + 5]);
-      u.w = pack_bf16x2(v[8 * q4 + 6], v[8 * q4 + 7]);
-      *reinterpret_cast<uint4*>(tile + attn_sw::p_chunk_off(r, (c >> 3) + q4)) = u;
-    }
-  } else {
-    store_bf16x32(tile + r * 16, c, v);
-  }
-}
-__device__ __forceinline__ uint8_t* align1024(uint8_t* p) { return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023)); }
 
 struct Item { int x, h, b; };
 __device__ __forceinline__ Item decode_item(const Params& p, int w, int nx) {
@@ -452,14 +409,13 @@ template <int HDP, int RES, int NST, bool TMA>
 __global__ void __launch_bounds__(NT, 1) attn_fwd_ws_tc_kernel(const Params p, const __grid_constant__ BwdMaps maps) {
   constexpr int TQ = 128 * HDP * 2, TK = KT * HDP * 2;
   constexpr int HH = HDP / 2;
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint8_t* smem = align1024(smem_raw);                      // swizzled tiles need 1024-byte aligned bases
-  uint8_t* sRes = smem;                                     // RES x Q tile, layout L1(128) / swizzled
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sRes = smem;                                     // RES x Q tile, layout L1(128)
   uint8_t* sKV = sRes + RES * TQ;                           // NST stages of {K tile, V tile}
-  uint8_t* sP = sKV + NST * 2 * TK;                         // 2 x [128 q][64 keys] bf16 (double-buffered by tile parity), 32 KB
-  bf16* sStage = reinterpret_cast<bf16*>(sP + 2 * 16384);   // [128][HDP] output staging
+  uint8_t* sP = sKV + NST * 2 * TK;                         // [128 q][64 keys] bf16, layout L1(128), 16 KB
+  bf16* sStage = reinterpret_cast<bf16*>(sP + 16384);       // [128][HDP] output staging
   float* sX = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sStage) + TQ);  // [2][2][128] pair exchange
-  __shared__ uint64_t full[NST], empty[NST], bar_s[2], ps_full, bar_o[2];
+  __shared__ uint64_t full[NST], empty[NST], bar_s[2], ps_full, bar_o;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
@@ -469,15 +425,15 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_ws_tc_kernel(const Params p, c
   const int G = n_my * T;
   if (tid == 0) {
     for (int i = 0; i < NST; ++i) { ptx::mbar_init(&full[i], TMA ? 1 : NPW * 32); ptx::mbar_init(&empty[i], 1); }
-    ptx::mbar_init(&bar_s[0], 1); ptx::mbar_init(&bar_s[1], 1); ptx::mbar_init(&ps_full, NC); ptx::mbar_init(&bar_o[0], 1); ptx::mbar_init(&bar_o[1], 1);
+    ptx::mbar_init(&bar_s[0], 1); ptx::mbar_init(&bar_s[1], 1); ptx::mbar_init(&ps_full, NC); ptx::mbar_init(&bar_o, 1);
     ptx::fence_mbar_init();
   }
-  // TMEM: S tiles at columns 0 / 64 (double-buffered), O tiles at columns 128 / 256 (double-buffered): the product
-  // O_g = P_g V_g of tile g runs while the compute warps already do the softmax of tile g + 1 and is drained one tile later
-  if (warp_u == 8) ptx::tmem_alloc<512>(&tmem_slot);
+  if (warp_u == 8) ptx::tmem_alloc<256>(&tmem_slot);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, KT, false, false);
+  constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, HDP, false, true);
 
   if (warp_u > 8) {
     // ---------------- producer warps ----------------
@@ -492,9 +448,9 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_ws_tc_kernel(const Params p, c
         if (pw == 0 && ptx::elect_one()) {
           uint64_t* bar = &full[u % NST];
           ptx::mbar_expect_tx(bar, 2 * TK + (uj == 0 ? TQ : 0));
-          if (uj == 0) tma_tile<HDP, 128>(res, maps, T_Q, p, it.b, it.h, it.x * 128, bar);
-          tma_tile<HDP, 64>(st, maps, T_K, p, it.b, it.h, uj * KT, bar);
-          tma_tile<HDP, 64>(st + TK, maps, T_V, p, it.b, it.h, uj * KT, bar);
+          if (uj == 0) tma_tile(res, maps, M_Q128, p, it.b, it.h, it.x * 128, bar);
+          tma_tile(st, maps, M_K64, p, it.b, it.h, uj * KT, bar);
+          tma_tile(st + TK, maps, M_V64, p, it.b, it.h, uj * KT, bar);
         }
         __syncwarp();
         if (++uj == T) { uj = 0; ++uk; }
@@ -511,7 +467,7 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_ws_tc_kernel(const Params p, c
     // ---------------- MMA-issue warp ----------------
     const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
     const uint32_t resa = ptx::smem_u32(sRes), kva = ptx::smem_u32(sKV);
-    const uint32_t pa = ptx::smem_u32(sP);
+    const uint64_t dp0 = desc_k128(ptx::smem_u32(sP));
     int tk = 0, tj = 0;
     for (int g = -1; g < G; ++g) {
       const bool next_ready = g + 1 < G && (g < 0 || __shfl_sync(0xffffffffu, (int)ptx::mbar_test_wait(&full[(g + 1) % NST], ((g + 1) / NST) & 1), 0) != 0);
@@ -519,24 +475,24 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_ws_tc_kernel(const Params p, c
       for (int pass = 0; pass < 2; ++pass) {
         if ((pass == 0) == next_ready && g + 1 < G) {  // S(t) = Q K_t^T into TMEM buffer t & 1
           const int t = g + 1;
-          MMA_TRACE(0, tk, 32 + tj * 4);
           ptx::mbar_wait(&full[t % NST], (t / NST) & 1);
-          MMA_TRACE(0, tk, 33 + tj * 4);
           ptx::fence_proxy_async_smem();
           ptx::tc_fence_after();
-          mma_scores64<HDP, TMA>(tmem + (t & 1) * KT, resa + (tk % RES) * TQ, kva + (t % NST) * 2 * TK);
+          const uint64_t dq0 = desc_k128(resa + (tk % RES) * TQ);
+          const uint64_t dk = desc_k64(kva + (t % NST) * 2 * TK);
+#pragma unroll
+          for (int ks = 0; ks < HDP / 16; ++ks) ptx::umma_bf16_elect(tmem + (t & 1) * KT, dq0 + ks * KSTEP_K128, dk + ks * KSTEP_K64, idesc_s, ks > 0);
           ptx::umma_commit_elect(&bar_s[t & 1]);
           if (++tj == T) { tj = 0; ++tk; }
         }
-        if (pass == 0 && g >= 0) {  // O_g = P_g V_g (fresh tile: the compute warps accumulate in registers)
-          // ps_full(g): P_g is written AND every compute thread has drained O_{g-2} (same TMEM buffer) and S_g
-          MMA_TRACE(0, g / T, 34 + (g % T) * 4);
+        if (pass == 0 && g >= 0) {  // O_g = P V_g (fresh tile: the compute warps accumulate in registers)
           ptx::mbar_wait(&ps_full, g & 1);
-          MMA_TRACE(0, g / T, 35 + (g % T) * 4);
           ptx::tc_fence_after();
-          mma_accum64<HDP, TMA>(tmem + 128 + (g & 1) * 128, pa + (g & 1) * 16384, kva + (g % NST) * 2 * TK + TK, false);
+          const uint64_t dv = desc_mn64(kva + (g % NST) * 2 * TK + TK);
+#pragma unroll
+          for (int ks = 0; ks < KT / 16; ++ks) ptx::umma_bf16_elect(tmem + 128, dp0 + ks * KSTEP_K128, dv + ks * KSTEP_MN64, idesc_o, ks > 0);
           ptx::umma_commit_elect(&empty[g % NST]);
-          ptx::umma_commit_elect(&bar_o[g & 1]);
+          ptx::umma_commit_elect(&bar_o);
         }
       }
     }
@@ -546,24 +502,20 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_ws_tc_kernel(const Params p, c
     const uint32_t tmem = tmem_slot;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tO = tmem + 128 + lane_off;
-    const int trace_item = n_my > 1 ? 1 : 0;
     int k = 0, j = 0;
     Item it = decode_item(p, blockIdx.x, nx);
     float o[HH];
     float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-    // o = o * alpha(t) + O_t (my half of the head dim); alpha(t) rescales what was accumulated before tile t
-    auto add_o_tile = [&](int t, float alpha) {
-      ptx::mbar_wait(&bar_o[t & 1], (t >> 1) & 1);
-      ptx::tc_fence_after();
+    auto add_o_tile = [&]() {  // o = o * alpha + O_tile (my half of the head dim)
       uint32_t v[HH];
-      const uint32_t a = tO + (t & 1) * 128 + half * HH;
+      const uint32_t a = tO + half * HH;
       ptx::tmem_ld32(a, v);
       if constexpr (HH == 40) ptx::tmem_ld8(a + 32, v + 32);
       if constexpr (HH == 48) ptx::tmem_ld16(a + 32, v + 32);
       if constexpr (HH == 64) ptx::tmem_ld32(a + 32, v + 32);
       ptx::tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < HH; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(v[i]));
+      for (int i = 0; i < HH; ++i) o[i] = fmaf(o[i], alpha_prev, __uint_as_float(v[i]));
     };
     for (int g = 0; g < G; ++g) {
       if (j == 0) {
@@ -574,10 +526,13 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_ws_tc_kernel(const Params p, c
         l = 0.f;
         alpha_prev = 0.f;
       }
-      if (j < 8) BWD_TRACE(0, 4 + j * 6);
       ptx::mbar_wait(&bar_s[g & 1], (g >> 1) & 1);
       ptx::tc_fence_after();
-      if (j < 8) BWD_TRACE(0, 5 + j * 6);
+      if (g >= 1) {
+        ptx::mbar_wait(&bar_o, (g - 1) & 1);  // O_{g-1} finished: sP and the O tile are free
+        ptx::tc_fence_after();
+        if (j > 0) add_o_tile();  // (for j == 0 the previous item's epilogue already consumed it)
+      }
       float s[32];
       {
         uint32_t v[32];
@@ -603,7 +558,7 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_ws_tc_kernel(const Params p, c
       const float mx = fmaxf(sx[r], sx[128 + r]);
       const float m_new = fmaxf(m, mx);
       const float ms = (m_new == -INFINITY) ? 0.f : m_new * p.scale_log2;
-      const float alpha = ex2(m * p.scale_log2 - ms);
+      alpha_prev = ex2(m * p.scale_log2 - ms);
 #pragma unroll
       for (int i = 0; i < 32; ++i) s[i] = ex2(s[i] * p.scale_log2 - ms);
       float ls0 = 0.f, ls1 = 0.f;
@@ -612,22 +567,16 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_ws_tc_kernel(const Params p, c
         ls0 += (s[i] + s[i + 1]) + (s[i + 2] + s[i + 3]);
         ls1 += (s[i + 4] + s[i + 5]) + (s[i + 6] + s[i + 7]);
       }
-      // P buffer g & 1 was last read by the product of tile g - 2, whose completion this thread observed when it drained
-      // O_{g-2} (previous iteration, or the previous item's epilogue)
-      if (j < 8) BWD_TRACE(0, 6 + j * 6);
-      store_p32<TMA>(sP + (g & 1) * 16384, r, half * 32, s);
-      l = l * alpha + (ls0 + ls1);
+      store_bf16x32(sP + r * 16, half * 32, s);
+      l = l * alpha_prev + (ls0 + ls1);
       m = m_new;
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&ps_full);
-      if (j < 8) BWD_TRACE(0, 7 + j * 6);
-      if (j > 0) add_o_tile(g - 1, alpha_prev);  // drain O_{g-1}: its product ran during this tile's softmax
-      alpha_prev = alpha;
-      if (j < 8) BWD_TRACE(0, 8 + j * 6);
       if (j == T - 1) {  // item epilogue
-        add_o_tile(g, alpha_prev);
-        BWD_TRACE(0, 56);
+        ptx::mbar_wait(&bar_o, g & 1);
+        ptx::tc_fence_after();
+        add_o_tile();
         float* sl = sX + 512 + (k & 1) * 256;
         sl[half * 128 + r] = l;
         pair_barrier(1 + (warp & 3));
@@ -645,9 +594,7 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_ws_tc_kernel(const Params p, c
         }
         ptx::tc_fence_before();
         compute_barrier();
-        BWD_TRACE(0, 58);
         store_tile<HDP, O_OUT>(sStage, p, it.b, it.h, it.x * 128, tid);
-        BWD_TRACE(0, 59);
         j = 0;
         ++k;
       } else {
@@ -657,7 +604,7 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_ws_tc_kernel(const Params p, c
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp_u == 8) ptx::tmem_dealloc<512>(__shfl_sync(0xffffffffu, tmem_slot, 0));
+  if (warp_u == 8) ptx::tmem_dealloc<256>(__shfl_sync(0xffffffffu, tmem_slot, 0));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -667,9 +614,8 @@ template <int HDP, int RES, int NST, bool TMA>
 __global__ void __launch_bounds__(NT, 1) attn_bwd_dq_tc_kernel(const Params p, const __grid_constant__ BwdMaps maps) {
   constexpr int TQ = 128 * HDP * 2, TK = KT * HDP * 2;
   constexpr int CPR = HDP / 8;
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint8_t* smem = align1024(smem_raw);
-  uint8_t* sRes = smem;                                    // RES x {Q, dO, O} resident tiles, layout L1(128) / swizzled
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sRes = smem;                                    // RES x {Q, dO, O} resident tiles, layout L1(128)
   uint8_t* sKV = sRes + RES * 3 * TQ;                      // NST stages of {K tile, V tile}
   uint8_t* sDS = sKV + NST * 2 * TK;                       // [128 q][64 keys] bf16, layout L1(128), 16 KB
   float* sLrow = reinterpret_cast<float*>(sDS + 16384);    // [RES][128] lse rows (natural log)
@@ -691,6 +637,8 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dq_tc_kernel(const Params p, c
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, KT, false, false);
+  constexpr uint32_t idesc_dq = ptx::make_idesc_bf16(128, HDP, false, true);
 
   if (warp_u > 8) {
     // ---------------- producer warps ----------------
@@ -706,13 +654,13 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dq_tc_kernel(const Params p, c
           uint64_t* bar = &full[u % NST];
           ptx::mbar_expect_tx(bar, 2 * TK + (uj == 0 ? 3 * TQ + 512 : 0));
           if (uj == 0) {
-            tma_tile<HDP, 128>(res, maps, T_Q, p, it.b, it.h, it.x * 128, bar);
-            tma_tile<HDP, 128>(res + TQ, maps, T_DO, p, it.b, it.h, it.x * 128, bar);
-            tma_tile<HDP, 128>(res + 2 * TQ, maps, T_O, p, it.b, it.h, it.x * 128, bar);
+            tma_tile(res, maps, M_Q128, p, it.b, it.h, it.x * 128, bar);
+            tma_tile(res + TQ, maps, M_DO128, p, it.b, it.h, it.x * 128, bar);
+            tma_tile(res + 2 * TQ, maps, M_O128, p, it.b, it.h, it.x * 128, bar);
             ptx::bulk_load_1d(sLrow + (uk % RES) * 128, p.lse + ((int64_t)it.b * p.H + it.h) * p.S + it.x * 128, 512, bar);
           }
-          tma_tile<HDP, 64>(st, maps, T_K, p, it.b, it.h, uj * KT, bar);
-          tma_tile<HDP, 64>(st + TK, maps, T_V, p, it.b, it.h, uj * KT, bar);
+          tma_tile(st, maps, M_K64, p, it.b, it.h, uj * KT, bar);
+          tma_tile(st + TK, maps, M_V64, p, it.b, it.h, uj * KT, bar);
         }
         __syncwarp();
         if (++uj == T) { uj = 0; ++uk; }
@@ -739,7 +687,7 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dq_tc_kernel(const Params p, c
     // ---------------- MMA-issue warp ----------------
     const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
     const uint32_t resa = ptx::smem_u32(sRes), kva = ptx::smem_u32(sKV);
-    const uint32_t dsa = ptx::smem_u32(sDS);
+    const uint64_t ds0 = desc_k128(ptx::smem_u32(sDS));
     int tk = 0, tj = 0;  // item / tile-in-item of tile t = g + 1
     int gj = 0;          // tile-in-item of tile g
     for (int g = -1; g < G; ++g) {
@@ -756,9 +704,14 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dq_tc_kernel(const Params p, c
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_after();
         const uint32_t ra = resa + (tk % RES) * 3 * TQ;
+        const uint64_t dq0 = desc_k128(ra), dd0 = desc_k128(ra + TQ);
+        const uint64_t dk = desc_k64(kva + (t % NST) * 2 * TK), dv = desc_k64(kva + (t % NST) * 2 * TK + TK);
         const uint32_t ts = tmem + (t & 1) * 128;
-        mma_scores64<HDP, TMA>(ts, ra, kva + (t % NST) * 2 * TK);                  // S  = Q K_t^T
-        mma_scores64<HDP, TMA>(ts + KT, ra + TQ, kva + (t % NST) * 2 * TK + TK);   // dP = dO V_t^T
+#pragma unroll
+        for (int ks = 0; ks < HDP / 16; ++ks) {
+          ptx::umma_bf16_elect(ts, dq0 + ks * KSTEP_K128, dk + ks * KSTEP_K64, idesc_s, ks > 0);
+          ptx::umma_bf16_elect(ts + KT, dd0 + ks * KSTEP_K128, dv + ks * KSTEP_K64, idesc_s, ks > 0);
+        }
         ptx::umma_commit_elect(&bar1[t & 1]);
         if (++tj == T) { tj = 0; ++tk; }
       }
@@ -767,7 +720,9 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dq_tc_kernel(const Params p, c
         ptx::mbar_wait(&ps_full, g & 1);
         MMA_TRACE(1, g / T, 35 + gj * 4);
         ptx::tc_fence_after();
-        mma_accum64<HDP, TMA>(tmem + 256, dsa, kva + (g % NST) * 2 * TK, gj > 0);
+        const uint64_t dk = desc_mn64(kva + (g % NST) * 2 * TK);
+#pragma unroll
+        for (int ks = 0; ks < KT / 16; ++ks) ptx::umma_bf16_elect(tmem + 256, ds0 + ks * KSTEP_K128, dk + ks * KSTEP_MN64, idesc_dq, (gj > 0 || ks > 0) ? 1u : 0u);
         ptx::umma_commit_elect(&empty[g % NST]);
         ptx::umma_commit_elect(&bar2);
         if (++gj == T) gj = 0;
@@ -790,16 +745,13 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dq_tc_kernel(const Params p, c
         BWD_TRACE(1, 0);
         it = decode_item(p, blockIdx.x + k * gridDim.x, nx);
         ptx::mbar_wait(&full[g % NST], (g / NST) & 1);  // resident tiles (and streamed tile 0) of this item have landed
-        const uint8_t* sdo = sRes + (k % RES) * 3 * TQ + TQ;
+        const uint8_t* sdo = sRes + (k % RES) * 3 * TQ + TQ + r * 16;
         float dpart = 0.f;
 #pragma unroll
         for (int c = half; c < CPR; c += 2) {
           float df[8], of[8];
-          uint32_t off;
-          if constexpr (TMA) off = attn_sw::chunk_off<HDP, 128>(r, c);
-          else off = r * 16 + c * 2048;
-          unpack8(*reinterpret_cast<const bf16x8*>(sdo + off), df);
-          unpack8(*reinterpret_cast<const bf16x8*>(sdo + TQ + off), of);
+          unpack8(*reinterpret_cast<const bf16x8*>(sdo + c * 2048), df);
+          unpack8(*reinterpret_cast<const bf16x8*>(sdo + TQ + c * 2048), of);
 #pragma unroll
           for (int i = 0; i < 8; ++i) dpart += df[i] * of[i];
         }
@@ -816,6 +768,8 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dq_tc_kernel(const Params p, c
       ptx::mbar_wait(&bar1[g & 1], (g >> 1) & 1);
       ptx::tc_fence_after();
       if (j < 8) BWD_TRACE(1, 5 + j * 6);
+      if (g >= 1) ptx::mbar_wait(&bar2, (g - 1) & 1);  // dQ += dS K_{g-1} finished: sDS is free
+      if (j < 8) BWD_TRACE(1, 6 + j * 6);
       {
         const uint32_t ts = tmem + lane_off + (g & 1) * 128 + half * 32;
         uint32_t vs[32], vd[32];
@@ -831,10 +785,7 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dq_tc_kernel(const Params p, c
 #pragma unroll
           for (int i = 0; i < 32; ++i) ds[i] = ex2(__uint_as_float(vs[i]) * p.scale_log2 - Lrow) * (__uint_as_float(vd[i]) - Drow);
         }
-        // sDS is free once dQ += dS K_{g-1} has finished; that product ran while this tile's dS was computed in registers
-        if (g >= 1) ptx::mbar_wait(&bar2, (g - 1) & 1);
-        if (j < 8) BWD_TRACE(1, 6 + j * 6);
-        store_p32<TMA>(sDS, r, half * 32, ds);
+        store_bf16x32(sDS + r * 16, half * 32, ds);
       }
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
@@ -869,9 +820,8 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dq_tc_kernel(const Params p, c
 template <int HDP, int RES, int NST, bool TMA>
 __global__ void __launch_bounds__(NT, 1) attn_bwd_dkv_tc_kernel(const Params p, const __grid_constant__ BwdMaps maps) {
   constexpr int TQ = 128 * HDP * 2, TK = KT * HDP * 2;
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint8_t* smem = align1024(smem_raw);
-  uint8_t* sRes = smem;                                    // RES x {K, V} resident tiles, layout L1(128) / swizzled
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sRes = smem;                                    // RES x {K, V} resident tiles, layout L1(128)
   uint8_t* sQD = sRes + RES * 2 * TQ;                      // NST stages of {Q tile, dO tile}
   uint8_t* sPT = sQD + NST * 2 * TK;                       // P^T  [128 keys][64 queries] bf16, layout L1(128)
   uint8_t* sDST = sPT + 16384;                             // dS^T
@@ -894,6 +844,8 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dkv_tc_kernel(const Params p, 
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, KT, false, false);
+  constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, HDP, false, true);
 
   if (warp_u > 8) {
     // ---------------- producer warps ----------------
@@ -910,11 +862,11 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dkv_tc_kernel(const Params p, 
           uint64_t* bar = &full[u % NST];
           ptx::mbar_expect_tx(bar, 2 * TK + 2 * KT * 4 + (uj == 0 ? 2 * TQ : 0));
           if (uj == 0) {
-            tma_tile<HDP, 128>(res, maps, T_K, p, it.b, it.h, it.x * 128, bar);
-            tma_tile<HDP, 128>(res + TQ, maps, T_V, p, it.b, it.h, it.x * 128, bar);
+            tma_tile(res, maps, M_K128, p, it.b, it.h, it.x * 128, bar);
+            tma_tile(res + TQ, maps, M_V128, p, it.b, it.h, it.x * 128, bar);
           }
-          tma_tile<HDP, 64>(st, maps, T_Q, p, it.b, it.h, uj * KT, bar);
-          tma_tile<HDP, 64>(st + TK, maps, T_DO, p, it.b, it.h, uj * KT, bar);
+          tma_tile(st, maps, M_Q64, p, it.b, it.h, uj * KT, bar);
+          tma_tile(st + TK, maps, M_DO64, p, it.b, it.h, uj * KT, bar);
           ptx::bulk_load_1d(sL + (u % NST) * KT, p.lse + base + uj * KT, KT * 4, bar);
           ptx::bulk_load_1d(sD + (u % NST) * KT, p.dsum + base + uj * KT, KT * 4, bar);
         }
@@ -944,7 +896,7 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dkv_tc_kernel(const Params p, 
     // ---------------- MMA-issue warp ----------------
     const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
     const uint32_t resa = ptx::smem_u32(sRes), qda = ptx::smem_u32(sQD);
-    const uint32_t pta = ptx::smem_u32(sPT), dsta = ptx::smem_u32(sDST);
+    const uint64_t dp0 = desc_k128(ptx::smem_u32(sPT)), ds0 = desc_k128(ptx::smem_u32(sDST));
     int tk = 0, tj = 0, gj = 0;
     for (int g = -1; g < G; ++g) {
       const bool next_ready = g + 1 < G && (g < 0 || __shfl_sync(0xffffffffu, (int)ptx::mbar_test_wait(&full[(g + 1) % NST], ((g + 1) / NST) & 1), 0) != 0);
@@ -958,9 +910,14 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dkv_tc_kernel(const Params p, 
         ptx::fence_proxy_async_smem();
         ptx::tc_fence_after();
         const uint32_t ra = resa + (tk % RES) * 2 * TQ;
+        const uint64_t dk0 = desc_k128(ra), dv0 = desc_k128(ra + TQ);
+        const uint64_t dq = desc_k64(qda + (t % NST) * 2 * TK), dd = desc_k64(qda + (t % NST) * 2 * TK + TK);
         const uint32_t ts = tmem + (t & 1) * 128;
-        mma_scores64<HDP, TMA>(ts, ra, qda + (t % NST) * 2 * TK);                  // S^T  = K Q_t^T
-        mma_scores64<HDP, TMA>(ts + KT, ra + TQ, qda + (t % NST) * 2 * TK + TK);   // dP^T = V dO_t^T
+#pragma unroll
+        for (int ks = 0; ks < HDP / 16; ++ks) {
+          ptx::umma_bf16_elect(ts, dk0 + ks * KSTEP_K128, dq + ks * KSTEP_K64, idesc_s, ks > 0);
+          ptx::umma_bf16_elect(ts + KT, dv0 + ks * KSTEP_K128, dd + ks * KSTEP_K64, idesc_s, ks > 0);
+        }
         ptx::umma_commit_elect(&bar1[t & 1]);
         if (++tj == T) { tj = 0; ++tk; }
       }
@@ -969,8 +926,13 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dkv_tc_kernel(const Params p, 
         ptx::mbar_wait(&ps_full, g & 1);
         MMA_TRACE(2, g / T, 35 + gj * 4);
         ptx::tc_fence_after();
-        mma_accum64<HDP, TMA>(tmem + 256 + HDP, pta, qda + (g % NST) * 2 * TK + TK, gj > 0);   // dV += P^T dO_g
-        mma_accum64<HDP, TMA>(tmem + 256, dsta, qda + (g % NST) * 2 * TK, gj > 0);             // dK += dS^T Q_g
+        const uint64_t dq = desc_mn64(qda + (g % NST) * 2 * TK), dd = desc_mn64(qda + (g % NST) * 2 * TK + TK);
+#pragma unroll
+        for (int ks = 0; ks < KT / 16; ++ks) {
+          const uint32_t acc = (gj > 0 || ks > 0) ? 1u : 0u;
+          ptx::umma_bf16_elect(tmem + 256 + HDP, dp0 + ks * KSTEP_K128, dd + ks * KSTEP_MN64, idesc_o, acc);
+          ptx::umma_bf16_elect(tmem + 256, ds0 + ks * KSTEP_K128, dq + ks * KSTEP_MN64, idesc_o, acc);
+        }
         ptx::umma_commit_elect(&empty[g % NST]);
         ptx::umma_commit_elect(&bar2);
         if (++gj == T) gj = 0;
@@ -998,6 +960,8 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dkv_tc_kernel(const Params p, 
       ptx::mbar_wait(&bar1[g & 1], (g >> 1) & 1);
       ptx::tc_fence_after();
       if (j < 8) BWD_TRACE(2, 5 + j * 6);
+      if (g >= 1) ptx::mbar_wait(&bar2, (g - 1) & 1);  // dV / dK accumulation of tile g-1 finished: sPT and sDST are free
+      if (j < 8) BWD_TRACE(2, 6 + j * 6);
       {
         const float* Lq = sL + (g % NST) * KT + half * 32;
         const float* Dq = sD + (g % NST) * KT + half * 32;
@@ -1014,11 +978,8 @@ __global__ void __launch_bounds__(NT, 1) attn_bwd_dkv_tc_kernel(const Params p, 
           if (i >= nq) pv[i] = 0.f;
           ds[i] = pv[i] * (__uint_as_float(vd[i]) - Dq[i]);
         }
-        // sPT / sDST are free once the dV / dK accumulation of tile g-1 has finished (it ran during this tile's arithmetic)
-        if (g >= 1) ptx::mbar_wait(&bar2, (g - 1) & 1);
-        if (j < 8) BWD_TRACE(2, 6 + j * 6);
-        store_p32<TMA>(sPT, r, half * 32, pv);
-        store_p32<TMA>(sDST, r, half * 32, ds);
+        store_bf16x32(sPT + r * 16, half * 32, pv);
+        store_bf16x32(sDST + r * 16, half * 32, ds);
       }
       ptx::fence_proxy_async_smem();
       ptx::tc_fence_before();
@@ -1064,38 +1025,49 @@ struct dlb_attn_seg {
   int32_t len;
 };
 
+#include <cudaTypedefs.h>
 #include <cstdlib>
-#include "attn_sw_host.cuh"
+#include <unordered_map>
 
 namespace {
-// swizzled-tile tensor maps (main + tail) of the tensors a kernel reads, per segment; `which` lists T_* indices
-int fill_maps(attn_tc::BwdMaps& maps, const dlb_attn_seg* segs, int nseg, int B, int H, int hd, int hdp, const int* which, int nwhich) {
-  for (int i = 0; i < nseg; ++i) {
-    const dlb_attn_seg& g = segs[i];
-    const int64_t rows = (int64_t)B * g.len;
-    for (int w = 0; w < nwhich; ++w) {
-      const void* ptr; int64_t ld;
-      switch (which[w]) {
-        case attn_tc::T_Q: ptr = g.q; ld = g.ldq; break;
-        case attn_tc::T_K: ptr = g.k; ld = g.ldk; break;
-        case attn_tc::T_V: ptr = g.v; ld = g.ldv; break;
-        case attn_tc::T_DO: ptr = g.dout; ld = g.lddo; break;
-        default: ptr = g.o; ld = g.ldo; break;
-      }
-      int rc = attn_sw_host::head_map3(&maps.m[i][which[w]][0], ptr, rows, ld, H, hd, 0);
-      if (!rc && hdp == 80) rc = attn_sw_host::head_map3(&maps.m[i][which[w]][1], ptr, rows, ld, H, hd, 1);
-      if (rc) return rc;
-    }
+struct MapKey {
+  const void* ptr; int64_t rows, ld; int H, hd, box_rows, cprb;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && ld == o.ld && H == o.H && hd == o.hd && box_rows == o.box_rows && cprb == o.cprb;
   }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    for (int64_t v : {k.rows, k.ld, (int64_t)k.H, (int64_t)k.hd, (int64_t)k.box_rows, (int64_t)k.cprb}) h = h * 1000003u ^ std::hash<int64_t>()(v);
+    return h;
+  }
+};
+// head-slice tensor map of a packed bf16 [rows, ld] activation (cached: the training loop reuses its buffers)
+int head_map(CUtensorMap* out, const void* base, int64_t rows, int64_t ld, int H, int hd, int box_rows, int cprb) {
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  static PFN_cuTensorMapEncodeTiled_v12000 enc = nullptr;
+  const MapKey key{base, rows, ld, H, hd, box_rows, cprb};
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return DLB_OK; }
+  if (!enc) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    const bool ok = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess;
+    DLB_REQUIRE(ok, DLB_ERR_DRIVER, "attn_bwd_tc: cuTensorMapEncodeTiled unavailable");
+    enc = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fp);
+  }
+  cuuint64_t dims[4] = {8, (cuuint64_t)rows, (cuuint64_t)(hd / 8), (cuuint64_t)H};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, 16, (cuuint64_t)hd * 2};
+  cuuint32_t box[4] = {8, (cuuint32_t)box_rows, (cuuint32_t)cprb, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DLB_REQUIRE(r == CUDA_SUCCESS, DLB_ERR_DRIVER, "attn_bwd_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, *out);
   return DLB_OK;
-}
-// the swizzled TMA path needs whole 128-row tiles per segment, 16-byte aligned head slices and a supported padded head dim
-bool sw_eligible(const dlb_attn_seg* segs, int nseg, int hd) {
-  const int hdp16 = (hd + 15) / 16 * 16;
-  if (!(hdp16 <= 64 || hdp16 == 80 || hdp16 > 96)) return false;
-  for (int i = 0; i < nseg; ++i)
-    if (segs[i].len <= 0 || segs[i].len % 128 != 0) return false;
-  return getenv("DLB_ATTN_NO_TMA") == nullptr;  // tests: force the cp.async producers on TMA-eligible shapes
 }
 }  // namespace
 
@@ -1148,25 +1120,27 @@ DLB_EXPORT int dlb_attn_fwd_tc(const dlb_attn_seg* segs, int nseg, float* lse, c
   if (!simple) {
     const int nitems = ((p.S + 127) / 128) * H * B, T = (p.S + 63) / 64;
     const int sms = dlb_num_sms();
-    const bool use_tma = sw_eligible(segs, nseg, hd);
+    bool use_tma = true;
+    for (int i = 0; i < nseg; ++i) use_tma = use_tma && segs[i].len > 0 && segs[i].len % 128 == 0;
+    if (getenv("DLB_ATTN_NO_TMA") != nullptr) use_tma = false;  // tests: force the cp.async producers on TMA-eligible shapes
     HDP_SWITCH_TC(hd, {
       constexpr int RES_F = HDPV <= 80 ? 2 : 1, NST_F = HDPV <= 96 ? 4 : 3;
-      const size_t smem = (size_t)RES_F * 128 * HDPV * 2 + (size_t)NST_F * 2 * 64 * HDPV * 2 + 2 * 16384 + (size_t)128 * HDPV * 2 + 1024 * 4 + 1024;
+      const size_t smem = (size_t)RES_F * 128 * HDPV * 2 + (size_t)NST_F * 2 * 64 * HDPV * 2 + 16384 + (size_t)128 * HDPV * 2 + 1024 * 4;
       const int grid_f = (RES_F == 2 && T >= NST_F && nitems > sms) ? sms : nitems;
       static BwdMaps maps;
-      bool launched = false;
-      if constexpr (HDPV != 96) {
-        if (use_tma) {
-          const int which[3] = {T_Q, T_K, T_V};
-          rc = fill_maps(maps, segs, nseg, B, H, hd, HDPV, which, 3);
+      if (use_tma) {
+        for (int i = 0; i < nseg; ++i) {
+          const dlb_attn_seg& g = segs[i];
+          const int64_t rows = (int64_t)B * g.len;
+          rc = head_map(&maps.m[i][M_Q128], g.q, rows, g.ldq, H, hd, 128, HDPV / 8);
+          if (!rc) rc = head_map(&maps.m[i][M_K64], g.k, rows, g.ldk, H, hd, 64, HDPV / 8);
+          if (!rc) rc = head_map(&maps.m[i][M_V64], g.v, rows, g.ldv, H, hd, 64, HDPV / 8);
           if (rc) return rc;
-          cudaError_t e = cudaFuncSetAttribute(attn_fwd_ws_tc_kernel<HDPV, RES_F, NST_F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-          DLB_REQUIRE(e == cudaSuccess, (int)e, "attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-          attn_fwd_ws_tc_kernel<HDPV, RES_F, NST_F, true><<<grid_f, NT, smem, stream>>>(p, maps);
-          launched = true;
         }
-      }
-      if (!launched) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_ws_tc_kernel<HDPV, RES_F, NST_F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        DLB_REQUIRE(e == cudaSuccess, (int)e, "attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attn_fwd_ws_tc_kernel<HDPV, RES_F, NST_F, true><<<grid_f, NT, smem, stream>>>(p, maps);
+      } else {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_ws_tc_kernel<HDPV, RES_F, NST_F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         DLB_REQUIRE(e == cudaSuccess, (int)e, "attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attn_fwd_ws_tc_kernel<HDPV, RES_F, NST_F, false><<<grid_f, NT, smem, stream>>>(p, maps);
@@ -1197,35 +1171,45 @@ DLB_EXPORT int dlb_attn_bwd_tc(const dlb_attn_seg* segs, int nseg, const float* 
   if (rc) return rc;
   const int nitems = ((p.S + 127) / 128) * H * B, T = (p.S + 63) / 64;
   const int sms = dlb_num_sms();
-  // TMA producer: every tile lies inside one segment and lse / dsum rows are 16-byte aligned
-  const bool use_tma = sw_eligible(segs, nseg, hd);
+  bool use_tma = true;  // TMA producer: every tile lies inside one segment and lse / dsum rows are 16-byte aligned
+  for (int i = 0; i < nseg; ++i) use_tma = use_tma && segs[i].len > 0 && segs[i].len % 128 == 0;
+    if (getenv("DLB_ATTN_NO_TMA") != nullptr) use_tma = false;  // tests: force the cp.async producers on TMA-eligible shapes
   HDP_SWITCH_TC(hd, {
     // resident double-buffering (persistent CTAs) where shared memory allows; otherwise one item per CTA
     constexpr int RES_DQ = HDPV <= 80 ? 2 : 1, NST_DQ = HDPV <= 96 ? 4 : 3;
-    constexpr int RES_DKV = HDPV <= 96 ? 2 : 1, NST_DKV = HDPV <= 96 ? 4 : 3;
-    const size_t sm_dq = (size_t)RES_DQ * 3 * 128 * HDPV * 2 + (size_t)NST_DQ * 2 * 64 * HDPV * 2 + 16384 + RES_DQ * 128 * 4 + 512 * 4 + 1024;
-    const size_t sm_dkv = (size_t)RES_DKV * 2 * 128 * HDPV * 2 + (size_t)NST_DKV * 2 * 64 * HDPV * 2 + 32768 + 2 * NST_DKV * 64 * 4 + 1024;
+    constexpr int RES_DKV = HDPV <= 96 ? 2 : 1, NST_DKV = 4;
+    const size_t sm_dq = (size_t)RES_DQ * 3 * 128 * HDPV * 2 + (size_t)NST_DQ * 2 * 64 * HDPV * 2 + 16384 + RES_DQ * 128 * 4 + 512 * 4;
+    const size_t sm_dkv = (size_t)RES_DKV * 2 * 128 * HDPV * 2 + (size_t)NST_DKV * 2 * 64 * HDPV * 2 + 32768 + 2 * NST_DKV * 64 * 4;
     const int grid_dq = (RES_DQ == 2 && T >= NST_DQ && nitems > sms) ? sms : nitems;
     const int grid_dkv = (RES_DKV == 2 && T >= NST_DKV && nitems > sms) ? sms : nitems;
     static BwdMaps maps;  // by-value kernel parameter; contents only read on the TMA path
-    bool launched = false;
-    if constexpr (HDPV != 96) {
-      if (use_tma) {
-        const int which[5] = {T_Q, T_K, T_V, T_DO, T_O};
-        rc = fill_maps(maps, segs, nseg, B, H, hd, HDPV, which, 5);
-        if (rc) return rc;
-        cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<HDPV, RES_DQ, NST_DQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dq);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<HDPV, RES_DKV, NST_DKV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dkv);
-        DLB_REQUIRE(e == cudaSuccess, (int)e, "attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attn_bwd_dq_tc_kernel<HDPV, RES_DQ, NST_DQ, true><<<grid_dq, NT, sm_dq, stream>>>(p, maps);
-        attn_bwd_dkv_tc_kernel<HDPV, RES_DKV, NST_DKV, true><<<grid_dkv, NT, sm_dkv, stream>>>(p, maps);
-        launched = true;
+    if (use_tma) {
+      for (int i = 0; i < nseg; ++i) {
+        const dlb_attn_seg& g = segs[i];
+        const int64_t rows = (int64_t)B * g.len;
+        const struct { int idx; const void* ptr; int64_t ld; int box; } want[M_COUNT] = {
+            {M_Q64, g.q, g.ldq, 64}, {M_Q128, g.q, g.ldq, 128}, {M_K64, g.k, g.ldk, 64}, {M_K128, g.k, g.ldk, 128},
+            {M_V64, g.v, g.ldv, 64}, {M_V128, g.v, g.ldv, 128}, {M_DO64, g.dout, g.lddo, 64}, {M_DO128, g.dout, g.lddo, 128},
+            {M_O128, g.o, g.ldo, 128}};
+        for (const auto& w : want) {
+          rc = head_map(&maps.m[i][w.idx], w.ptr, rows, w.ld, H, hd, w.box, HDPV / 8);
+          if (rc) return rc;
+        }
       }
     }
-    if (!launched) {
-      cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<HDPV, RES_DQ, NST_DQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dq);
+    cudaError_t e = cudaSuccess;
+    if (use_tma) {
+      e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<HDPV, RES_DQ, NST_DQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dq);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<HDPV, RES_DKV, NST_DKV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dkv);
+    } else {
+      e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<HDPV, RES_DQ, NST_DQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dq);
       if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<HDPV, RES_DKV, NST_DKV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_dkv);
-      DLB_REQUIRE(e == cudaSuccess, (int)e, "attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    DLB_REQUIRE(e == cudaSuccess, (int)e, "attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    if (use_tma) {
+      attn_bwd_dq_tc_kernel<HDPV, RES_DQ, NST_DQ, true><<<grid_dq, NT, sm_dq, stream>>>(p, maps);
+      attn_bwd_dkv_tc_kernel<HDPV, RES_DKV, NST_DKV, true><<<grid_dkv, NT, sm_dkv, stream>>>(p, maps);
+    } else {
       attn_bwd_dq_tc_kernel<HDPV, RES_DQ, NST_DQ, false><<<grid_dq, NT, sm_dq, stream>>>(p, maps);
       attn_bwd_dkv_tc_kernel<HDPV, RES_DKV, NST_DKV, false><<<grid_dkv, NT, sm_dkv, stream>>>(p, maps);
     }

@@ -104,6 +104,64 @@ __global__ void silu_bwd_kernel(const TG* __restrict__ dy, const TIn* __restrict
     dx[i] = (TOut)((float)dy[i] * dsilu_f((float)x[i]));
 }
 
+// exact (erf) GELU on bf16 rows, 8 channels per thread: y = x Phi(x); backward dx = dy (Phi(x) + x phi(x))   (nn.GELU default,
+// the PerceiverResampler feed-forward, reference networks/repa/perceiver_resampler.py:75-77)
+__global__ void gelu_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int64_t n8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float f[8];
+    unpack8(ld8(x + i * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
+    st8(y + i * 8, pack8(f));
+  }
+}
+__global__ void gelu_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, bf16* __restrict__ dx, int64_t n8) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    float f[8], g[8];
+    unpack8(ld8(x + i * 8), f);
+    unpack8(ld8(dy + i * 8), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float cdf = 0.5f * (1.f + erff(f[j] * 0.70710678118654752f));
+      const float pdf = 0.3989422804014327f * __expf(-0.5f * f[j] * f[j]);
+      g[j] *= cdf + f[j] * pdf;
+    }
+    st8(dx + i * 8, pack8(g));
+  }
+}
+
+// N-D interleaved-pair RoPE applied to the heads of a packed bf16 [R, ld] tensor (H heads of hd channels from column 0), in
+// place or out of place; `inverse` applies the transposed rotation (the backward pass). No normalisation, no scale: the
+// key-only rotation of the PerceiverResampler (reference perceiver_resampler.py:13-56). One thread per 8-channel vector.
+__global__ void rope_apply_kernel(const bf16* __restrict__ x, int64_t ld_in, bf16* __restrict__ y, int64_t ld_out, const uint32_t* __restrict__ cs_t,
+                                  int rot_half, const int32_t* __restrict__ pos_idx, int pos_offset, int tokens_per_sample, int hd, int d,
+                                  int64_t R, int inverse) {
+  const int nv = d >> 3;
+  const int64_t total = R * nv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / nv;
+    const int c = (int)(i - row * nv) * 8;
+    const int cl = c % hd;
+    const uint32_t* csr = cs_t + (int64_t)(pos_idx ? pos_idx[row] : pos_offset + (int)(row % tokens_per_sample)) * rot_half;
+    float f[8];
+    unpack8(ld8(x + row * ld_in + c), f);
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const int pj = (cl + j) >> 1;
+      if (pj < rot_half) {
+        const uint32_t cs = __ldg(csr + pj);
+        const float co = __uint_as_float(cs << 16);
+        float sn = __uint_as_float(cs & 0xffff0000u);
+        if (inverse) sn = -sn;
+        const float e = f[j], o = f[j + 1];
+        f[j] = e * co - o * sn;
+        f[j + 1] = e * sn + o * co;
+      }
+    }
+    st8(y + row * ld_out + c, pack8(f));
+  }
+}
+
 // te[b, :] = [cos(t_b f_i) | sin(t_b f_i)], f_i = exp(-ln(max_period) i / half); bf16 output (GEMM operand).
 __global__ void timestep_embed_kernel(const float* __restrict__ t, bf16* __restrict__ out, int B, int dim,
                                       float max_period) {
@@ -364,4 +422,28 @@ DLB_EXPORT int dlb_colsum(const void* in, int in_dtype, int64_t ld, float* out, 
   else colsum_kernel<float><<<grid, 256, 0, stream>>>((const float*)in, ld, out, R, Cn, rpb);
   dlb_count_launch();
   return dlb_check_launch("colsum");
+}
+
+DLB_EXPORT int dlb_gelu_fwd(const void* x, void* y, int64_t n, cudaStream_t stream) {
+  DLB_REQUIRE(n > 0 && n % 8 == 0, DLB_ERR_SHAPE, "gelu_fwd: element count must be a positive multiple of 8");
+  gelu_fwd_kernel<<<grid_for(n / 8), 256, 0, stream>>>((const bf16*)x, (bf16*)y, n / 8);
+  dlb_count_launch();
+  return dlb_check_launch("gelu_fwd");
+}
+DLB_EXPORT int dlb_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, cudaStream_t stream) {
+  DLB_REQUIRE(n > 0 && n % 8 == 0, DLB_ERR_SHAPE, "gelu_bwd: element count must be a positive multiple of 8");
+  gelu_bwd_kernel<<<grid_for(n / 8), 256, 0, stream>>>((const bf16*)dy, (const bf16*)x, (bf16*)dx, n / 8);
+  dlb_count_launch();
+  return dlb_check_launch("gelu_bwd");
+}
+// x, y: bf16 [R, ld] (y may alias x); cs_t: packed bf16x2 (cos, sin) table [positions, rot_half] as written by dlb_rope_table
+DLB_EXPORT int dlb_rope_apply(const void* x, int64_t ld_in, void* y, int64_t ld_out, const uint32_t* cs_t, int rot_half, const int32_t* pos_idx,
+                              int pos_offset, int tokens_per_sample, int hd, int d, int64_t R, int inverse, cudaStream_t stream) {
+  DLB_REQUIRE(R > 0 && d > 0 && d % 8 == 0 && hd > 0 && hd % 8 == 0 && d % hd == 0 && 2 * rot_half <= hd && ld_in % 8 == 0 && ld_out % 8 == 0,
+              DLB_ERR_SHAPE, "rope_apply: bad shape R=%lld d=%d hd=%d rot_half=%d", (long long)R, d, hd, rot_half);
+  DLB_REQUIRE(pos_idx != nullptr || tokens_per_sample > 0, DLB_ERR_SHAPE, "rope_apply: tokens_per_sample required without pos_idx");
+  rope_apply_kernel<<<grid_for(R * (d / 8)), 256, 0, stream>>>((const bf16*)x, ld_in, (bf16*)y, ld_out, cs_t, rot_half, pos_idx, pos_offset,
+                                                               tokens_per_sample > 0 ? tokens_per_sample : 1, hd, d, R, inverse);
+  dlb_count_launch();
+  return dlb_check_launch("rope_apply");
 }

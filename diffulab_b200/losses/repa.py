@@ -46,6 +46,53 @@ class _RepaProjCosFn(torch.autograd.Function):
         return (df.view(ctx.fshape) if df is not None else None), None, None, None, None, None, None, None, None
 
 
+class _RepaProjFn(torch.autograd.Function):
+    """The 3-layer SiLU projector alone (used when a PerceiverResampler sits between projector and cosine)."""
+
+    @staticmethod
+    def forward(ctx, feats: Tensor, w0, b0, w1, b1, w2, b2):
+        f2 = feats.reshape(-1, feats.shape[-1])
+        if not f2.is_contiguous():
+            f2 = f2.contiguous()
+        z1 = K.linear_fwd(f2, w0, b0)
+        a1 = ops.silu_fwd(z1)
+        z2 = K.linear_fwd(a1, w1, b1)
+        a2 = ops.silu_fwd(z2)
+        s = K.linear_fwd(a2, w2, b2)
+        ctx.save_for_backward(f2, z1, a1, z2, a2)
+        ctx.p, ctx.fshape = (w0, b0, w1, b1, w2, b2), feats.shape
+        return s.view(*feats.shape[:-1], s.shape[-1])
+
+    @staticmethod
+    def backward(ctx, ds: Tensor):
+        f2, z1, a1, z2, a2 = ctx.saved_tensors
+        w0, b0, w1, b1, w2, b2 = ctx.p
+        ds2 = ds.reshape(-1, ds.shape[-1]).contiguous()
+        da2 = K.linear_bwd(ds2, a2, w2, b2)
+        dz2 = ops.silu_bwd(da2, z2, torch.bfloat16)
+        da1 = K.linear_bwd(dz2, a1, w1, b1)
+        dz1 = ops.silu_bwd(da1, z1, torch.bfloat16)
+        df = K.linear_bwd(dz1, f2, w0, b0, need_dx=ctx.needs_input_grad[0])
+        return (df.view(ctx.fshape) if df is not None else None), None, None, None, None, None, None
+
+
+class _CosFn(torch.autograd.Function):
+    """coeff * (1 - mean cosine similarity) between bf16 projected features and fp32 targets (fused kernels)."""
+
+    @staticmethod
+    def forward(ctx, s: Tensor, dst: Tensor, coeff: float):
+        s2 = s.reshape(-1, s.shape[-1]).contiguous()
+        d2 = dst.reshape(-1, dst.shape[-1]).to(torch.float32).contiguous()
+        ctx.save_for_backward(s2, d2)
+        ctx.coeff, ctx.shape = coeff, s.shape
+        return ops.repa_cos_fwd(s2, d2, coeff)
+
+    @staticmethod
+    def backward(ctx, gout: Tensor):
+        s2, d2 = ctx.saved_tensors
+        return ops.repa_cos_bwd(s2, d2, ctx.coeff, gout.to(torch.float32).contiguous()).view(ctx.shape), None, None
+
+
 class RepaLoss(LossFunction):
     name: str = "RepaLoss"
 
@@ -68,14 +115,17 @@ class RepaLoss(LossFunction):
                 "diffulab_b200.RepaLoss aligns against precomputed features (`dst_features`); the frozen DINO tower is "
                 "outside the accelerated hot path (pass load_dino=False)"
             )
-        if use_resampler:
-            raise NotImplementedError("PerceiverResampler is not part of the accelerated hot path (SURVEY.md 8f-3)")
         self.repa_encoder = None
         self.proj = nn.Sequential(
             nn.Linear(denoiser_dimension, hidden_dim), nn.SiLU(), nn.Linear(hidden_dim, hidden_dim), nn.SiLU(),
             nn.Linear(hidden_dim, embedding_dim),
         )
         self.resampler = None
+        if use_resampler:
+            assert resampler_params is not None, "Resampler parameters must be provided when using the perceiver resampler."
+            from .perceiver import PerceiverResampler
+
+            self.resampler = PerceiverResampler(**resampler_params)
         self.alignment_layer = alignment_layer
         self._handles: dict[int, RemovableHandle] = {}
         self._captured_features: dict[int, Tensor] = {}
@@ -111,5 +161,9 @@ class RepaLoss(LossFunction):
         if isinstance(src, tuple):
             src = src[0]
         p = self.proj
+        if self.resampler is not None:  # proj -> PerceiverResampler -> cosine (reference repa.py:180-186)
+            s = _RepaProjFn.apply(src, p[0].weight, p[0].bias, p[2].weight, p[2].bias, p[4].weight, p[4].bias)
+            s = self.resampler(s)
+            return _CosFn.apply(s, dst_features, float(self.coeff))
         return _RepaProjCosFn.apply(src, dst_features, float(self.coeff), p[0].weight, p[0].bias, p[2].weight, p[2].bias,
                                     p[4].weight, p[4].bias)

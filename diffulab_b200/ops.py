@@ -387,6 +387,16 @@ def _seg_array(specs, outs, douts=None, dqks=None, dqkvs=None):
     for i, s in enumerate(specs):
         d = s.d
         e = arr[i]
+        if isinstance(s, AttnSegViews):
+            e.q, e.k, e.v = s.q.data_ptr(), s.k.data_ptr(), s.v.data_ptr()
+            e.ldq, e.ldk, e.ldv = s.q.stride(0), s.k.stride(0), s.v.stride(0)
+            e.o, e.ldo, e.len = outs[i].data_ptr(), outs[i].stride(0), s.len
+            if douts is not None:
+                dq, dk, dv = dqks[i]
+                e.dout, e.lddo = douts[i].data_ptr(), douts[i].stride(0)
+                e.dq, e.dk, e.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+                e.lddq, e.lddk, e.lddv = dq.stride(0), dk.stride(0), dv.stride(0)
+            continue
         e.q = s.qk.data_ptr()
         e.k = s.qk.data_ptr() + d * 2
         e.v = s.qkv.data_ptr() + 2 * d * 2
@@ -406,12 +416,23 @@ def _seg_array(specs, outs, douts=None, dqks=None, dqkvs=None):
     return arr
 
 
+class AttnSegViews:
+    """One sequence segment given as explicit 2-D bf16 views q, k, v [B*len, d] (unit inner stride, any row stride): the general
+    form of AttnSegSpec (cross-attention layouts such as the PerceiverResampler's)."""
+
+    def __init__(self, q: Tensor, k: Tensor, v: Tensor, length: int):
+        for name, t in (("q", q), ("k", k), ("v", v)):
+            _check_2d(t, name)
+        self.q, self.k, self.v, self.len = q, k, v, length
+        self.d = q.shape[-1]
+
+
 ATTN_FWD_IMPL = "dlb_attn_fwd_tc"  # tcgen05 forward; "dlb_attn_fwd" is the mma.sync kernel (kept for comparison tests)
 
 
 def attn_fwd(specs: list[AttnSegSpec], B: int, H: int, hd: int, scale: float, kmask: Tensor | None = None, impl: str | None = None):
     S = sum(s.len for s in specs)
-    dev = specs[0].qk.device
+    dev = (specs[0].q if isinstance(specs[0], AttnSegViews) else specs[0].qk).device
     outs = [torch.empty(B * s.len, s.d, device=dev, dtype=BF16) for s in specs]
     lse = torch.empty(B, H, S, device=dev, dtype=F32)
     arr = _seg_array(specs, outs)
@@ -439,6 +460,19 @@ def attn_bwd(specs: list[AttnSegSpec], outs: list[Tensor], douts: list[Tensor], 
     _lib_call(impl or ATTN_BWD_IMPL, C.cast(arr, C.c_void_p), len(specs), lse.data_ptr(), dsum.data_ptr(), _ptr(kmask), mask_len,
               B, H, hd, scale, _stream())
     return dqks
+
+
+def attn_bwd_views(specs: list[AttnSegViews], outs: list[Tensor], douts: list[Tensor], lse: Tensor, B: int, H: int, hd: int, scale: float,
+                   kmask: Tensor | None = None) -> list[tuple[Tensor, Tensor, Tensor]]:
+    """Backward of attn_fwd over AttnSegViews segments -> per segment (dq, dk, dv), each [B*len, d] bf16."""
+    dev = specs[0].q.device
+    grads = [tuple(torch.empty(B * s.len, s.d, device=dev, dtype=BF16) for _ in range(3)) for s in specs]
+    dsum = torch.empty_like(lse)
+    arr = _seg_array(specs, outs, douts, grads, None)
+    mask_len = kmask.shape[1] if kmask is not None else 0
+    import ctypes as C
+    _lib_call(ATTN_BWD_IMPL, C.cast(arr, C.c_void_p), len(specs), lse.data_ptr(), dsum.data_ptr(), _ptr(kmask), mask_len, B, H, hd, scale, _stream())
+    return grads
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -477,6 +511,35 @@ def add(a: Tensor, b: Tensor) -> Tensor:
     _req(b, BF16, "b")
     out = torch.empty_like(a)
     _lib_call("dlb_add_bf16", a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), _stream())
+    return out
+
+
+def gelu_fwd(x: Tensor) -> Tensor:
+    _req(x, BF16, "x")
+    y = torch.empty_like(x)
+    _lib_call("dlb_gelu_fwd", x.data_ptr(), y.data_ptr(), x.numel(), _stream())
+    return y
+
+
+def gelu_bwd(dy: Tensor, x: Tensor) -> Tensor:
+    _req(dy, BF16, "dy")
+    _req(x, BF16, "x")
+    dx = torch.empty_like(x)
+    _lib_call("dlb_gelu_bwd", dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel(), _stream())
+    return dx
+
+
+def rope_apply(x: Tensor, rope: "RopeTable", hd: int, *, tokens_per_sample: int, pos_offset: int = 0, pos_idx: Tensor | None = None,
+               inverse: bool = False, out: Tensor | None = None) -> Tensor:
+    """RoPE (no norm / scale) on the heads of a 2-D bf16 [R, d] view (row stride allowed); inverse = transposed rotation."""
+    _check_2d(x, "x")
+    if x.dtype != BF16:
+        raise ValueError("rope_apply: expected bfloat16")
+    R, d = x.shape
+    if out is None:
+        out = torch.empty(R, d, device=x.device, dtype=BF16)
+    _lib_call("dlb_rope_apply", x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), rope.cs.data_ptr(), rope.cs.shape[-1], _ptr(pos_idx),
+              pos_offset, tokens_per_sample, hd, d, R, int(inverse), _stream())
     return out
 
 

@@ -147,6 +147,14 @@ int dlb_attn_bwd_tc(const dlb_attn_seg* segs, int nseg, const float* lse, float*
  * kernel (slots 0..63 forward, 64..127 dq, 128..191 dkv); NULL switches tracing off (the default) */
 int dlb_attn_set_trace(long long* dev_buf);
 
+/* exact (erf) GELU forward / backward on bf16 (nn.GELU default; PerceiverResampler feed-forward, perceiver_resampler.py:75-77) */
+int dlb_gelu_fwd(const void* x, void* y, int64_t n, dlb_stream_t stream);
+int dlb_gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, dlb_stream_t stream);
+/* N-D interleaved-pair RoPE on the heads of a packed bf16 [R, ld] tensor, no norm / scale (key-only rotation of the
+ * PerceiverResampler, perceiver_resampler.py:13-56); inverse = 1 applies the transposed rotation (backward) */
+int dlb_rope_apply(const void* x, int64_t ld_in, void* y, int64_t ld_out, const uint32_t* cs_t, int rot_half, const int32_t* pos_idx,
+                   int pos_offset, int tokens_per_sample, int hd, int d, int64_t R, int inverse, dlb_stream_t stream);
+
 /* ---- glue ------------------------------------------------------------------------------------------------ */
 int dlb_cast_f32_bf16(const float* in, void* out, int64_t rows, int64_t cols, int64_t ld_out, dlb_stream_t stream);
 int dlb_cast_bf16_f32(const void* in, float* out, int64_t n, dlb_stream_t stream);

@@ -485,6 +485,52 @@ def repa_loss(sd_repa: SD, feats: Tensor, dst: Tensor, coeff: float) -> Tensor:
     return coeff * (1 - (dot / (ns * nz)).mean())
 
 
+def perceiver_resampler(sd: SD, x: Tensor, num_heads: int, head_dim: int, rope_axes_dim: list[int], rope_base: float, prefix: str = "") -> Tensor:
+    """PerceiverResampler.forward networks/repa/perceiver_resampler.py:90-252 (PerceiverAttention :119-166, FeedForward :59-77).
+    The reference builds un-batched position ids and then indexes the tables with a batch dimension (IndexError, SURVEY.md
+    4.3-3); the tables are sample-independent, so they are used un-batched here (golden fixtures call the reference with
+    explicitly batched `cos_sin`, which is the same arithmetic). Key-only RoPE on the input tokens' keys; latents attend over
+    cat(x keys, latent keys)."""
+    B, N, dim = x.shape
+    H, hd = num_heads, head_dim
+    hw = int(N**0.5)
+    cos, sin = rope_tables(pos_ids_2d(hw, hw).to(x.device), rope_axes_dim, rope_base)
+    lat = sd[f"{prefix}latents"].to(x.dtype)[None].expand(B, -1, -1)
+    M = lat.shape[1]
+    n_layers = n_blocks(sd, f"{prefix}layers") if prefix else max(int(k.split(".")[1]) for k in sd if k.startswith("layers.")) + 1
+    for i in range(n_layers):
+        a, f = f"{prefix}layers.{i}.0", f"{prefix}layers.{i}.1"
+        xn = r(layer_norm(x, sd[f"{a}.norm_x.weight"], sd[f"{a}.norm_x.bias"], 1e-5))
+        ln = r(layer_norm(lat, sd[f"{a}.norm_latents.weight"], sd[f"{a}.norm_latents.bias"], 1e-5))
+        q = linear(ln, sd[f"{a}.to_q.weight"]).view(B, M, H, hd)
+        kx, vx = linear(xn, sd[f"{a}.to_kv.weight"]).chunk(2, dim=-1)
+        kl, vl = linear(ln, sd[f"{a}.to_kv.weight"]).chunk(2, dim=-1)
+        kx = apply_rope(kx.reshape(B, N, H, hd), cos, sin)
+        k = torch.cat([kx, kl.reshape(B, M, H, hd)], 1)
+        v = torch.cat([vx.reshape(B, N, H, hd), vl.reshape(B, M, H, hd)], 1)
+        sim = torch.einsum("bihd,bjhd->bhij", r(q * hd**-0.5), k)
+        attn = r((sim - sim.amax(dim=-1, keepdim=True)).softmax(-1))
+        o = r(torch.einsum("bhij,bjhd->bihd", attn, v)).reshape(B, M, H * hd)
+        lat = r(linear(o, sd[f"{a}.to_out.weight"]) + lat)
+        h = r(layer_norm(lat, sd[f"{f}.0.weight"], sd[f"{f}.0.bias"], 1e-5))
+        h = r(F.gelu(linear(h, sd[f"{f}.1.weight"])))
+        lat = r(linear(h, sd[f"{f}.3.weight"]) + lat)
+    return r(layer_norm(lat, sd[f"{prefix}norm.weight"], sd[f"{prefix}norm.bias"], 1e-5))
+
+
+def repa_loss_resampled(sd_repa: SD, feats: Tensor, dst: Tensor, coeff: float, resampler_kw: dict) -> Tensor:
+    """RepaLoss.forward with use_resampler=True (training/losses/repa.py:176-186): proj -> PerceiverResampler -> cosine."""
+    h = r(F.silu(linear(feats, sd_repa["proj.0.weight"], sd_repa["proj.0.bias"])))
+    h = r(F.silu(linear(h, sd_repa["proj.2.weight"], sd_repa["proj.2.bias"])))
+    s = linear(h, sd_repa["proj.4.weight"], sd_repa["proj.4.bias"])
+    s = perceiver_resampler(sd_repa, s, resampler_kw["num_heads"], resampler_kw["head_dim"], resampler_kw["rope_axes_dim"],
+                            resampler_kw.get("rope_base", 10000), prefix="resampler.").float()
+    dot = (s * dst).sum(-1)
+    ns = s.norm(dim=-1).clamp_min(1e-8)
+    nz = dst.norm(dim=-1).clamp_min(1e-8)
+    return coeff * (1 - (dot / (ns * nz)).mean())
+
+
 def euler_step(x: Tensor, v: Tensor, t_curr: float, t_prev: float) -> tuple[Tensor, Tensor]:
     """Euler.step samplers/flow/euler.py:37-39"""
     return x - v * (t_curr - t_prev), x - v * t_curr
