@@ -62,7 +62,7 @@ _SIGNATURES: dict[str, list] = {
     # x, v, v_dtype, noise, x_prev_in, c, one_minus_t, dt, t_curr, std, x_prev, mean, x0_est, logprob, n, stream
     "dlb_euler_maruyama_step": [p, p, i32, p, p, f32, f32, f32, f32, f32, p, p, p, p, i64, p],
     # pred, pred_dtype, xt, noise, table, t, sampler, mean_type, clamp, eta, B, per_sample, x_prev, x0, mean, logprob, stream
-    "dlb_gaussian_step": [p, i32, p, p, p, p, i32, i32, i32, f32, i64, i64, p, p, p, p, p],
+    "dlb_gaussian_step": [p, i32, p, p, p, p, i32, i32, i32, i32, f32, i64, i64, p, p, p, p, p, p],
     "dlb_add_bf16": [p, p, p, i64, p],
     "dlb_gelu_fwd": [p, p, i64, p],
     "dlb_gelu_bwd": [p, p, p, i64, p],

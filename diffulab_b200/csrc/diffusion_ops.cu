@@ -257,24 +257,31 @@ __global__ void euler_step_kernel(const float* __restrict__ x, const TV* __restr
 // mean + mask * std * noise and the per-element log-probability, in one pass. All schedule-dependent scalars come
 // from a per-timestep fp32 table built on the host from the float64 schedule exactly as `extract_into_tensor` yields
 // them (GS_* columns); arithmetic keeps the reference's operation order (no FMA contraction) so results agree to ~1 ulp.
-enum { GS_RSAB = 0, GS_CEPS, GS_RC1, GS_C2C1, GS_C1, GS_C2, GS_VAR, GS_STD, GS_MASK, GS_EDEN, GS_SABP, GS_SA, GS_SB, GS_ABP, GS_COLS = 16 };
+enum { GS_RSAB = 0, GS_CEPS, GS_RC1, GS_C2C1, GS_C1, GS_C2, GS_VAR, GS_STD, GS_MASK, GS_EDEN, GS_SABP, GS_SA, GS_SB, GS_ABP, GS_MINLOG, GS_MAXLOG, GS_COLS = 16 };
+// var_mode 0: variance from the table (fixed_small / fixed_large). 1 ("learned") / 2 ("learned_range"): the model output holds
+// 2C channels per sample, [mean prediction | variance head] (torch.chunk(.., 2, dim=1), ddpm.py:268-270): sample b's prediction
+// starts at pred + b * pred_stride and its variance head per_sample elements later; the per-element variance follows
+// ddpm.py:213-223 and the per-element std (x_prev_std of DDPM.step) goes to std_out.
 template <typename TP>
 __global__ void gaussian_step_kernel(const TP* __restrict__ pred, const float* __restrict__ xt, const float* __restrict__ noise,
                                      const float* __restrict__ table, const int* __restrict__ t, int sampler, int mean_type,
-                                     int clamp, float eta, int64_t per_sample, float* __restrict__ x_prev,
-                                     float* __restrict__ x0_out, float* __restrict__ mean_out, float* __restrict__ logprob) {
+                                     int var_mode, int clamp, float eta, int64_t per_sample, int64_t pred_stride,
+                                     float* __restrict__ x_prev, float* __restrict__ x0_out, float* __restrict__ mean_out,
+                                     float* __restrict__ logprob, float* __restrict__ std_out) {
   const int b = blockIdx.y;
   const float* c = table + (int64_t)t[b] * GS_COLS;
   const float r_sab = c[GS_RSAB], c_eps = c[GS_CEPS], r_c1 = c[GS_RC1], c2c1 = c[GS_C2C1], c1 = c[GS_C1], c2 = c[GS_C2];
-  const float var = c[GS_VAR], stdv = c[GS_STD], mask = c[GS_MASK], e_den = c[GS_EDEN], sabp = c[GS_SABP], abp = c[GS_ABP];
+  const float mask = c[GS_MASK], e_den = c[GS_EDEN], sabp = c[GS_SABP], abp = c[GS_ABP];
+  const float min_log = c[GS_MINLOG], max_log = c[GS_MAXLOG];
   const float sigma = __fmul_rn(__fmul_rn(eta, c[GS_SA]), c[GS_SB]);
   const float dir = sqrtf(__fsub_rn(__fsub_rn(1.f, abp), __fmul_rn(sigma, sigma)));
-  const float vs = fmaxf(var, 1e-20f);
-  const float two_vs = __fmul_rn(2.f, vs), lconst = __fmul_rn(logf(__fmul_rn(6.283185307179586f, vs)), 0.5f);
+  float stdv = c[GS_STD], vs = fmaxf(c[GS_VAR], 1e-20f);
+  float two_vs = __fmul_rn(2.f, vs), lconst = __fmul_rn(logf(__fmul_rn(6.283185307179586f, vs)), 0.5f);
   const float two_s2 = __fmul_rn(2.f, __fmul_rn(sigma, sigma)), lsig = logf(sigma), lhalf = __fmul_rn(0.5f, logf(6.283185307179586f));
   const int64_t base = (int64_t)b * per_sample;
+  const TP* pb = pred + (int64_t)b * pred_stride;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_sample; i += (int64_t)gridDim.x * blockDim.x) {
-    const float p = (float)pred[base + i], x = xt[base + i], nz = noise[base + i];
+    const float p = (float)pb[i], x = xt[base + i], nz = noise[base + i];
     float x0;
     if (mean_type == 0) x0 = __fsub_rn(__fmul_rn(r_sab, x), __fmul_rn(c_eps, p));
     else if (mean_type == 1) x0 = p;
@@ -282,6 +289,18 @@ __global__ void gaussian_step_kernel(const TP* __restrict__ pred, const float* _
     if (clamp && x0 == x0) x0 = fminf(fmaxf(x0, -1.f), 1.f);  // NaN propagates, like torch.clamp
     float mean, xp, lp;
     if (sampler == 0) {
+      if (var_mode != 0) {
+        float lv = (float)pb[per_sample + i];
+        if (var_mode == 2) {
+          const float w = __fdiv_rn(__fadd_rn(lv, 1.f), 2.f);
+          lv = __fadd_rn(__fmul_rn(w, max_log), __fmul_rn(__fsub_rn(1.f, w), min_log));
+        }
+        vs = fmaxf(expf(lv), 1e-20f);
+        stdv = expf(__fmul_rn(0.5f, lv));
+        two_vs = __fmul_rn(2.f, vs);
+        lconst = __fmul_rn(logf(__fmul_rn(6.283185307179586f, vs)), 0.5f);
+        std_out[base + i] = sqrtf(vs);
+      }
       mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, x));
       xp = __fadd_rn(mean, __fmul_rn(__fmul_rn(mask, nz), stdv));
       const float d = __fsub_rn(xp, mean);
@@ -496,19 +515,26 @@ DLB_EXPORT int dlb_euler_step(const float* x, const void* vc, const void* vu, in
 }
 
 // table: [n_steps, 16] fp32 (columns GS_*), t: [B] int32 timestep indices into it. sampler 0 = DDPM, 1 = DDIM (eta);
-// mean_type 0 = epsilon, 1 = xstart, 2 = xprev; pred_dtype 0 = bf16, 1 = fp32; logprob may be null.
+// mean_type 0 = epsilon, 1 = xstart, 2 = xprev; var_mode 0 = table, 1 = learned, 2 = learned_range (pred then holds 2 * per_sample
+// elements per sample and std_out receives the per-element std; DDIM ignores the variance head); pred_dtype 0 = bf16, 1 = fp32.
 DLB_EXPORT int dlb_gaussian_step(const void* pred, int pred_dtype, const float* xt, const float* noise, const float* table,
-                                 const int* t, int sampler, int mean_type, int clamp, float eta, int64_t B, int64_t per_sample,
-                                 float* x_prev, float* x0, float* mean, float* logprob, cudaStream_t stream) {
+                                 const int* t, int sampler, int mean_type, int var_mode, int clamp, float eta, int64_t B,
+                                 int64_t per_sample, float* x_prev, float* x0, float* mean, float* logprob, float* std_out,
+                                 cudaStream_t stream) {
   DLB_REQUIRE(B > 0 && B < 65536 && per_sample > 0, DLB_ERR_SHAPE, "gaussian_step: bad shape B=%lld per_sample=%lld", (long long)B, (long long)per_sample);
-  DLB_REQUIRE((sampler == 0 || sampler == 1) && mean_type >= 0 && mean_type <= 2, DLB_ERR_UNSUPPORTED, "gaussian_step: bad sampler / mean_type");
+  DLB_REQUIRE((sampler == 0 || sampler == 1) && mean_type >= 0 && mean_type <= 2 && var_mode >= 0 && var_mode <= 2, DLB_ERR_UNSUPPORTED,
+              "gaussian_step: bad sampler / mean_type / var_mode");
+  DLB_REQUIRE(var_mode == 0 || sampler == 1 || std_out != nullptr, DLB_ERR_UNSUPPORTED, "gaussian_step: learned variance needs std_out");
+  const int64_t pred_stride = var_mode == 0 ? per_sample : 2 * per_sample;
   int gx = (int)((per_sample + 255) / 256);
   if (gx > 1024) gx = 1024;
   dim3 grid(gx, (unsigned)B);
   if (pred_dtype == 0)
-    gaussian_step_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)pred, xt, noise, table, t, sampler, mean_type, clamp, eta, per_sample, x_prev, x0, mean, logprob);
+    gaussian_step_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)pred, xt, noise, table, t, sampler, mean_type, var_mode, clamp, eta, per_sample,
+                                                         pred_stride, x_prev, x0, mean, logprob, std_out);
   else
-    gaussian_step_kernel<float><<<grid, 256, 0, stream>>>((const float*)pred, xt, noise, table, t, sampler, mean_type, clamp, eta, per_sample, x_prev, x0, mean, logprob);
+    gaussian_step_kernel<float><<<grid, 256, 0, stream>>>((const float*)pred, xt, noise, table, t, sampler, mean_type, var_mode, clamp, eta, per_sample,
+                                                          pred_stride, x_prev, x0, mean, logprob, std_out);
   dlb_count_launch();
   return dlb_check_launch("gaussian_step");
 }

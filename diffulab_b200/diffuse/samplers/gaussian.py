@@ -6,8 +6,9 @@ per timestep — each entry computed in float32 from the float64 table value exa
 after `extract_into_tensor` (diffuse/utils.py:6-19). `step` is then a single fused CUDA launch (dlb_gaussian_step):
 x0 from the model output, optional clamp, posterior mean, x_{t-1} = mean + [t>0] * std * noise and the log-probability.
 The noise is drawn with `torch.randn_like` at the same point as in the reference, so seeded runs consume the same
-Philox stream. Learned-variance parameterisations ("learned", "learned_range": the model emits 2C channels) belong to
-the UNet path, which is out of scope — they are rejected.
+Philox stream. Learned-variance parameterisations ("learned", "learned_range", ddpm.py:213-223): the model prediction
+holds 2C channels [mean prediction | variance head]; the same launch reads both halves in place (no torch.chunk copies)
+and also writes the per-element standard deviation. DDIM ignores the variance head, as the reference does.
 """
 
 from __future__ import annotations
@@ -46,8 +47,6 @@ class DDPM(GaussianSampler):
             raise ValueError(f"mean_type must be one of {list(_MEAN_TYPES)}")
         if var_type not in _VAR_TYPES:
             raise ValueError(f"variance_type must be one of {list(_VAR_TYPES)}")
-        if var_type in ("learned", "learned_range"):
-            raise NotImplementedError("learned-variance samplers need the 2C-channel UNet head, which diffulab_b200 does not build")
         self.mean_type = mean_type
         self.var_type = var_type
         self._dev_tables: dict[torch.device, tuple[Tensor, Tensor]] = {}
@@ -69,7 +68,7 @@ class DDPM(GaussianSampler):
         f = lambda a: a.float()  # noqa: E731  (what extract_into_tensor hands to the fp32 arithmetic)
         ab, sab, abp = f(self.alphas_bar), f(self.sqrt_alphas_bar), f(self.alphas_bar_prev)
         c1, c2 = f(self.posterior_mean_coef1), f(self.posterior_mean_coef2)
-        if self.var_type == "fixed_small":
+        if self.var_type != "fixed_large":  # learned types: columns 6 / 7 are unused by the kernel
             var, lv = f(self.posterior_variance), f(self.posterior_log_variance_clipped)
         else:
             seq = torch.cat([self.posterior_variance[1:2], self.betas[1:]])
@@ -90,6 +89,8 @@ class DDPM(GaussianSampler):
         tab[:, 11] = ((torch.ones_like(abp) - abp) / (torch.ones_like(ab) - ab)).sqrt()   # DDIM sigma = eta * [11] * [12]
         tab[:, 12] = (torch.ones_like(ab) - ab / abp).sqrt()
         tab[:, 13] = abp
+        tab[:, 14] = f(self.posterior_log_variance_clipped)    # learned_range: min_log
+        tab[:, 15] = f(self.betas).log()                       #                max_log (fp32 log of the fp32 beta, ddpm.py:219)
         self._table = tab
         self._std = var.clamp_min(1e-20).sqrt()               # x_prev_std of DDPM.step
         self._dev_tables = {}
@@ -104,14 +105,19 @@ class DDPM(GaussianSampler):
         table, std = self._tables(x.device)
         t = timesteps.to(device=x.device, dtype=torch.int32).contiguous()
         noise = torch.randn_like(x)
-        out = ops.gaussian_step(model_prediction, x, noise, table, t, self._sampler_id, _MEAN_TYPES[self.mean_type], clamp_x, eta, want_logprob)
-        return out, t, std
+        var_mode = {"learned": 1, "learned_range": 2}.get(self.var_type, 0)
+        if var_mode and (model_prediction.dim() < 2 or model_prediction.shape[1] != 2 * x.shape[1]):
+            raise ValueError(f"var_type {self.var_type!r}: the model must emit 2 x {x.shape[1]} channels, got {tuple(model_prediction.shape)}")
+        *out, std_el = ops.gaussian_step(model_prediction, x, noise, table, t, self._sampler_id, _MEAN_TYPES[self.mean_type], clamp_x, eta,
+                                         want_logprob, var_mode)
+        return out, t, (std, std_el)
 
     def step(self, model_prediction: Tensor, timesteps: Tensor, xt: Tensor, clamp_x: bool = False) -> StepResult:
-        (x_prev, x0, mean, logprob), t, std = self._run(model_prediction, timesteps, xt, clamp_x, 0.0, True)
+        (x_prev, x0, mean, logprob), t, (std, std_el) = self._run(model_prediction, timesteps, xt, clamp_x, 0.0, True)
         shape = (-1,) + (1,) * (xt.dim() - 1)
         assert logprob is not None
-        return StepResult(x_prev=x_prev, estimated_x0=x0, x_prev_mean=mean, x_prev_std=std[t.long()].view(shape).expand_as(x_prev), logprob=logprob)
+        x_prev_std = std_el if std_el is not None else std[t.long()].view(shape).expand_as(x_prev)
+        return StepResult(x_prev=x_prev, estimated_x0=x0, x_prev_mean=mean, x_prev_std=x_prev_std, logprob=logprob)
 
 
 class DDIM(DDPM):

@@ -29,14 +29,20 @@ class PrecomputedEmbedder(ContextEmbedder):
         )
         self._output_size = (self.null_embedding.shape[-1],)
         self._n_output = 1
+        self._resident: dict = {}  # (device, dtype) -> device copies, so that sampling can be captured in a CUDA graph
+
+    def _null(self, device, dtype) -> tuple[Tensor, Tensor]:
+        key = (str(device), dtype)
+        if key not in self._resident:
+            self._resident[key] = (self.null_embedding.to(device=device, dtype=dtype), self.null_embedding_mask.to(device=device))
+        return self._resident[key]
 
     def drop_conditions(self, context: ContextEmbedderOutput, p: float) -> ContextEmbedderOutput:
         emb = context["embeddings"]
         batch_size = emb.shape[0]
         device, dtype = emb.device, emb.dtype
         drop_mask = torch.rand(batch_size, device=device) < p
-        null_emb = self.null_embedding.to(device=device, dtype=dtype)
-        null_mask = self.null_embedding_mask.to(device=device)
+        null_emb, null_mask = self._null(device, dtype)
         embeddings = torch.where(drop_mask[:, None, None], null_emb.unsqueeze(0).expand(batch_size, -1, -1), emb)
         attn_mask = torch.where(drop_mask[:, None], null_mask.unsqueeze(0).expand(batch_size, -1), context["attn_mask"])
         return {"embeddings": embeddings, "attn_mask": attn_mask}

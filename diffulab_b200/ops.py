@@ -674,8 +674,10 @@ def euler_maruyama_step(x: Tensor, v: Tensor, noise: Tensor | None, x_prev_in: T
 
 
 def gaussian_step(pred: Tensor, xt: Tensor, noise: Tensor, table: Tensor, t: Tensor, sampler: int, mean_type: int, clamp: bool,
-                  eta: float, want_logprob: bool) -> tuple[Tensor, Tensor, Tensor, Tensor | None]:
-    """One fused DDPM (sampler 0) / DDIM (sampler 1) reverse step -> (x_prev, x0, mean, logprob)."""
+                  eta: float, want_logprob: bool, var_mode: int = 0) -> tuple[Tensor, Tensor, Tensor, Tensor | None, Tensor | None]:
+    """One fused DDPM (sampler 0) / DDIM (sampler 1) reverse step -> (x_prev, x0, mean, logprob, std).
+    var_mode 1 / 2 (learned / learned_range): `pred` holds 2C channels [mean prediction | variance head] and `std` is the
+    per-element standard deviation (DDPM); var_mode 0: std is None (it comes from the schedule table)."""
     _req(xt, F32, "xt")
     _req(noise, F32, "noise")
     _req(table, F32, "table")
@@ -683,12 +685,15 @@ def gaussian_step(pred: Tensor, xt: Tensor, noise: Tensor, table: Tensor, t: Ten
         raise ValueError("gaussian_step: timesteps must be a contiguous int32 CUDA tensor")
     pred = pred.contiguous()
     B = xt.shape[0]
+    if pred.numel() != (2 if var_mode else 1) * xt.numel():
+        raise ValueError(f"gaussian_step: prediction has {pred.numel()} elements, expected {(2 if var_mode else 1) * xt.numel()}")
     x_prev, x0, mean = torch.empty_like(xt), torch.empty_like(xt), torch.empty_like(xt)
     logprob = torch.empty_like(xt) if want_logprob else None
+    std = torch.empty_like(xt) if (var_mode and sampler == 0) else None
     _lib_call("dlb_gaussian_step", pred.data_ptr(), _dt(pred), xt.data_ptr(), noise.data_ptr(), table.data_ptr(), t.data_ptr(),
-              int(sampler), int(mean_type), int(bool(clamp)), float(eta), B, xt.numel() // B, x_prev.data_ptr(), x0.data_ptr(),
-              mean.data_ptr(), _ptr(logprob), _stream())
-    return x_prev, x0, mean, logprob
+              int(sampler), int(mean_type), int(var_mode), int(bool(clamp)), float(eta), B, xt.numel() // B, x_prev.data_ptr(), x0.data_ptr(),
+              mean.data_ptr(), _ptr(logprob), _ptr(std), _stream())
+    return x_prev, x0, mean, logprob, std
 
 
 def repa_cos_fwd(s: Tensor, z: Tensor, coeff: float) -> Tensor:

@@ -211,11 +211,16 @@ int dlb_euler_step(const float* x, const void* vc, const void* vu, int v_dtype, 
 /* One reverse step of the Gaussian samplers, fused: replaces DDPM.step / DDIM.step
  * (reference diffuse/samplers/gaussian_diffusion/ddpm.py `_get_p_mean_var` + `step`, ddim.py:27-103).
  * table [n_steps,16] fp32 per-timestep coefficients (columns: 1/sqrt(ab), sqrt(1-ab)/sqrt(ab), 1/c1, c2/c1, c1, c2, var,
- * exp(0.5 logvar), [t>0], sqrt(1/ab-1), sqrt(ab_prev), sqrt((1-ab_prev)/(1-ab)), sqrt(1-ab/ab_prev), ab_prev, 0, 0);
- * t [B] int32; sampler 0 DDPM / 1 DDIM(eta); mean_type 0 epsilon / 1 xstart / 2 xprev; logprob nullable. */
+ * exp(0.5 logvar), [t>0], sqrt(1/ab-1), sqrt(ab_prev), sqrt((1-ab_prev)/(1-ab)), sqrt(1-ab/ab_prev), ab_prev,
+ * posterior_log_variance_clipped, log(beta));
+ * t [B] int32; sampler 0 DDPM / 1 DDIM(eta); mean_type 0 epsilon / 1 xstart / 2 xprev; var_mode 0 fixed (table) /
+ * 1 learned / 2 learned_range (ddpm.py:213-223: pred holds [mean prediction | variance head], 2*per_sample elements per
+ * sample as torch.chunk(.., 2, dim=1) splits it; std_out [B*per_sample] receives sqrt(max(var, 1e-20)), DDPM only);
+ * logprob nullable; std_out nullable when var_mode == 0. */
 int dlb_gaussian_step(const void* pred, int pred_dtype, const float* xt, const float* noise, const float* table,
-                      const int* t, int sampler, int mean_type, int clamp, float eta, int64_t B, int64_t per_sample,
-                      float* x_prev, float* x0, float* mean, float* logprob, dlb_stream_t stream);
+                      const int* t, int sampler, int mean_type, int var_mode, int clamp, float eta, int64_t B,
+                      int64_t per_sample, float* x_prev, float* x0, float* mean, float* logprob, float* std_out,
+                      dlb_stream_t stream);
 
 /* Euler-Maruyama flow step with log-probability (reference diffuse/samplers/flow/euler_meruyama.py:24-57), one launch.
  * c = sigma^2/(2 t_curr), stdv = sigma sqrt(t_curr - t_prev); exactly one of noise / x_prev_in is non-null. */

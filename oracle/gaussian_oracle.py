@@ -107,13 +107,24 @@ def x_start(T: Tables, mean_type: str, pred, xt, t, clamp: bool):
 def ddpm_step(betas, mean_type, var_type, pred, xt, t, noise, clamp=False):
     T = Tables(betas)
     n = xt.dim()
+    log_var = None
+    if var_type in ("learned", "learned_range"):  # ddpm.py:268-270: model output = [mean prediction | variance head] on dim 1
+        pred, log_var = torch.chunk(pred, 2, dim=1)
     x0 = x_start(T, mean_type, pred, xt, t, clamp)
     mean = _ex(T.c1, t, n) * x0 + _ex(T.c2, t, n) * xt
     if var_type == "fixed_small":
         var, lv = _ex(T.post_var, t, n), _ex(T.post_logvar, t, n)
-    else:
+    elif var_type == "fixed_large":
         seq = torch.cat([T.post_var[1:2], T.betas[1:]])
         var, lv = _ex(seq, t, n), _ex(torch.log(seq), t, n)
+    elif var_type == "learned":  # ddpm.py:213-215: the model's second channel half is log sigma^2
+        lv = log_var
+        var = lv.exp()
+    else:  # learned_range, ddpm.py:217-223: interpolate between the clipped posterior log-variance and log beta_t
+        min_log, max_log = _ex(T.post_logvar, t, n), _ex(T.betas, t, n).log()
+        w = (log_var + 1) / 2
+        lv = w * max_log + (1 - w) * min_log
+        var = lv.exp()
     var, lv = var.expand_as(xt), lv.expand_as(xt)
     mask = (t > 0).float().view(-1, *([1] * (n - 1)))
     x_prev = mean + mask * noise * torch.exp(0.5 * lv)

@@ -57,10 +57,34 @@ def test_space_timesteps_and_errors():
         GaussianDiffusion(sampling_method="euler")
     with pytest.raises(ValueError):
         DDPM(mean_type="velocity")
-    with pytest.raises(NotImplementedError):
-        DDPM(var_type="learned_range")
+    with pytest.raises(ValueError):
+        DDPM(var_type="learned_sigma")
     t = GaussianDiffusion(n_steps=100).draw_timesteps(64)
     assert t.dtype == torch.int32 and t.shape == (64,) and int(t.min()) >= 0 and int(t.max()) < 100
+
+
+def test_oracle_learned_variance_matches_reference():
+    """the oracle's learned / learned_range DDPM step against the reference's own outputs (tests/golden/gaussian_learned.pt,
+    made by oracle/make_golden_gaussian_learned.py): bit-exact on CPU"""
+    from oracle import gaussian_oracle as G
+
+    fl = torch.load(os.path.join(os.path.dirname(__file__), "golden", "gaussian_learned.pt"), weights_only=False)
+    betas = G.variance_schedule(1000)
+    assert len(fl["steps"]) == 12
+    for c in fl["steps"]:
+        out = G.ddpm_step(betas, c["mean_type"], c["var_type"], c["pred"], c["xt"], c["t"], c["noise"], c["clamp"])
+        for k, v in c["out"].items():
+            assert torch.equal(torch.nan_to_num(out[k]), torch.nan_to_num(v)), (c["var_type"], c["mean_type"], k)
+
+
+def test_learned_range_table_columns():
+    from diffulab_b200 import GaussianDiffusion
+    from oracle import gaussian_oracle as G
+
+    gd = GaussianDiffusion(n_steps=1000, sampler_parameters=dict(var_type="learned_range"))
+    T = G.Tables(G.variance_schedule(1000))
+    tab = gd.sampler._table
+    assert torch.equal(tab[:, 14], T.post_logvar.float()) and torch.equal(tab[:, 15], T.betas.float().log())
 
 
 def test_no_cpu_fallback():

@@ -65,6 +65,35 @@ def test_sampler_steps_match_reference(cuda_device, fx):
             close(out[k], v, f"{tag}:{k}", rtol=2e-5 if k == "logprob" else 2e-6, atol=1e-4 if k == "logprob" else 2e-6)
 
 
+def test_learned_variance_steps_match_reference(cuda_device):
+    """DDPM with var_type learned / learned_range (2C-channel prediction, per-element variance) against the reference's own
+    step outputs; exp / log of a per-element value: 4e-6 relative (expf and logf are each <= 2 ulp)."""
+    from diffulab_b200 import GaussianDiffusion
+
+    fl = torch.load(os.path.join(os.path.dirname(__file__), "golden", "gaussian_learned.pt"), weights_only=False)
+    for c in fl["steps"]:
+        gd = GaussianDiffusion(n_steps=1000, sampling_method="ddpm", sampler_parameters=dict(mean_type=c["mean_type"], var_type=c["var_type"]))
+        orig = torch.randn_like
+        torch.randn_like = lambda t, *a, **k: c["noise"].to(t.device)
+        try:
+            out = gd.sampler.step(model_prediction=c["pred"].cuda(), timesteps=c["t"].cuda(), xt=c["xt"].cuda(), clamp_x=c["clamp"])
+        finally:
+            torch.randn_like = orig
+        assert set(out) == set(c["out"])
+        tag = f"ddpm/{c['mean_type']}/{c['var_type']}/clamp={c['clamp']}"
+        for k, v in c["out"].items():
+            close(out[k], v, f"{tag}:{k}", rtol=2e-5 if k == "logprob" else 4e-6, atol=1e-4 if k == "logprob" else 4e-6)
+    # DDIM ignores the variance head (ddim.py:86: only x_start of _get_p_mean_var is used)
+    c = fl["steps"][0]
+    ddim = GaussianDiffusion(n_steps=1000, sampling_method="ddim", sampler_parameters=dict(mean_type=c["mean_type"], var_type="learned"))
+    plain = GaussianDiffusion(n_steps=1000, sampling_method="ddim", sampler_parameters=dict(mean_type=c["mean_type"]))
+    a = ddim.sampler.step(model_prediction=c["pred"].cuda(), timesteps=c["t"].cuda(), xt=c["xt"].cuda())
+    b = plain.sampler.step(model_prediction=c["pred"][:, :3].contiguous().cuda(), timesteps=c["t"].cuda(), xt=c["xt"].cuda())
+    assert torch.equal(a["x_prev"], b["x_prev"]) and torch.equal(a["estimated_x0"], b["estimated_x0"])
+    with pytest.raises(ValueError):
+        ddim.sampler.step(model_prediction=c["pred"][:, :3].contiguous().cuda(), timesteps=c["t"].cuda(), xt=c["xt"].cuda())
+
+
 def test_sampler_accepts_bf16_predictions(cuda_device, fx):
     from diffulab_b200 import GaussianDiffusion
     from oracle import gaussian_oracle as G
