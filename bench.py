@@ -292,7 +292,7 @@ def run_gpu_arm(args) -> None:
     import diffulab_b200 as dl
     from diffulab_b200 import _lib, ops
     from diffulab_b200.synthetic import Workload, build_workload
-    from diffulab_b200.training import EMA, FusedAdamW, GradReducer, training_step
+    from diffulab_b200.training import EMA, FusedAdamW, GradReducer, make_reduce_group, training_step
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -325,7 +325,10 @@ def run_gpu_arm(args) -> None:
         tr = cfg["trainer"]
         ema = EMA(opt, beta=float(tr.get("ema_rate", 0.999)), update_after_step=int(tr.get("ema_update_after_step", 0)),
                   update_every=int(tr.get("ema_update_every", 10)))
-    reducer = GradReducer(stores=opt.stores, bucket_mb=args.bucket_mb) if world > 1 else None
+    reducer = None
+    if world > 1:
+        reducer = GradReducer(stores=opt.stores, bucket_mb=args.bucket_mb or GradReducer.DEFAULT_BUCKET_MB, tail_bucket_mb=args.tail_bucket_mb or None,
+                              process_group=make_reduce_group(args.comm_ctas), reserve_sms=args.reserve_sms)
     n_params = sum(p.numel() for p in model.parameters())
 
     pool = 4
@@ -387,6 +390,28 @@ def run_gpu_arm(args) -> None:
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = B * world * args.steps / e2e_s
     h2d = Workload.nbytes(host[0])
+
+    # ---- data parallel: replicas must hold identical parameters after the steps; per-bucket timeline of one step ------
+    dp = None
+    if world > 1:
+        sums = torch.stack([st.flat_p.double().sum() for st in opt.stores] + [st.flat_p.double().abs().sum() for st in opt.stores])
+        gathered = [torch.empty_like(sums) for _ in range(world)]
+        dist.all_gather(gathered, sums)
+        identical = all(bool(torch.equal(gathered[0], gi)) for gi in gathered)
+        assert identical, f"data-parallel replicas diverged: per-rank parameter checksums {[gi.tolist() for gi in gathered]}"
+        reducer.timeline = []
+        step_resident(0)
+        torch.cuda.synchronize()
+        tl = reducer.read_timeline()
+        reducer.timeline = None
+        dp = {"replicas_identical_after_steps": identical, "buckets": len(reducer.buckets), "bucket_mb": args.bucket_mb or GradReducer.DEFAULT_BUCKET_MB,
+              "tail_bucket_mb": args.tail_bucket_mb or None, "comm_ctas": args.comm_ctas, "reserve_sms": args.reserve_sms,
+              "grad_bytes_per_step": int(sum(b.numel() for b in reducer.buckets) * 4), "backward_after_first_bucket_ms": tl["end_backward_ms"],
+              "exposed_tail_ms": tl["exposed_tail_ms"]}
+        if rank == 0:
+            os.makedirs("gpurun_out", exist_ok=True)
+            with open(f"gpurun_out/dp_timeline_{world}gpu.json", "w") as f:
+                json.dump({**dp, "timeline": tl}, f, indent=1)
 
     # ---- separate profiled pass: per-kernel CUDA-event times -> roofline of the dominant kernel -------------
     psteps = max(1, min(args.profile_steps, args.steps))
@@ -515,7 +540,7 @@ def run_gpu_arm(args) -> None:
         line = {
             "metric": METRICS.get(name, f"{name} train throughput"), "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic", "config": config_block(name, wl, B, world, n_params),
+            "dtype": "bf16", "data": "synthetic", "config": {**config_block(name, wl, B, world, n_params), **({"dp": dp} if dp else {})},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "losses": final_losses,
             "loss_check": loss_check, "sample": sample, "kernel_breakdown": breakdown,
         }
@@ -553,7 +578,10 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="imagenet_repa", help="imagenet_repa (metric config) | cifar10 | txt_to_img | sprint | path to a YAML")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's dataloader.batch_size)")
-    ap.add_argument("--bucket-mb", type=float, default=256.0)
+    ap.add_argument("--bucket-mb", type=float, default=0.0, help="gradient bucket size (default: GradReducer.DEFAULT_BUCKET_MB)")
+    ap.add_argument("--tail-bucket-mb", type=float, default=32.0, help="size cap of the buckets backward produces last (0 = same as --bucket-mb)")
+    ap.add_argument("--comm-ctas", type=int, default=4, help="CTAs per gradient all-reduce (dedicated NCCL communicator); 0 = NCCL's default")
+    ap.add_argument("--reserve-sms", type=int, default=4, help="SMs the persistent kernels leave to NCCL while buckets are in flight")
     ap.add_argument("--sample-batch", type=int, default=64)
     ap.add_argument("--sample-batches", default="", help="comma-separated batch sweep for the sampling benchmark")
     ap.add_argument("--no-sample", action="store_true")

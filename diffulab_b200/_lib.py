@@ -26,6 +26,7 @@ _SIGNATURES: dict[str, list] = {
     "dlb_launch_count": [],
     "dlb_reset_launch_count": [],
     "dlb_device_check": [],
+    "dlb_set_sm_budget": [i32],
     # C[M,N] (+)= A*B^T (+bias): A, B, C, bias, M, N, K, lda, ldb, ldc, a_mn, b_mn, out_mode, split_k, tile_n, stream
     "dlb_gemm_bf16": [p, p, p, p, i64, i64, i64, i64, i64, i64, i32, i32, i32, i32, i32, p],
     # x, w, b, scale, shift, mod_ld, rows_per_mod, y, mean, rstd, R, d, eps, stream
@@ -190,3 +191,8 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     load().dlb_reset_launch_count()
+
+
+def set_sm_budget(sms: int) -> int:
+    """SMs the persistent kernels use (0 = all); returns the previous budget (see include/diffulab_b200.h)."""
+    return int(load().dlb_set_sm_budget(int(sms)))

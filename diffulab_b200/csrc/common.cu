@@ -24,6 +24,8 @@ int dlb_check_launch(const char* what) {
 
 void dlb_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+static std::atomic<int> g_sm_budget{0};
+
 int dlb_num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -32,7 +34,18 @@ int dlb_num_sms() {
         sms <= 0)
       sms = 148;
   }
-  return sms;
+  const int budget = g_sm_budget.load(std::memory_order_relaxed);
+  return (budget > 0 && budget < sms) ? budget : sms;
+}
+
+// Persistent kernels (GEMMs, attention) size their grids to dlb_num_sms(). While gradient buckets are being all-reduced
+// behind backward, the data-parallel reducer lowers the budget by the collective's CTA count so that the NCCL kernel gets
+// SMs of its own instead of time-slicing with a statically scheduled persistent CTA (which makes that CTA the straggler of
+// every GEMM launched meanwhile). 0 restores all SMs. Rounded down to an even count (CTA-pair kernels). Returns the old budget.
+DLB_EXPORT int dlb_set_sm_budget(int sms) {
+  if (sms < 0) sms = 0;
+  if (sms > 0 && sms < 16) sms = 16;
+  return g_sm_budget.exchange(sms & ~1, std::memory_order_relaxed);
 }
 
 DLB_EXPORT const char* dlb_last_error(void) { return g_err; }

@@ -258,6 +258,19 @@ class EMA:
         return {n: by_id[id(p)] for n, p in model.named_parameters() if id(p) in by_id}
 
 
+def make_reduce_group(comm_ctas: int = 4) -> Any:
+    """A dedicated NCCL communicator for the gradient buckets, limited to `comm_ctas` CTAs per collective. The buckets need
+    ~3.3 GB per ~95 ms of backward (DiT-XL/2, fp32) = 35 GB/s — a few CTAs over NVLink 5 — while NCCL's default of 16-32
+    CTAs would time-slice with as many persistent GEMM CTAs and make each of them the straggler of its GEMM. Returns None
+    (default group) when the job is not distributed or the backend is not NCCL."""
+    if not dist.is_initialized() or dist.get_backend() != "nccl" or comm_ctas <= 0:
+        return None
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.config.max_ctas = int(comm_ctas)
+    opts.config.min_ctas = min(int(comm_ctas), 2)
+    return dist.new_group(backend="nccl", pg_options=opts)
+
+
 class GradReducer:
     """Bucketed gradient all-reduce (mean over ranks) launched during backward.
 
@@ -266,16 +279,26 @@ class GradReducer:
     when all parameters of a bucket are ready the bucket's all-reduce is issued with async_op=True (c10d orders it
     after the compute stream's current position and runs it on the communicator's own stream), so communication
     overlaps the rest of backward. Parameters that never receive a gradient (reference quirk) are
-    tolerated: their buckets are flushed, in a fixed order, by `finish()`."""
+    tolerated: their buckets are flushed, in a fixed order, by `finish()`.
+
+    `tail_bucket_mb`: the buckets produced LAST by backward (the first-registered parameters) are capped at this size so that
+    the part of the reduction that cannot overlap anything is short. `reserve_sms`: between `begin()` and `finish()` the
+    persistent GEMM / attention kernels leave this many SMs to the collective (dlb_set_sm_budget)."""
+
+    DEFAULT_BUCKET_MB = 128.0
 
     def __init__(self, stores: list[FlatParams] | None = None, params: list[nn.Parameter] | None = None,
-                 bucket_mb: float = 128.0, process_group: Any = None):
+                 bucket_mb: float = DEFAULT_BUCKET_MB, process_group: Any = None, tail_bucket_mb: float | None = None,
+                 reserve_sms: int = 0):
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.reserve_sms = int(reserve_sms)
         self.buckets: list[Tensor] = []
         self.bucket_of: dict[int, int] = {}
         self.pending_init: list[int] = []
+        self.timeline: list[tuple[int, Any]] | None = None
         cap = int(bucket_mb * 1024 * 1024 / 4)
+        tail_cap = int((tail_bucket_mb if tail_bucket_mb else bucket_mb) * 1024 * 1024 / 4)
         if stores:
             for st in stores:
                 start, count, members = None, 0, []
@@ -287,7 +310,9 @@ class GradReducer:
                     start = o
                     count += n
                     members.append(p)
-                    if count >= cap:
+                    # what is still ahead of this parameter (offsets below `o`) is produced later in backward: once less than
+                    # two tail buckets remain, switch to the small cap
+                    if count >= (tail_cap if o <= 2 * tail_cap else cap):
                         self._add_bucket(st.flat_g[start:end], members)
                         start, count, members = None, 0, []
                 if members:
@@ -315,6 +340,9 @@ class GradReducer:
         self.seen: set[int] = set()
         self.active = True
         K.set_grad_ready_hook(self._ready)
+        if self.reserve_sms > 0 and self.world > 1:
+            from . import _lib
+            _lib.set_sm_budget(torch.cuda.get_device_properties(self.buckets[0].device).multi_processor_count - self.reserve_sms)
 
     def _launch(self, bi: int) -> None:
         if self.launched[bi]:
@@ -324,6 +352,10 @@ class GradReducer:
             return
         t = self.buckets[bi]
         if t.is_cuda:
+            if self.timeline is not None:  # where on the compute stream this bucket became ready
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                self.timeline.append((bi, ev))
             self.works.append(dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
         else:  # gloo (CPU tests of the host logic) has no AVG
             w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
@@ -352,15 +384,42 @@ class GradReducer:
         """Flush buckets holding never-produced gradients (fixed order on every rank), then wait for all of them."""
         K.set_grad_ready_hook(None)
         self.active = False
+        if self.reserve_sms > 0 and self.world > 1:
+            from . import _lib
+            _lib.set_sm_budget(0)
         for bi in range(len(self.buckets)):
             self._launch(bi)
+        done: list[Any] = []
+        if self.timeline is not None and self.works and not isinstance(self.works[0], tuple):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.timeline.append((-1, ev))  # end of backward on the compute stream
         for w in self.works:
             if isinstance(w, tuple):
                 w[0].wait()
                 w[1].div_(self.world)
             else:
                 w.wait()
+                if self.timeline is not None:  # the compute stream now waits for this bucket: an event here is its completion
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record()
+                    done.append(ev)
+        if self.timeline is not None:
+            self.timeline.extend((-2 - i, ev) for i, ev in enumerate(done))
         self.works = []
+
+    def read_timeline(self) -> dict[str, Any]:
+        """After a step run with `self.timeline = []` (and a device synchronize): per-bucket ready / done times in ms relative
+        to the first bucket's ready point, the end of backward, and the exposed tail = last completion - end of backward."""
+        assert self.timeline, "set reducer.timeline = [] before the step"
+        t0 = self.timeline[0][1]
+        ready = {bi: t0.elapsed_time(ev) for bi, ev in self.timeline if bi >= 0}
+        end_bwd = next(t0.elapsed_time(ev) for bi, ev in self.timeline if bi == -1)
+        done = [t0.elapsed_time(ev) for bi, ev in self.timeline if bi <= -2]
+        order = [bi for bi, _ in self.timeline if bi >= 0]
+        return {"bucket_mb": [round(self.buckets[bi].numel() * 4 / 2**20, 1) for bi in order], "ready_ms": [round(ready[bi], 3) for bi in order],
+                "done_ms": [round(d, 3) for d in done], "end_backward_ms": round(end_bwd, 3),
+                "exposed_tail_ms": round(max(done) - end_bwd, 3) if done else 0.0}
 
 
 def training_step(diffuser, optimizer: torch.optim.Optimizer, batch: dict[str, Any], p_classifier_free_guidance: float = 0.0,

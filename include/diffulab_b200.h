@@ -40,6 +40,11 @@ const char* dlb_last_error(void);
 int dlb_device_check(void);            /* 0 iff the current device is compute capability 10.x */
 long long dlb_launch_count(void);      /* kernels launched by this library since load / last reset */
 void dlb_reset_launch_count(void);
+/* Number of SMs the persistent kernels (GEMMs, attention) size their grids to; 0 = all. The data-parallel reducer lowers it
+ * by the collective's CTA count while gradient buckets are in flight behind backward (the role DDP's bucketed overlap plays
+ * under accelerate in the reference, base_trainer.py:111-123) so that NCCL does not time-slice with a persistent CTA.
+ * Returns the previous budget. */
+int dlb_set_sm_budget(int sms);
 
 /* ---- dense contractions: tcgen05 / TMEM / TMA GEMM -------------------------------------------------------
  * C[M,N] (+)= A * B^T (+ bias[N]); bf16 operands, fp32 accumulate.

@@ -13,7 +13,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def fixture_names() -> list[str]:
     """Denoiser fixtures (gaussian.pt holds the model-free Gaussian-diffusion vectors and is loaded separately)."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
-    return [n for n in names if n not in ("gaussian", "flow_misc", "perceiver")]
+    return [n for n in names if n not in ("gaussian", "gaussian_learned", "flow_misc", "perceiver")]
 
 
 def load_fixture(name: str) -> dict:

@@ -77,3 +77,26 @@ def test_bucket_layout_reverse_order():
         b = red.buckets[red.bucket_of[id(p)]]
         lo = (b.data_ptr() - st.flat_g.data_ptr()) // 4
         assert lo <= o and o + p.numel() <= lo + b.numel()
+
+
+def test_tail_buckets_are_small():
+    """tail_bucket_mb: the buckets backward produces last (lowest offsets) are capped at the small size; everything is covered once"""
+    from diffulab_b200.training import _ALIGN, GradReducer
+
+    class FakeStore:
+        def __init__(self, sizes):
+            self.params = [torch.nn.Parameter(torch.zeros(n)) for n in sizes]
+            self.offsets, off = [], 0
+            for p in self.params:
+                self.offsets.append(off)
+                off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            self.flat_g = torch.zeros(off)
+
+    st = FakeStore([256] * 64)
+    mb = lambda n: 4 * n / (1024 * 1024)  # noqa: E731
+    red = GradReducer(stores=[st], bucket_mb=mb(4096), tail_bucket_mb=mb(512))
+    sizes = [b.numel() for b in red.buckets]
+    assert sum(sizes) == st.flat_g.numel() and len(set(red.bucket_of.values())) == len(red.buckets)
+    assert sizes[0] == 4096 and sizes[-1] == 512 and sizes[-2] == 512 and max(sizes) == 4096
+    same = GradReducer(stores=[st], bucket_mb=mb(4096))
+    assert [b.numel() for b in same.buckets] == [4096] * 4
