@@ -328,7 +328,8 @@ def run_gpu_arm(args) -> None:
     reducer = None
     if world > 1:
         reducer = GradReducer(stores=opt.stores, bucket_mb=args.bucket_mb or GradReducer.DEFAULT_BUCKET_MB, tail_bucket_mb=args.tail_bucket_mb or None,
-                              process_group=make_reduce_group(args.comm_ctas), reserve_sms=args.reserve_sms)
+                              process_group=make_reduce_group(args.comm_ctas) if args.dp_mode == "nccl" else None, reserve_sms=args.reserve_sms,
+                              mode=args.dp_mode, comm_ctas=args.comm_ctas)
     n_params = sum(p.numel() for p in model.parameters())
 
     pool = 4
@@ -404,7 +405,7 @@ def run_gpu_arm(args) -> None:
         torch.cuda.synchronize()
         tl = reducer.read_timeline()
         reducer.timeline = None
-        dp = {"replicas_identical_after_steps": identical, "buckets": len(reducer.buckets), "bucket_mb": args.bucket_mb or GradReducer.DEFAULT_BUCKET_MB,
+        dp = {"mode": reducer.mode, "replicas_identical_after_steps": identical, "buckets": len(reducer.buckets), "bucket_mb": args.bucket_mb or GradReducer.DEFAULT_BUCKET_MB,
               "tail_bucket_mb": args.tail_bucket_mb or None, "comm_ctas": args.comm_ctas, "reserve_sms": args.reserve_sms,
               "grad_bytes_per_step": int(sum(b.numel() for b in reducer.buckets) * 4), "backward_after_first_bucket_ms": tl["end_backward_ms"],
               "exposed_tail_ms": tl["exposed_tail_ms"]}
@@ -580,7 +581,9 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's dataloader.batch_size)")
     ap.add_argument("--bucket-mb", type=float, default=0.0, help="gradient bucket size (default: GradReducer.DEFAULT_BUCKET_MB)")
     ap.add_argument("--tail-bucket-mb", type=float, default=32.0, help="size cap of the buckets backward produces last (0 = same as --bucket-mb)")
-    ap.add_argument("--comm-ctas", type=int, default=4, help="CTAs per gradient all-reduce (dedicated NCCL communicator); 0 = NCCL's default")
+    ap.add_argument("--dp-mode", default="nccl", choices=["nccl", "ce", "nvls"], help="gradient reduction: NCCL all-reduce | copy-engine pulls over peer "
+                    "memory + reduce kernel | in-switch multimem reduction kernel")
+    ap.add_argument("--comm-ctas", type=int, default=4, help="CTAs per gradient reduction (nccl: dedicated communicator, 0 = NCCL's default; nvls: kernel grid)")
     ap.add_argument("--reserve-sms", type=int, default=4, help="SMs the persistent kernels leave to NCCL while buckets are in flight")
     ap.add_argument("--sample-batch", type=int, default=64)
     ap.add_argument("--sample-batches", default="", help="comma-separated batch sweep for the sampling benchmark")

@@ -27,6 +27,8 @@ _SIGNATURES: dict[str, list] = {
     "dlb_reset_launch_count": [],
     "dlb_device_check": [],
     "dlb_set_sm_budget": [i32],
+    "dlb_reduce_pieces": [p, p, i64, i32, i32, i64, f32, i32, p],
+    "dlb_multimem_allreduce": [p, i64, f32, i32, p],
     # C[M,N] (+)= A*B^T (+bias): A, B, C, bias, M, N, K, lda, ldb, ldc, a_mn, b_mn, out_mode, split_k, tile_n, stream
     "dlb_gemm_bf16": [p, p, p, p, i64, i64, i64, i64, i64, i64, i32, i32, i32, i32, i32, p],
     # x, w, b, scale, shift, mod_ld, rows_per_mod, y, mean, rstd, R, d, eps, stream

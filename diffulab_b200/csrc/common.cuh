@@ -68,6 +68,41 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 
 // 8 bf16 values <-> 8 floats through one 16-byte vector.
 struct alignas(16) bf16x8 { uint32_t u[4]; };
+// Packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 issue ONE instruction for two IEEE-rn operations, same results as the scalar
+// forms). Used where a kernel is bound by issue slots rather than by the FP32 pipe (GEMM epilogue math, row kernels).
+struct f32x2 { unsigned long long v; };
+__device__ __forceinline__ f32x2 make_f32x2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void split_f32x2(f32x2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+  return r;
+}
+// bf16x2 word -> (lo, hi) as an fp32 pair
+__device__ __forceinline__ f32x2 unpack2(uint32_t u) { return make_f32x2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+// fp32 pair -> bf16x2 word (round to nearest even), one CVT
+__device__ __forceinline__ uint32_t pack2(f32x2 a) {
+  float lo, hi;
+  split_f32x2(a, lo, hi);
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 __device__ __forceinline__ void unpack8(const bf16x8& p, float* f) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) { float2 t = unpack_bf16x2(p.u[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }

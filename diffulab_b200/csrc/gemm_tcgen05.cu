@@ -114,21 +114,26 @@ __device__ __forceinline__ void epilogue_tile(const CUtensorMap& tmC, const CUte
       for (int j = 0; j < 8; ++j) {
         const int off = (j ^ (lane & 7)) << 4;
         const bf16x8 av = *reinterpret_cast<const bf16x8*>(rowa + off), gv = *reinterpret_cast<const bf16x8*>(rowg + off);
-        float a[8], g[8], da[8], dg[8];
-        unpack8(av, a);
-        unpack8(gv, g);
+        // ~10 issue slots per element instead of ~20 (packed fp32 pairs): with 2 epilogue warps per scheduler the epilogue of a
+        // 128 x 128 tile must fit under the 2304-cycle main loop of a K = 1152 tile
+        bf16x8 dav, dgv;
+        const f32x2 half2 = make_f32x2(0.5f, 0.5f), one2 = make_f32x2(1.f, 1.f), mone2 = make_f32x2(-1.f, -1.f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float go = bf16_round(__uint_as_float(r[8 * j + i]));  // d(act) as the bf16 tensor autocast would hold
-          const float hh = 0.5f * a[i];
-          float th;
-          asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hh));
-          const float sg = fmaf(0.5f, th, 0.5f);  // sigmoid(a)
-          da[i] = go * g[i] * sg * (1.f + a[i] * (1.f - sg));
-          dg[i] = go * a[i] * sg;
+        for (int i = 0; i < 4; ++i) {
+          const f32x2 a2 = unpack2(av.u[i]), g2 = unpack2(gv.u[i]);
+          // d(act) as the bf16 tensor autocast would hold
+          const f32x2 go2 = unpack2(pack2(make_f32x2(__uint_as_float(r[8 * j + 2 * i]), __uint_as_float(r[8 * j + 2 * i + 1]))));
+          float h0, h1, t0, t1;
+          split_f32x2(mul2(a2, half2), h0, h1);
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+          const f32x2 sg2 = fma2(make_f32x2(t0, t1), half2, half2);      // sigmoid(a)
+          const f32x2 t2 = fma2(a2, fma2(sg2, mone2, one2), one2);       // 1 + a (1 - sigmoid(a))
+          dav.u[i] = pack2(mul2(mul2(mul2(go2, g2), sg2), t2));
+          dgv.u[i] = pack2(mul2(mul2(go2, a2), sg2));
         }
-        *reinterpret_cast<bf16x8*>(rowa + off) = pack8(da);
-        *reinterpret_cast<bf16x8*>(rowg + off) = pack8(dg);
+        *reinterpret_cast<bf16x8*>(rowa + off) = dav;
+        *reinterpret_cast<bf16x8*>(rowg + off) = dgv;
       }
       ptx::fence_proxy_async_smem();
       __syncwarp();

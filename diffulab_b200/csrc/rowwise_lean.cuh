@@ -134,27 +134,27 @@ ln_modulate_fwd_lean(const bf16* __restrict__ x, const float* __restrict__ w, co
     const int r = base + warp;
     if (r + WARPS < row1) nxt.load(x + (int64_t)(r + WARPS) * d, lane);
     if (r < row1) {
-      float f[UPL][U];
-      cur.unpack(f);
-      float s = 0.f;
+      // packed fp32 pairs (FADD2 / FFMA2): one issue slot per two channels; two-pass statistics as before
+      f32x2 f[UPL][U / 2];
+      f32x2 s2 = make_f32x2(0.f, 0.f);
 #pragma unroll
-      for (int u = 0; u < UPL; ++u) {
-        float t = 0.f;
+      for (int u = 0; u < UPL; ++u)
 #pragma unroll
-        for (int j = 0; j < U; ++j) t += f[u][j];
-        s += t;
-      }
-      const float mean = warp_sum(s) * (1.f / d);
-      float q = 0.f;
+        for (int j = 0; j < U / 2; ++j) { f[u][j] = unpack2(cur.w[u][j]); s2 = add2(s2, f[u][j]); }
+      float s_lo, s_hi;
+      split_f32x2(s2, s_lo, s_hi);
+      const float mean = warp_sum(s_lo + s_hi) * (1.f / d);
+      const f32x2 nmean2 = make_f32x2(-mean, -mean);
+      f32x2 q2 = make_f32x2(0.f, 0.f);
 #pragma unroll
-      for (int u = 0; u < UPL; ++u) {
-        float t = 0.f;
+      for (int u = 0; u < UPL; ++u)
 #pragma unroll
-        for (int j = 0; j < U; ++j) { f[u][j] -= mean; t = fmaf(f[u][j], f[u][j], t); }
-        q += t;
-      }
-      const float rstd = rsqrtf(warp_sum(q) * (1.f / d) + eps);
+        for (int j = 0; j < U / 2; ++j) { f[u][j] = add2(f[u][j], nmean2); q2 = fma2(f[u][j], f[u][j], q2); }
+      float q_lo, q_hi;
+      split_f32x2(q2, q_lo, q_hi);
+      const float rstd = rsqrtf(warp_sum(q_lo + q_hi) * (1.f / d) + eps);
       if (lane == 0 && mean_out) { mean_out[r] = mean; rstd_out[r] = rstd; }
+      const f32x2 rstd2 = make_f32x2(rstd, rstd);
       Row<U, UPL> o;
 #pragma unroll
       for (int u = 0; u < UPL; ++u) {
@@ -163,7 +163,7 @@ ln_modulate_fwd_lean(const bf16* __restrict__ x, const float* __restrict__ w, co
         ldf<U>(sQ + (lane + 32 * u) * U, qv);
 #pragma unroll
         for (int j = 0; j < U / 2; ++j)
-          o.w[u][j] = pack_bf16x2(fmaf(f[u][2 * j], rstd * pv[2 * j], qv[2 * j]), fmaf(f[u][2 * j + 1], rstd * pv[2 * j + 1], qv[2 * j + 1]));
+          o.w[u][j] = pack2(fma2(f[u][j], mul2(rstd2, make_f32x2(pv[2 * j], pv[2 * j + 1])), make_f32x2(qv[2 * j], qv[2 * j + 1])));
       }
       o.store(y + (int64_t)r * d, lane);
     }

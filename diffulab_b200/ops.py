@@ -774,6 +774,19 @@ def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, shadow: Tensor | None
               _stream())
 
 
+def reduce_pieces_(own: Tensor, staged: Tensor, stage_stride: int, world: int, rank: int, scale: float, max_ctas: int = 0) -> None:
+    """own = scale * (own + the world-1 peer pieces staged by the copy engines), summed in rank order (dlb_reduce_pieces)."""
+    _req(own, F32, "own")
+    _req(staged, F32, "staged")
+    _lib_call("dlb_reduce_pieces", own.data_ptr(), staged.data_ptr(), int(stage_stride), int(world), int(rank), own.numel(), float(scale),
+              int(max_ctas), _stream())
+
+
+def multimem_allreduce_(mc_ptr: int, n: int, scale: float, ctas: int) -> None:
+    """In-switch (NVLS) sum of n floats at multicast address mc_ptr over all ranks, scaled, written back to every rank."""
+    _lib_call("dlb_multimem_allreduce", int(mc_ptr), int(n), float(scale), int(ctas), _stream())
+
+
 def ema_lerp_(ema: Tensor, p: Tensor, decay: float) -> None:
     """ema = ema * decay + p * (1 - decay), flat fp32 buffers."""
     _req(ema, F32, "ema")

@@ -64,6 +64,14 @@ class FlatParams:
         if any(p._version != v for p, v in zip(self.params, self._versions)):
             self.refresh_shadows()
 
+    def use_grad_buffer(self, buf: Tensor) -> None:
+        """Move the flat gradient buffer (e.g. into symmetric / peer-mapped memory for the NVLink gradient reduction)."""
+        assert buf.dtype == torch.float32 and buf.numel() == self.total and buf.device == self.flat_g.device and buf.is_contiguous()
+        buf.copy_(self.flat_g)
+        self.flat_g = buf
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.flat_g[o : o + p.numel()].view(p.shape)
+
     def zero_grad(self) -> None:
         self.flat_g.zero_()
         for p, o in zip(self.params, self.offsets):  # re-attach if someone set .grad to None
@@ -283,16 +291,44 @@ class GradReducer:
 
     `tail_bucket_mb`: the buckets produced LAST by backward (the first-registered parameters) are capped at this size so that
     the part of the reduction that cannot overlap anything is short. `reserve_sms`: between `begin()` and `finish()` the
-    persistent GEMM / attention kernels leave this many SMs to the collective (dlb_set_sm_budget)."""
+    persistent GEMM / attention kernels leave this many SMs to the collective (dlb_set_sm_budget).
+
+    `mode`:
+      "nccl"  ncclAllReduce(AVG) per bucket on the communicator's stream (16-32 CTAs that time-slice with the persistent GEMMs:
+              measured +5 ms of kernel time per 143 ms step at N = 2, profiles/dp_overlap_r2.md).
+      "ce"    the flat gradient buffer lives in symmetric (peer-mapped) memory; per bucket, rank p pulls piece p of every peer with
+              device-to-device copies (copy engines over NVLink, no SMs), averages them (dlb_reduce_pieces), and all ranks pull
+              the reduced pieces back. Stream-ordered symmetric-memory barriers order the phases across ranks.
+      "nvls"  one dlb_multimem_allreduce kernel per bucket (sum inside the NVSwitch, `comm_ctas` CTAs) between two barriers.
+    Modes "ce" / "nvls" need a FlatParams store and an NCCL (CUDA) job; the mean is exact in fp32 as with NCCL."""
 
     DEFAULT_BUCKET_MB = 128.0
 
     def __init__(self, stores: list[FlatParams] | None = None, params: list[nn.Parameter] | None = None,
                  bucket_mb: float = DEFAULT_BUCKET_MB, process_group: Any = None, tail_bucket_mb: float | None = None,
-                 reserve_sms: int = 0):
+                 reserve_sms: int = 0, mode: str = "nccl", comm_ctas: int = 4):
+        assert mode in ("nccl", "ce", "nvls"), mode
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         self.reserve_sms = int(reserve_sms)
+        self.mode = mode if self.world > 1 else "nccl"
+        self.comm_ctas = int(comm_ctas)
+        self.bucket_span: list[tuple[int, int, int]] = []  # (store index, start, end) of every bucket in its flat buffer
+        self._sym: list[Any] = []
+        if self.mode != "nccl":
+            assert stores and all(st.flat_g.is_cuda for st in stores), "peer-memory gradient reduction needs FlatParams stores on CUDA"
+            import torch.distributed._symmetric_memory as symm_mem
+
+            group = process_group if process_group is not None else dist.group.WORLD
+            self.rank = dist.get_rank(group)
+            for st in stores:
+                buf = symm_mem.empty(st.total, dtype=torch.float32, device=st.flat_g.device)
+                st.use_grad_buffer(buf)
+                self._sym.append(symm_mem.rendezvous(buf, group))
+            if self.mode == "nvls":
+                assert all(int(h.multicast_ptr) != 0 for h in self._sym), "no NVLink multicast (NVLS) mapping on this system: use mode='ce'"
+            self.comm = torch.cuda.Stream(priority=-1)
+            self._stage: Tensor | None = None
         self.buckets: list[Tensor] = []
         self.bucket_of: dict[int, int] = {}
         self.pending_init: list[int] = []
@@ -314,9 +350,11 @@ class GradReducer:
                     # two tail buckets remain, switch to the small cap
                     if count >= (tail_cap if o <= 2 * tail_cap else cap):
                         self._add_bucket(st.flat_g[start:end], members)
+                        self.bucket_span.append((stores.index(st), start, end))
                         start, count, members = None, 0, []
                 if members:
                     self._add_bucket(st.flat_g[start:end], members)
+                    self.bucket_span.append((stores.index(st), start, end))
         else:
             assert params is not None
             for p in reversed([q for q in params if q.requires_grad]):
@@ -356,10 +394,53 @@ class GradReducer:
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()
                 self.timeline.append((bi, ev))
-            self.works.append(dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+            if self.mode == "nccl":
+                self.works.append(dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+            else:
+                self.works.append(self._peer_reduce(bi))
         else:  # gloo (CPU tests of the host logic) has no AVG
             w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
             self.works.append((w, t))
+
+    _BARRIER_TIMEOUT_MS = 30000  # a lost peer traps the kernel instead of hanging the GPU
+
+    def _pieces(self, n: int) -> tuple[int, list[int]]:
+        """piece length (multiple of 64 floats) and per-rank lengths of a bucket of n floats (the last pieces may be short / empty)"""
+        piece = ((n + self.world - 1) // self.world + _ALIGN - 1) // _ALIGN * _ALIGN
+        return piece, [max(0, min(piece, n - q * piece)) for q in range(self.world)]
+
+    def _peer_reduce(self, bi: int) -> Any:
+        """Reduce bucket bi over NVLink peer memory on the communication stream; returns an event the compute stream waits for."""
+        si, start, end = self.bucket_span[bi]
+        hdl, t = self._sym[si], self.buckets[bi]
+        W, r = self.world, self.rank
+        piece, lens = self._pieces(end - start)
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(ready)
+            hdl.barrier(channel=0, timeout_ms=self._BARRIER_TIMEOUT_MS)  # every rank's gradients of this bucket are complete
+            if self.mode == "nvls":
+                if lens[r] > 0:
+                    ops.multimem_allreduce_(int(hdl.multicast_ptr) + 4 * (start + r * piece), lens[r], 1.0 / W, self.comm_ctas)
+            else:
+                if lens[r] > 0:
+                    if self._stage is None or self._stage.numel() < (W - 1) * piece:
+                        self._stage = torch.empty((W - 1) * piece, device=t.device, dtype=torch.float32)
+                    for s_ in range(W - 1):  # pull my piece of every peer's bucket (copy engines)
+                        peer = (r + 1 + s_) % W
+                        src = hdl.get_buffer(peer, (lens[r],), torch.float32, start + r * piece)
+                        self._stage[s_ * piece : s_ * piece + lens[r]].copy_(src, non_blocking=True)
+                    ops.reduce_pieces_(t[r * piece : r * piece + lens[r]], self._stage, piece, W, r, 1.0 / W)
+                hdl.barrier(channel=0, timeout_ms=self._BARRIER_TIMEOUT_MS)  # every rank's piece is reduced
+                for s_ in range(W - 1):  # pull the reduced pieces of the peers (copy engines)
+                    peer = (r + 1 + s_) % W
+                    if lens[peer] > 0:
+                        src = hdl.get_buffer(peer, (lens[peer],), torch.float32, start + peer * piece)
+                        t[peer * piece : peer * piece + lens[peer]].copy_(src, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        return done
 
     def _ready(self, p: Tensor) -> None:
         if not self.active:
@@ -394,16 +475,29 @@ class GradReducer:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             self.timeline.append((-1, ev))  # end of backward on the compute stream
+        if self.mode != "nccl" and self.works:
+            # peers read my pieces (and, multicast mode, write theirs into my buffer) until THEIR last operation: one closing barrier
+            # per store before this rank's optimizer reads / the next zero_grad overwrites the gradient buffer
+            with torch.cuda.stream(self.comm):
+                for hdl in self._sym:
+                    hdl.barrier(channel=0, timeout_ms=self._BARRIER_TIMEOUT_MS)
+                closing = torch.cuda.Event()
+                closing.record()
         for w in self.works:
             if isinstance(w, tuple):
                 w[0].wait()
                 w[1].div_(self.world)
             else:
-                w.wait()
+                if self.mode == "nccl":
+                    w.wait()
+                else:
+                    torch.cuda.current_stream().wait_event(w)
                 if self.timeline is not None:  # the compute stream now waits for this bucket: an event here is its completion
                     ev = torch.cuda.Event(enable_timing=True)
                     ev.record()
                     done.append(ev)
+        if self.mode != "nccl" and self.works:
+            torch.cuda.current_stream().wait_event(closing)
         if self.timeline is not None:
             self.timeline.extend((-2 - i, ev) for i, ev in enumerate(done))
         self.works = []

@@ -232,6 +232,16 @@ int dlb_gaussian_step(const void* pred, int pred_dtype, const float* xt, const f
 int dlb_euler_maruyama_step(const float* x, const void* v, int v_dtype, const float* noise, const float* x_prev_in, float c,
                             float one_minus_t, float dt, float t_curr, float stdv, float* x_prev, float* mean,
                             float* x0_est, float* logprob, int64_t n, dlb_stream_t stream);
+/* ---- data-parallel gradient reduction over NVLink peer memory (replaces the NCCL all-reduce kernels DDP runs under the
+ * reference's Accelerate wrapper, training/trainers/common.py:103-109; orchestration in diffulab_b200/training.py GradReducer) ----
+ * dlb_reduce_pieces: own[0..n) = scale * sum over ranks (fixed order) of this rank's piece; the world-1 peer copies were pulled by
+ * the copy engines into `staged` (slot s, stride stage_stride floats, holds rank (rank + 1 + s) % world). max_ctas 0 = no cap.
+ * dlb_multimem_allreduce: mc_piece = MULTICAST address of this rank's piece of a symmetric buffer; multimem.ld_reduce (sum in the
+ * NVSwitch) -> * scale -> multimem.st to every rank, on `ctas` CTAs. Cross-rank ordering is the caller's (stream barriers). */
+int dlb_reduce_pieces(float* own, const float* staged, int64_t stage_stride, int world, int rank, int64_t n, float scale,
+                      int max_ctas, dlb_stream_t stream);
+int dlb_multimem_allreduce(void* mc_piece, int64_t n, float scale, int ctas, dlb_stream_t stream);
+
 /* torch.optim.AdamW step over a flat buffer (+ bf16 shadow, + optional EMA lerp ema = ema*decay + p*(1-decay))
  * (base_trainer.py:149-153). Hyper-parameters are doubles (python floats); bias corrections are evaluated in double as
  * torch does. chunk_active (nullable): one byte per 64 elements, 0 = skip (parameters whose .grad is None in torch). */

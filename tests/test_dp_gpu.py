@@ -1,4 +1,4 @@
-"""2-GPU data parallel parity (NCCL): gradients after the bucketed all-reduce on 2 ranks (half batch each) equal the
+"""2-GPU data parallel parity (NCCL and the two NVLink peer-memory reducers): gradients after the bucketed all-reduce on 2 ranks (half batch each) equal the
 single-process gradients of the full batch; losses average to the global loss. Needs >= 2 GPUs (skipped otherwise)."""
 import os
 
@@ -30,7 +30,7 @@ def _data(B):
             torch.randint(0, 10, (B,), generator=g))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, mode="nccl"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -43,15 +43,27 @@ def _worker(rank, world, port, q):
         sl = slice(rank * B // world, (rank + 1) * B // world)
         model = _build().cuda()
         opt = FusedAdamW(model.parameters(), lr=1e-4)
-        red = GradReducer(stores=opt.stores, bucket_mb=0.25)
-        assert len(red.buckets) > 2
+        red = GradReducer(stores=opt.stores, bucket_mb=0.25, tail_bucket_mb=0.05, mode=mode, comm_ctas=2)
+        assert len(red.buckets) > 2 and red.mode == mode
         flow = dl.Flow(n_steps=4)
+        # local (un-reduced) gradients, averaged by a plain NCCL all-reduce: what every mode must reproduce
         opt.zero_grad()
-        loss = flow.compute_loss(model, {"x": x0[sl].cuda(), "p": 0.0, "y": y[sl].cuda()}, t[sl].cuda(), noise=eps[sl].cuda())["loss"]
-        red.begin()
-        loss.backward()
-        red.finish()
+        flow.compute_loss(model, {"x": x0[sl].cuda(), "p": 0.0, "y": y[sl].cuda()}, t[sl].cuda(), noise=eps[sl].cuda())["loss"].backward()
+        want = opt.stores[0].flat_g.clone()
+        dist.all_reduce(want, op=dist.ReduceOp.AVG)
+        for _ in range(3):  # repeated steps: barrier / staging reuse, zero_grad against the peers' reads of the previous step
+            opt.zero_grad()
+            loss = flow.compute_loss(model, {"x": x0[sl].cuda(), "p": 0.0, "y": y[sl].cuda()}, t[sl].cuda(), noise=eps[sl].cuda())["loss"]
+            red.begin()
+            loss.backward()
+            red.finish()
         torch.cuda.synchronize()
+        got = opt.stores[0].flat_g
+        dev = ((got - want).norm() / want.norm()).item()
+        assert dev < 1e-5, f"mode {mode}: reduced gradients differ from the NCCL mean by {dev}"
+        both = [torch.empty_like(got) for _ in range(world)]
+        dist.all_gather(both, got)
+        assert all(torch.equal(both[0], b) for b in both), f"mode {mode}: ranks hold different reduced gradients"
         lt = loss.detach().clone()
         dist.all_reduce(lt, op=dist.ReduceOp.AVG)
         if rank == 0:
@@ -71,13 +83,15 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_gpu_gradients_match_single_process(cuda_device):
+@pytest.mark.parametrize("mode", ["nccl", "ce", "nvls"])
+def test_two_gpu_gradients_match_single_process(cuda_device, mode):
+    """mode: NCCL all-reduce / copy-engine pulls + dlb_reduce_pieces / in-switch multimem reduction (GradReducer docstring)"""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 400
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + 7 * ["nccl", "ce", "nvls"].index(mode)) % 400
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, mode)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=300) for _ in procs)
