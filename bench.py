@@ -327,9 +327,25 @@ def run_gpu_arm(args) -> None:
                   update_every=int(tr.get("ema_update_every", 10)))
     reducer = None
     if world > 1:
-        reducer = GradReducer(stores=opt.stores, bucket_mb=args.bucket_mb or GradReducer.DEFAULT_BUCKET_MB, tail_bucket_mb=args.tail_bucket_mb or None,
-                              process_group=make_reduce_group(args.comm_ctas) if args.dp_mode == "nccl" else None, reserve_sms=args.reserve_sms,
-                              mode=args.dp_mode, comm_ctas=args.comm_ctas)
+        def make_reducer(mode: str):
+            return GradReducer(stores=opt.stores, bucket_mb=args.bucket_mb or GradReducer.DEFAULT_BUCKET_MB, tail_bucket_mb=args.tail_bucket_mb or None,
+                               process_group=make_reduce_group(args.comm_ctas) if mode == "nccl" and args.comm_ctas > 0 else None,
+                               reserve_sms=args.reserve_sms, mode=mode, comm_ctas=max(1, args.comm_ctas))
+
+        mode, why = args.dp_mode, None
+        if mode != "nccl":  # symmetric (peer-mapped) memory must come up on EVERY rank, else all ranks use NCCL
+            ok = torch.ones(1, device=device)
+            try:
+                reducer = make_reducer(mode)
+            except Exception as e:  # noqa: BLE001
+                ok.zero_()
+                why = repr(e)[:200]
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() == 0:
+                print(f"[bench] rank {rank}: dp mode {mode!r} unavailable ({why or 'failed on another rank'}); using NCCL all-reduce", file=sys.stderr, flush=True)
+                mode, reducer = "nccl", None
+        if reducer is None:
+            reducer = make_reducer("nccl")
     n_params = sum(p.numel() for p in model.parameters())
 
     pool = 4
@@ -581,10 +597,10 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's dataloader.batch_size)")
     ap.add_argument("--bucket-mb", type=float, default=0.0, help="gradient bucket size (default: GradReducer.DEFAULT_BUCKET_MB)")
     ap.add_argument("--tail-bucket-mb", type=float, default=32.0, help="size cap of the buckets backward produces last (0 = same as --bucket-mb)")
-    ap.add_argument("--dp-mode", default="nccl", choices=["nccl", "ce", "nvls"], help="gradient reduction: NCCL all-reduce | copy-engine pulls over peer "
+    ap.add_argument("--dp-mode", default="ce", choices=["nccl", "ce", "nvls"], help="gradient reduction: NCCL all-reduce | copy-engine pulls over peer "
                     "memory + reduce kernel | in-switch multimem reduction kernel")
-    ap.add_argument("--comm-ctas", type=int, default=4, help="CTAs per gradient reduction (nccl: dedicated communicator, 0 = NCCL's default; nvls: kernel grid)")
-    ap.add_argument("--reserve-sms", type=int, default=4, help="SMs the persistent kernels leave to NCCL while buckets are in flight")
+    ap.add_argument("--comm-ctas", type=int, default=0, help="CTAs per gradient reduction (nccl: dedicated communicator, 0 = NCCL's default; nvls: kernel grid)")
+    ap.add_argument("--reserve-sms", type=int, default=0, help="SMs the persistent kernels leave to the collective while buckets are in flight")
     ap.add_argument("--sample-batch", type=int, default=64)
     ap.add_argument("--sample-batches", default="", help="comma-separated batch sweep for the sampling benchmark")
     ap.add_argument("--no-sample", action="store_true")

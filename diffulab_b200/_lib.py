@@ -6,10 +6,12 @@ There is no CPU or PyTorch fallback: if the shared library is missing or a call 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libdiffulab_b200.so"
+# DIFFULAB_B200_LIB: an alternative BUILD of the same library (same exported symbols), for same-box A/B timing in scripts/
+LIB_PATH = Path(os.environ["DIFFULAB_B200_LIB"]) if os.environ.get("DIFFULAB_B200_LIB") else _HERE / "libdiffulab_b200.so"
 
 _lib: C.CDLL | None = None
 

@@ -105,7 +105,7 @@ gate_residual_fwd_lean(const bf16* __restrict__ x, const bf16* __restrict__ a1, 
 // P = w (1 + scale), Q = b (1 + scale) + shift per sample in shared memory (rebuilt when the CTA's sample changes).
 // ---------------------------------------------------------------------------------------------------------
 template <int U, int UPL>
-__global__ void __launch_bounds__(WARPS * 32, 2)
+__global__ void __launch_bounds__(WARPS * 32, 3)
 ln_modulate_fwd_lean(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, const bf16* __restrict__ scale,
                      const bf16* __restrict__ shift, int64_t mod_ld, int rows_per_mod, bf16* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int R, float eps, int rows_per_cta) {
@@ -181,7 +181,7 @@ ln_modulate_fwd_lean(const bf16* __restrict__ x, const float* __restrict__ w, co
 // ---------------------------------------------------------------------------------------------------------
 constexpr int QK_WARPS = 4;  // 2 q-warps + 2 k-warps per CTA (the per-lane scale registers make this kernel register-heavy)
 template <int U, int UPL>
-__global__ void __launch_bounds__(QK_WARPS * 32, 3)
+__global__ void __launch_bounds__(QK_WARPS * 32, 4)
 qknorm_rope_fwd_lean(const bf16* __restrict__ qkv, int64_t ld_in, const float* __restrict__ sq, const float* __restrict__ sk,
                      const uint32_t* __restrict__ cs_t, const int32_t* __restrict__ pos_idx, int rot_half, int pos_offset, int tokens_per_sample,
                      int hd, bf16* __restrict__ out, int64_t ld_out, float* __restrict__ rrms_out, int R, float eps, int rows_per_cta) {
@@ -189,13 +189,17 @@ qknorm_rope_fwd_lean(const bf16* __restrict__ qkv, int64_t ld_in, const float* _
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int which = warp & 1;  // 0: q half-rows, 1: k half-rows
   const int row0 = blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
-  // loop invariants of this lane: learnable scales and the rotary pair index of every unit (-1: the unit does not rotate)
-  float sc[UPL][U];
+  // loop invariants of this lane: learnable scales (even / odd channels of every rotary pair, as packed fp32 pairs over two
+  // adjacent pairs) and the rotary pair index of every unit (-1: the unit does not rotate)
+  f32x2 sce[UPL][U / 4], sco[UPL][U / 4];
   int pj[UPL];
 #pragma unroll
   for (int u = 0; u < UPL; ++u) {
     const int c = (lane + 32 * u) * U;
-    ldf<U>((which ? sk : sq) + c, sc[u]);
+    float sc[U];
+    ldf<U>((which ? sk : sq) + c, sc);
+#pragma unroll
+    for (int j = 0; j < U / 4; ++j) { sce[u][j] = make_f32x2(sc[4 * j], sc[4 * j + 2]); sco[u][j] = make_f32x2(sc[4 * j + 1], sc[4 * j + 3]); }
     const int cl = c % hd;  // hd % 8 == 0 keeps a unit inside one head
     pj[u] = (cl >> 1) < rot_half ? (cl >> 1) : -1;
   }
@@ -207,18 +211,25 @@ qknorm_rope_fwd_lean(const bf16* __restrict__ qkv, int64_t ld_in, const float* _
   for (; r < row1; r += STEP) {
     if (r + STEP < row1) nxt.load(qkv + (int64_t)(r + STEP) * ld_in + col0, lane);
     const uint32_t* csr = cs_t + (int64_t)(pos_idx ? pos_idx[r] : pos_offset + r % tokens_per_sample) * rot_half;
-    float f[UPL][U];
-    cur.unpack(f);
-    float ss = 0.f;
+    // word j of a unit = channels (2j, 2j+1) = one rotary pair (even, odd). Two adjacent words are processed together as packed
+    // fp32 pairs E = (even_j, even_j+1), O = (odd_j, odd_j+1): FMUL2 / FFMA2 do two pairs per issue slot.
+    f32x2 E[UPL][U / 4], O[UPL][U / 4];
+    f32x2 ss2 = make_f32x2(0.f, 0.f);
 #pragma unroll
-    for (int u = 0; u < UPL; ++u) {
-      float t = 0.f;
+    for (int u = 0; u < UPL; ++u)
 #pragma unroll
-      for (int j = 0; j < U; ++j) t = fmaf(f[u][j], f[u][j], t);
-      ss += t;
-    }
-    const float rrms = rsqrtf(warp_sum(ss) * (1.f / d) + eps);
+      for (int j = 0; j < U / 4; ++j) {
+        const uint32_t w0 = cur.w[u][2 * j], w1 = cur.w[u][2 * j + 1];
+        E[u][j] = make_f32x2(blo(w0), blo(w1));
+        O[u][j] = make_f32x2(bhi(w0), bhi(w1));
+        ss2 = fma2(E[u][j], E[u][j], ss2);
+        ss2 = fma2(O[u][j], O[u][j], ss2);
+      }
+    float ss_lo, ss_hi;
+    split_f32x2(ss2, ss_lo, ss_hi);
+    const float rrms = rsqrtf(warp_sum(ss_lo + ss_hi) * (1.f / d) + eps);
     if (lane == 0 && rrms_out) rrms_out[(int64_t)r * 2 + which] = rrms;
+    const f32x2 rr2 = make_f32x2(rrms, rrms);
     Row<U, UPL> o;
 #pragma unroll
     for (int u = 0; u < UPL; ++u) {
@@ -228,15 +239,21 @@ qknorm_rope_fwd_lean(const bf16* __restrict__ qkv, int64_t ld_in, const float* _
         else { const uint2 v = __ldg(reinterpret_cast<const uint2*>(csr + pj[u])); cs[0] = v.x; cs[1] = v.y; }
       }
 #pragma unroll
-      for (int j = 0; j < U / 2; ++j) {
-        float e = f[u][2 * j] * rrms * sc[u][2 * j], od = f[u][2 * j + 1] * rrms * sc[u][2 * j + 1];
+      for (int j = 0; j < U / 4; ++j) {
+        f32x2 e2 = mul2(mul2(E[u][j], rr2), sce[u][j]), o2 = mul2(mul2(O[u][j], rr2), sco[u][j]);
         if (pj[u] >= 0) {  // (cos, sin) packed as bf16x2: the reference casts the tables to the activation dtype
-          const float c = blo(cs[j]), s = bhi(cs[j]);
-          const float re = e * c - od * s, ro = fmaf(e, s, od * c);
-          e = re;
-          od = ro;
+          const uint32_t c0 = cs[2 * j], c1 = cs[2 * j + 1];
+          const f32x2 C = make_f32x2(blo(c0), blo(c1)), S = make_f32x2(bhi(c0), bhi(c1));
+          const f32x2 nS = make_f32x2(__uint_as_float((c0 & 0xffff0000u) ^ 0x80000000u), __uint_as_float((c1 & 0xffff0000u) ^ 0x80000000u));
+          const f32x2 re = fma2(o2, nS, mul2(e2, C)), ro = fma2(e2, S, mul2(o2, C));  // e c - o s,  e s + o c
+          e2 = re;
+          o2 = ro;
         }
-        o.w[u][j] = pack_bf16x2(e, od);
+        float e_a, e_b, o_a, o_b;
+        split_f32x2(e2, e_a, e_b);
+        split_f32x2(o2, o_a, o_b);
+        o.w[u][2 * j] = pack_bf16x2(e_a, o_a);
+        o.w[u][2 * j + 1] = pack_bf16x2(e_b, o_b);
       }
     }
     o.store(out + (int64_t)r * ld_out + col0, lane);
@@ -305,11 +322,20 @@ ln_modulate_bwd_lean(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint8_t* my = ring + (size_t)warp * 2 * NIN * ROWB;
   const int row0 = blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
-  float S1[UPL][U], S2[UPL][U];
+  // column accumulators and all row arithmetic as packed fp32 pairs (FADD2 / FMUL2 / FFMA2: one issue slot per two channels)
+  f32x2 S1[UPL][U / 2], S2[UPL][U / 2];
 #pragma unroll
   for (int u = 0; u < UPL; ++u)
 #pragma unroll
-    for (int j = 0; j < U; ++j) { S1[u][j] = 0.f; S2[u][j] = 0.f; }
+    for (int j = 0; j < U / 2; ++j) { S1[u][j] = make_f32x2(0.f, 0.f); S2[u][j] = make_f32x2(0.f, 0.f); }
+  auto flush = [&](f32x2 (&S)[UPL][U / 2], float* dst) {
+    float acc[UPL][U];
+#pragma unroll
+    for (int u = 0; u < UPL; ++u)
+#pragma unroll
+      for (int j = 0; j < U / 2; ++j) { split_f32x2(S[u][j], acc[u][2 * j], acc[u][2 * j + 1]); S[u][j] = make_f32x2(0.f, 0.f); }
+    flush_columns<U, UPL>(acc, sAcc, dst, tid, lane);
+  };
   auto prefetch = [&](int r, int stage) {
     if (r < row1) {
       uint8_t* sb = my + stage * NIN * ROWB;
@@ -325,8 +351,8 @@ ln_modulate_bwd_lean(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
     const int sample = base / rows_per_mod;  // uniform over the CTA (row0 and rows_per_mod are multiples of 8)
     if (sample != cur_sample) {
       if (cur_sample >= 0) {
-        flush_columns<U, UPL>(S1, sAcc, acc1 + (int64_t)cur_sample * acc_ld, tid, lane);
-        flush_columns<U, UPL>(S2, sAcc, acc2 + (int64_t)cur_sample * acc_ld, tid, lane);
+        flush(S1, acc1 + (int64_t)cur_sample * acc_ld);
+        flush(S2, acc2 + (int64_t)cur_sample * acc_ld);
       }
       const bf16* sc = scale + (int64_t)sample * mod_ld;
       for (int j = tid; j < d; j += WARPS * 32) {
@@ -345,8 +371,9 @@ ln_modulate_bwd_lean(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
     if (r < row1) {
       const uint8_t* sb = my + stage * NIN * ROWB;
       const float nmr = -mean * rstd;
-      float q[UPL][U], xh[UPL][U];
-      float p1 = 0.f, p2 = 0.f;
+      const f32x2 rstd2 = make_f32x2(rstd, rstd), nmr2 = make_f32x2(nmr, nmr);
+      f32x2 q[UPL][U / 2], xh[UPL][U / 2];
+      f32x2 p1 = make_f32x2(0.f, 0.f), p2 = make_f32x2(0.f, 0.f);
 #pragma unroll
       for (int u = 0; u < UPL; ++u) {
         const int unit = lane + 32 * u;
@@ -355,24 +382,25 @@ ln_modulate_bwd_lean(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
         ldsu<U>(sb, unit, gw);
         ldsu<U>(sb + ROWB, unit, xw);
         ldf<U>(sG + unit * U, G);
-        float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-          const float g = (j & 1) ? bhi(gw[j >> 1]) : blo(gw[j >> 1]);
-          const float xv = (j & 1) ? bhi(xw[j >> 1]) : blo(xw[j >> 1]);
-          xh[u][j] = fmaf(xv, rstd, nmr);
-          S1[u][j] += g;
-          S2[u][j] = fmaf(g, xh[u][j], S2[u][j]);
-          q[u][j] = g * G[j];
-          t1 += q[u][j];
-          t2 = fmaf(q[u][j], xh[u][j], t2);
+        for (int j = 0; j < U / 2; ++j) {
+          const f32x2 g = unpack2(gw[j]);
+          xh[u][j] = fma2(unpack2(xw[j]), rstd2, nmr2);
+          S1[u][j] = add2(S1[u][j], g);
+          S2[u][j] = fma2(g, xh[u][j], S2[u][j]);
+          q[u][j] = mul2(g, make_f32x2(G[2 * j], G[2 * j + 1]));
+          p1 = add2(p1, q[u][j]);
+          p2 = fma2(q[u][j], xh[u][j], p2);
         }
-        p1 += t1;
-        p2 += t2;
       }
+      float p1a, p1b, p2a, p2b;
+      split_f32x2(p1, p1a, p1b);
+      split_f32x2(p2, p2a, p2b);
+      float s1 = p1a + p1b, s2 = p2a + p2b;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { p1 += __shfl_xor_sync(0xffffffffu, p1, o); p2 += __shfl_xor_sync(0xffffffffu, p2, o); }
-      const float c1 = rstd * p1 * (1.f / d), c2 = rstd * p2 * (1.f / d);  // rstd * mean(q), rstd * mean(q xhat)
+      for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+      const float c1 = rstd * s1 * (1.f / d), c2 = rstd * s2 * (1.f / d);  // rstd * mean(q), rstd * mean(q xhat)
+      const f32x2 nc1 = make_f32x2(-c1, -c1), nc2 = make_f32x2(-c2, -c2);
       bf16* out = dx + (int64_t)r * d;
 #pragma unroll
       for (int u = 0; u < UPL; ++u) {
@@ -381,10 +409,9 @@ ln_modulate_bwd_lean(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
         if constexpr (HAS_RES) ldsu<U>(sb + 2 * ROWB, unit, rw);
 #pragma unroll
         for (int j = 0; j < U / 2; ++j) {
-          float t0 = fmaf(-xh[u][2 * j], c2, fmaf(q[u][2 * j], rstd, -c1));
-          float t1 = fmaf(-xh[u][2 * j + 1], c2, fmaf(q[u][2 * j + 1], rstd, -c1));
-          if constexpr (HAS_RES) { t0 += blo(rw[j]); t1 += bhi(rw[j]); }
-          ow[j] = pack_bf16x2(t0, t1);
+          f32x2 t = fma2(xh[u][j], nc2, fma2(q[u][j], rstd2, nc1));
+          if constexpr (HAS_RES) t = add2(t, unpack2(rw[j]));
+          ow[j] = pack2(t);
         }
         stu<U>(out + unit * U, ow);
       }
@@ -393,8 +420,8 @@ ln_modulate_bwd_lean(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
   }
   cp_async_wait<0>();
   if (cur_sample >= 0) {
-    flush_columns<U, UPL>(S1, sAcc, acc1 + (int64_t)cur_sample * acc_ld, tid, lane);
-    flush_columns<U, UPL>(S2, sAcc, acc2 + (int64_t)cur_sample * acc_ld, tid, lane);
+    flush(S1, acc1 + (int64_t)cur_sample * acc_ld);
+    flush(S2, acc2 + (int64_t)cur_sample * acc_ld);
   }
 }
 
@@ -469,16 +496,23 @@ qknorm_rope_bwd_lean(const bf16* __restrict__ dqk, int64_t ld_dqk, const bf16* _
   uint8_t* my = ring + (size_t)warp * QB_NS * 2 * ROWB;
   const int row0 = blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
   const int col0 = which * d;
-  float sc[UPL][U], S[UPL][U];
+  // Packed fp32 pairs over two adjacent rotary pairs, as in the forward kernel: E = (even_j, even_j+1), O = (odd_j, odd_j+1).
+  f32x2 sce[UPL][U / 4], sco[UPL][U / 4], SE[UPL][U / 4], SO[UPL][U / 4];
   int pj[UPL];
 #pragma unroll
   for (int u = 0; u < UPL; ++u) {
     const int c = (lane + 32 * u) * U;
-    ldf<U>((which ? sk : sq) + c, sc[u]);
+    float sc[U];
+    ldf<U>((which ? sk : sq) + c, sc);
     const int cl = c % hd;
     pj[u] = (cl >> 1) < rot_half ? (cl >> 1) : -1;
 #pragma unroll
-    for (int j = 0; j < U; ++j) S[u][j] = 0.f;
+    for (int j = 0; j < U / 4; ++j) {
+      sce[u][j] = make_f32x2(sc[4 * j], sc[4 * j + 2]);
+      sco[u][j] = make_f32x2(sc[4 * j + 1], sc[4 * j + 3]);
+      SE[u][j] = make_f32x2(0.f, 0.f);
+      SO[u][j] = make_f32x2(0.f, 0.f);
+    }
   }
   constexpr int STEP = WARPS / 2;
   auto prefetch = [&](int r, int stage) {
@@ -495,12 +529,13 @@ qknorm_rope_bwd_lean(const bf16* __restrict__ dqk, int64_t ld_dqk, const bf16* _
   for (; r < row1; r += STEP, stage = stage == QB_NS - 1 ? 0 : stage + 1) {
     prefetch(r + 2 * STEP, stage >= 1 ? stage - 1 : QB_NS - 1);  // (stage + 2) % 3: the stage released one iteration ago
     const float rrms = __ldg(rrms_in + (int64_t)r * 2 + which);
+    const f32x2 rr2 = make_f32x2(rrms, rrms);
     const uint32_t* csr = cs_t + (int64_t)(pos_idx ? pos_idx[r] : pos_offset + r % tokens_per_sample) * rot_half;
     cp_async_wait<2>();
     __syncwarp();
     const uint8_t* sb = my + stage * 2 * ROWB;
-    float gn[UPL][U], xr[UPL][U];
-    float dot = 0.f;
+    f32x2 gne[UPL][U / 4], gno[UPL][U / 4], xe[UPL][U / 4], xo[UPL][U / 4];
+    f32x2 dot2 = make_f32x2(0.f, 0.f);
 #pragma unroll
     for (int u = 0; u < UPL; ++u) {
       const int unit = lane + 32 * u;
@@ -511,36 +546,44 @@ qknorm_rope_bwd_lean(const bf16* __restrict__ dqk, int64_t ld_dqk, const bf16* _
         if constexpr (U == 8) { const uint4 v = __ldg(reinterpret_cast<const uint4*>(csr + pj[u])); cs[0] = v.x; cs[1] = v.y; cs[2] = v.z; cs[3] = v.w; }
         else { const uint2 v = __ldg(reinterpret_cast<const uint2*>(csr + pj[u])); cs[0] = v.x; cs[1] = v.y; }
       }
-      float t = 0.f;
 #pragma unroll
-      for (int j = 0; j < U / 2; ++j) {
-        float ge = blo(gw[j]), go = bhi(gw[j]);
-        if (pj[u] >= 0) {
-          const float c = blo(cs[j]), sn = bhi(cs[j]);
-          const float e2 = fmaf(go, sn, ge * c), o2 = fmaf(go, c, -ge * sn);
+      for (int j = 0; j < U / 4; ++j) {
+        f32x2 ge = make_f32x2(blo(gw[2 * j]), blo(gw[2 * j + 1])), go = make_f32x2(bhi(gw[2 * j]), bhi(gw[2 * j + 1]));
+        if (pj[u] >= 0) {  // transposed rotation: e' = e c + o s,  o' = o c - e s
+          const uint32_t c0 = cs[2 * j], c1 = cs[2 * j + 1];
+          const f32x2 C = make_f32x2(blo(c0), blo(c1)), S = make_f32x2(bhi(c0), bhi(c1));
+          const f32x2 nS = make_f32x2(__uint_as_float((c0 & 0xffff0000u) ^ 0x80000000u), __uint_as_float((c1 & 0xffff0000u) ^ 0x80000000u));
+          const f32x2 e2 = fma2(go, S, mul2(ge, C)), o2 = fma2(ge, nS, mul2(go, C));
           ge = e2;
           go = o2;
         }
-        const float xe = blo(xw[j]) * rrms, xo = bhi(xw[j]) * rrms;
-        xr[u][2 * j] = xe;
-        xr[u][2 * j + 1] = xo;
-        S[u][2 * j] = fmaf(ge, bf16_round(xe), S[u][2 * j]);  // the reference multiplies the bf16-rounded normalised value
-        S[u][2 * j + 1] = fmaf(go, bf16_round(xo), S[u][2 * j + 1]);
-        gn[u][2 * j] = ge * sc[u][2 * j];
-        gn[u][2 * j + 1] = go * sc[u][2 * j + 1];
-        t = fmaf(gn[u][2 * j], xe, t);
-        t = fmaf(gn[u][2 * j + 1], xo, t);
+        xe[u][j] = mul2(make_f32x2(blo(xw[2 * j]), blo(xw[2 * j + 1])), rr2);
+        xo[u][j] = mul2(make_f32x2(bhi(xw[2 * j]), bhi(xw[2 * j + 1])), rr2);
+        // the reference multiplies the bf16-rounded normalised value into the scale gradient
+        SE[u][j] = fma2(ge, unpack2(pack2(xe[u][j])), SE[u][j]);
+        SO[u][j] = fma2(go, unpack2(pack2(xo[u][j])), SO[u][j]);
+        gne[u][j] = mul2(ge, sce[u][j]);
+        gno[u][j] = mul2(go, sco[u][j]);
+        dot2 = fma2(gne[u][j], xe[u][j], dot2);
+        dot2 = fma2(gno[u][j], xo[u][j], dot2);
       }
-      dot += t;
     }
-    dot = warp_sum(dot) * (1.f / d);
+    float dot_a, dot_b;
+    split_f32x2(dot2, dot_a, dot_b);
+    const float dot = warp_sum(dot_a + dot_b) * (1.f / d);
+    const f32x2 ndot2 = make_f32x2(-dot, -dot);
     bf16* out = dqkv + (int64_t)r * ld_out + col0;
 #pragma unroll
     for (int u = 0; u < UPL; ++u) {
       uint32_t ow[U / 2];
 #pragma unroll
-      for (int j = 0; j < U / 2; ++j)
-        ow[j] = pack_bf16x2(rrms * fmaf(-xr[u][2 * j], dot, gn[u][2 * j]), rrms * fmaf(-xr[u][2 * j + 1], dot, gn[u][2 * j + 1]));
+      for (int j = 0; j < U / 4; ++j) {
+        float e_a, e_b, o_a, o_b;
+        split_f32x2(mul2(rr2, fma2(xe[u][j], ndot2, gne[u][j])), e_a, e_b);
+        split_f32x2(mul2(rr2, fma2(xo[u][j], ndot2, gno[u][j])), o_a, o_b);
+        ow[2 * j] = pack_bf16x2(e_a, o_a);
+        ow[2 * j + 1] = pack_bf16x2(e_b, o_b);
+      }
       stu<U>(out + (lane + 32 * u) * U, ow);
     }
     __syncwarp();
@@ -553,7 +596,16 @@ qknorm_rope_bwd_lean(const bf16* __restrict__ dqk, int64_t ld_dqk, const bf16* _
 #pragma unroll
     for (int u = 0; u < UPL; ++u)
 #pragma unroll
-      for (int j = 0; j < U; ++j) atomicAdd(mine + (lane + 32 * u) * U + j, S[u][j]);
+      for (int j = 0; j < U / 4; ++j) {
+        float e_a, e_b, o_a, o_b;
+        split_f32x2(SE[u][j], e_a, e_b);
+        split_f32x2(SO[u][j], o_a, o_b);
+        float* col = mine + (lane + 32 * u) * U + 4 * j;
+        atomicAdd(col, e_a);
+        atomicAdd(col + 1, o_a);
+        atomicAdd(col + 2, e_b);
+        atomicAdd(col + 3, o_b);
+      }
     __syncthreads();
     for (int c4 = tid; c4 < 2 * d / 4; c4 += WARPS * 32) {
       float* dst = c4 < d / 4 ? dsq + c4 * 4 : dsk + (c4 - d / 4) * 4;
