@@ -292,7 +292,7 @@ def run_gpu_arm(args) -> None:
     import diffulab_b200 as dl
     from diffulab_b200 import _lib, ops
     from diffulab_b200.synthetic import Workload, build_workload
-    from diffulab_b200.training import EMA, FusedAdamW, GradReducer, make_reduce_group, training_step
+    from diffulab_b200.training import EMA, DevicePrefetcher, FusedAdamW, GradReducer, LossReader, make_reduce_group, training_step
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -359,9 +359,17 @@ def run_gpu_arm(args) -> None:
     def step_resident(i: int):
         return training_step(diffuser, opt, fresh(dev[i % pool]), wl.p_cfg, reducer, ema=ema)
 
-    def step_e2e(i: int) -> float:
-        losses = training_step(diffuser, opt, Workload.to_step(host[i % pool], device, non_blocking=True), wl.p_cfg, reducer, ema=ema)
-        return sum(float(v.item()) for v in losses.values())  # D2H read of the step's result, every step
+    def run_e2e(n: int) -> float:
+        """n steps through the public API with HOST batches: every step's inputs are copied from pinned host memory (the copy of
+        batch i + 1 runs on a side stream while step i computes) and every step's losses are read back to the host (asynchronously:
+        the value of step i is collected while step i + 1 runs, the last one after the loop)."""
+        reader, total = LossReader(), 0.0
+        move = lambda b, dev_, non_blocking=True: Workload.to_step(b, dev_, non_blocking=non_blocking)  # noqa: E731
+        for batch in DevicePrefetcher((host[i % pool] for i in range(n)), device, move=move):
+            got = reader.push(training_step(diffuser, opt, batch, wl.p_cfg, reducer, ema=ema))
+            total += sum(got.values()) if got else 0.0
+        total += sum(reader.flush().values())
+        return total
 
     def barrier():
         if world > 1:
@@ -397,14 +405,13 @@ def run_gpu_arm(args) -> None:
     final_losses = {k: float(v.item()) for k, v in last.items()}
 
     # ---- timed region 2: end to end through the public API with host batches -------------------------------
-    for i in range(2):
-        step_e2e(i)
+    run_e2e(2)
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_e2e(i)
+    e2e_loss_sum = run_e2e(args.steps)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert e2e_loss_sum == e2e_loss_sum and e2e_loss_sum > 0, "end-to-end leg produced no finite losses"
     e2e_value = B * world * args.steps / e2e_s
     h2d = Workload.nbytes(host[0])
 

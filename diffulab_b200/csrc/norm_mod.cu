@@ -992,7 +992,7 @@ DLB_EXPORT int dlb_ln_modulate_fwd(const void* x, const float* w, const float* b
   // lean warp-per-row kernel (rowwise_lean.cuh): per-sample modulation, exact per-lane unit split of the channels
   static const bool no_lean = getenv("DLB_NO_LEAN") != nullptr;  // tests: force the general kernels
   if (!no_lean && rows_per_mod % lean::WARPS == 0 && R < (1ll << 31) && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0) {
-    const int rpc = lean::rows_per_cta_for((int)R, dlb_num_sms() * 2);
+    const int rpc = lean::rows_per_cta_for((int)R, dlb_num_sms() * 3);  // 3 CTAs / SM resident (80 registers)
     const int grid_l = (int)((R + rpc - 1) / rpc);
     DLB_LEAN_SWITCH(d, {
       lean::ln_modulate_fwd_lean<U, UPL><<<grid_l, lean::WARPS * 32, 0, stream>>>((const bf16*)x, w, b, (const bf16*)scale, (const bf16*)shift, mod_ld,
@@ -1055,7 +1055,7 @@ DLB_EXPORT int dlb_ln_modulate_bwd(const void* dy, const void* x, const float* m
       ((uintptr_t)dx % 16) == 0 && ((uintptr_t)dres % 16) == 0 && ((uintptr_t)dscale % 16) == 0 && ((uintptr_t)dshift % 16) == 0 && dmod_ld % 4 == 0) {
     const int rpc = lean::rows_per_cta_for((int)R, dlb_num_sms());
     const int grid_l = (int)((R + rpc - 1) / rpc);
-    const size_t smem_l = (size_t)2 * d * 4 + (size_t)lean::WARPS * 2 * (dres ? 3 : 2) * d * 2;
+    const size_t smem_l = (size_t)2 * d * 4 + (size_t)lean::WARPS * lean::LNB_NS * (dres ? 3 : 2) * d * 2;
     if (smem_l <= 220 * 1024) {
       DLB_LEAN_SWITCH(d, {
         if (dres) {

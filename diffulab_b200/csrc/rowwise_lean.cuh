@@ -115,8 +115,11 @@ ln_modulate_fwd_lean(const bf16* __restrict__ x, const float* __restrict__ w, co
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row0 = blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);  // row0 % 8 == 0, rows_per_mod % 8 == 0
   int cur_sample = -1;
-  Row<U, UPL> cur, nxt;
+  // TWO rows in flight per warp beyond the one being processed: at 16-24 resident warps per SM one row each (2.3 KB) is ~40-55 KB
+  // in flight per SM, which by Little's law caps the kernel near 0.55 of the HBM peak (measured); two rows lift that bound
+  Row<U, UPL> cur, nxt, nx2;
   if (row0 + warp < row1) cur.load(x + (int64_t)(row0 + warp) * d, lane);
+  if (row0 + warp + WARPS < row1) nxt.load(x + (int64_t)(row0 + warp + WARPS) * d, lane);
   for (int base = row0; base < row1; base += WARPS) {
     const int sample = base / rows_per_mod;  // uniform over the CTA: all 8 rows of this step belong to one sample
     if (sample != cur_sample) {
@@ -132,7 +135,7 @@ ln_modulate_fwd_lean(const bf16* __restrict__ x, const float* __restrict__ w, co
       cur_sample = sample;
     }
     const int r = base + warp;
-    if (r + WARPS < row1) nxt.load(x + (int64_t)(r + WARPS) * d, lane);
+    if (r + 2 * WARPS < row1) nx2.load(x + (int64_t)(r + 2 * WARPS) * d, lane);
     if (r < row1) {
       // packed fp32 pairs (FADD2 / FFMA2): one issue slot per two channels; two-pass statistics as before
       f32x2 f[UPL][U / 2];
@@ -168,6 +171,7 @@ ln_modulate_fwd_lean(const bf16* __restrict__ x, const float* __restrict__ w, co
       o.store(y + (int64_t)r * d, lane);
     }
     cur = nxt;
+    nxt = nx2;
   }
 }
 
@@ -181,7 +185,7 @@ ln_modulate_fwd_lean(const bf16* __restrict__ x, const float* __restrict__ w, co
 // ---------------------------------------------------------------------------------------------------------
 constexpr int QK_WARPS = 4;  // 2 q-warps + 2 k-warps per CTA (the per-lane scale registers make this kernel register-heavy)
 template <int U, int UPL>
-__global__ void __launch_bounds__(QK_WARPS * 32, 4)
+__global__ void __launch_bounds__(QK_WARPS * 32, 3)
 qknorm_rope_fwd_lean(const bf16* __restrict__ qkv, int64_t ld_in, const float* __restrict__ sq, const float* __restrict__ sk,
                      const uint32_t* __restrict__ cs_t, const int32_t* __restrict__ pos_idx, int rot_half, int pos_offset, int tokens_per_sample,
                      int hd, bf16* __restrict__ out, int64_t ld_out, float* __restrict__ rrms_out, int R, float eps, int rows_per_cta) {
@@ -205,11 +209,12 @@ qknorm_rope_fwd_lean(const bf16* __restrict__ qkv, int64_t ld_in, const float* _
   }
   const int col0 = which * d;
   constexpr int STEP = QK_WARPS / 2;  // token rows advanced per iteration by the warps of each half
-  Row<U, UPL> cur, nxt;
+  Row<U, UPL> cur, nxt, nx2;  // two half-rows in flight per warp beyond the current one (see ln_modulate_fwd_lean)
   int r = row0 + (warp >> 1);
   if (r < row1) cur.load(qkv + (int64_t)r * ld_in + col0, lane);
+  if (r + STEP < row1) nxt.load(qkv + (int64_t)(r + STEP) * ld_in + col0, lane);
   for (; r < row1; r += STEP) {
-    if (r + STEP < row1) nxt.load(qkv + (int64_t)(r + STEP) * ld_in + col0, lane);
+    if (r + 2 * STEP < row1) nx2.load(qkv + (int64_t)(r + 2 * STEP) * ld_in + col0, lane);
     const uint32_t* csr = cs_t + (int64_t)(pos_idx ? pos_idx[r] : pos_offset + r % tokens_per_sample) * rot_half;
     // word j of a unit = channels (2j, 2j+1) = one rotary pair (even, odd). Two adjacent words are processed together as packed
     // fp32 pairs E = (even_j, even_j+1), O = (odd_j, odd_j+1): FMUL2 / FFMA2 do two pairs per issue slot.
@@ -258,6 +263,7 @@ qknorm_rope_fwd_lean(const bf16* __restrict__ qkv, int64_t ld_in, const float* _
     }
     o.store(out + (int64_t)r * ld_out + col0, lane);
     cur = nxt;
+    nxt = nx2;
   }
 }
 
@@ -309,6 +315,7 @@ __device__ __forceinline__ void flush_columns(float (&acc)[UPL][U], float* sAcc,
 //   dx = rstd (q - mean(q) - xhat mean(q xhat)) (+ dres),  q = dy G,  G = w (1 + scale)
 // and the per-sample column sums S1 = sum dy, S2 = sum dy xhat (finalised by ln_modulate_bwd_finalize_kernel).
 // ---------------------------------------------------------------------------------------------------------
+constexpr int LNB_NS = 3;  // ring depth: two rows (x 2-3 tensors) in flight per warp
 template <int U, int UPL, bool HAS_RES>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 ln_modulate_bwd_lean(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
@@ -318,9 +325,9 @@ ln_modulate_bwd_lean(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
   extern __shared__ __align__(16) uint8_t smem[];
   float* sG = reinterpret_cast<float*>(smem);            // [d] G of the current sample
   float* sAcc = sG + d;                                  // [d] flush buffer
-  uint8_t* ring = reinterpret_cast<uint8_t*>(sAcc + d);  // [WARPS][2][NIN][ROWB]
+  uint8_t* ring = reinterpret_cast<uint8_t*>(sAcc + d);  // [WARPS][LNB_NS][NIN][ROWB]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint8_t* my = ring + (size_t)warp * 2 * NIN * ROWB;
+  uint8_t* my = ring + (size_t)warp * LNB_NS * NIN * ROWB;
   const int row0 = blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
   // column accumulators and all row arithmetic as packed fp32 pairs (FADD2 / FMUL2 / FFMA2: one issue slot per two channels)
   f32x2 S1[UPL][U / 2], S2[UPL][U / 2];
@@ -346,8 +353,9 @@ ln_modulate_bwd_lean(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
     cp_async_commit();
   };
   prefetch(row0 + warp, 0);
+  prefetch(row0 + warp + WARPS, 1);
   int cur_sample = -1, stage = 0;
-  for (int base = row0; base < row1; base += WARPS, stage ^= 1) {
+  for (int base = row0; base < row1; base += WARPS, stage = stage == LNB_NS - 1 ? 0 : stage + 1) {
     const int sample = base / rows_per_mod;  // uniform over the CTA (row0 and rows_per_mod are multiples of 8)
     if (sample != cur_sample) {
       if (cur_sample >= 0) {
@@ -363,10 +371,10 @@ ln_modulate_bwd_lean(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
       cur_sample = sample;
     }
     const int r = base + warp;
-    prefetch(r + WARPS, stage ^ 1);
+    prefetch(r + 2 * WARPS, stage >= 1 ? stage - 1 : LNB_NS - 1);  // (stage + 2) % 3: the stage released one iteration ago
     float mean = 0.f, rstd = 0.f;
     if (r < row1) { mean = __ldg(mean_in + r); rstd = __ldg(rstd_in + r); }
-    cp_async_wait<1>();
+    cp_async_wait<2>();
     __syncwarp();
     if (r < row1) {
       const uint8_t* sb = my + stage * NIN * ROWB;
@@ -480,7 +488,7 @@ gate_residual_bwd_lean(const bf16* __restrict__ dout, const bf16* __restrict__ a
 // rotated half-row; output: gradient wrt the raw projection half-row; the gradient of the learnable scale accumulates per lane.
 //   gz = R^T g (rotation transposed),  dscale += gz * bf16(x rrms),  gn = gz * scale,  dx = rrms (gn - x rrms mean(gn x rrms))
 // ---------------------------------------------------------------------------------------------------------
-constexpr int QB_NS = 3;  // ring depth: two rows in flight per warp (a half-row is only 2 x d bytes)
+constexpr int QB_NS = 4;  // ring depth: three half-rows (x 2 tensors) in flight per warp
 template <int U, int UPL>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 qknorm_rope_bwd_lean(const bf16* __restrict__ dqk, int64_t ld_dqk, const bf16* __restrict__ qkv, int64_t ld_in, const float* __restrict__ sq,
@@ -526,12 +534,13 @@ qknorm_rope_bwd_lean(const bf16* __restrict__ dqk, int64_t ld_dqk, const bf16* _
   int r = row0 + (warp >> 1), stage = 0;
   prefetch(r, 0);
   prefetch(r + STEP, 1);
+  prefetch(r + 2 * STEP, 2);
   for (; r < row1; r += STEP, stage = stage == QB_NS - 1 ? 0 : stage + 1) {
-    prefetch(r + 2 * STEP, stage >= 1 ? stage - 1 : QB_NS - 1);  // (stage + 2) % 3: the stage released one iteration ago
+    prefetch(r + 3 * STEP, stage >= 1 ? stage - 1 : QB_NS - 1);  // (stage + 3) % 4: the stage released one iteration ago
     const float rrms = __ldg(rrms_in + (int64_t)r * 2 + which);
     const f32x2 rr2 = make_f32x2(rrms, rrms);
     const uint32_t* csr = cs_t + (int64_t)(pos_idx ? pos_idx[r] : pos_offset + r % tokens_per_sample) * rot_half;
-    cp_async_wait<2>();
+    cp_async_wait<3>();
     __syncwarp();
     const uint8_t* sb = my + stage * 2 * ROWB;
     f32x2 gne[UPL][U / 4], gno[UPL][U / 4], xe[UPL][U / 4], xo[UPL][U / 4];

@@ -516,6 +516,100 @@ class GradReducer:
                 "exposed_tail_ms": round(max(done) - end_bwd, 3) if done else 0.0}
 
 
+class DevicePrefetcher:
+    """Iterates host batches (pinned memory) as device batches, copying batch i + 1 on a side stream while step i computes —
+    the place of `accelerator.prepare(train_dataloader)` in the reference's loop (base_trainer.py:277-307: the prepared DataLoader
+    moves every batch to the device). `move(batch, device, non_blocking=True)` builds the device batch (default: tensors / nested
+    dicts of tensors are moved, everything else passes through). The compute stream waits for the copy's event, so a batch is
+    never read before it has landed; the caching allocator is told about the cross-stream use (record_stream)."""
+
+    def __init__(self, batches: Iterable[Any], device: torch.device, move: Any = None):
+        self.it = iter(batches)
+        self.device = torch.device(device)
+        self.move = move or self._move
+        self.stream = torch.cuda.Stream(device=self.device)
+        self._next: tuple[Any, torch.cuda.Event] | None = None
+        self._fill()
+
+    @staticmethod
+    def _move(b: Any, device: torch.device, non_blocking: bool = True) -> Any:
+        if isinstance(b, Tensor):
+            return b.to(device, non_blocking=non_blocking)
+        if isinstance(b, dict):
+            return {k: DevicePrefetcher._move(v, device, non_blocking) for k, v in b.items()}
+        return b
+
+    @staticmethod
+    def _tensors(b: Any):
+        if isinstance(b, Tensor):
+            yield b
+        elif isinstance(b, dict):
+            for v in b.values():
+                yield from DevicePrefetcher._tensors(v)
+
+    def _fill(self) -> None:
+        try:
+            host = next(self.it)
+        except StopIteration:
+            self._next = None
+            return
+        with torch.cuda.stream(self.stream):
+            dev = self.move(host, self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        self._next = (dev, ev)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> Any:
+        if self._next is None:
+            raise StopIteration
+        dev, ev = self._next
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for t in self._tensors(dev):
+            t.record_stream(cur)
+        self._fill()  # the next batch's copy overlaps the step the caller is about to run
+        return dev
+
+
+class LossReader:
+    """Per-step device -> host read of the loss dict without stalling the launch queue: `push(losses)` starts an asynchronous
+    copy into pinned memory and returns the PREVIOUS step's values (None on the first call); `flush()` returns the last one.
+    (The reference calls `loss.item()` inside the step, base_trainer.py:125-137, which serialises host and device every step.)"""
+
+    def __init__(self):
+        self._pending: tuple[list[str], Tensor, torch.cuda.Event] | None = None
+        self._host: list[Tensor] = []
+        self._i = 0
+
+    def _take(self) -> dict[str, float] | None:
+        if self._pending is None:
+            return None
+        keys, host, ev = self._pending
+        ev.synchronize()
+        self._pending = None
+        return {k: float(host[i]) for i, k in enumerate(keys)}
+
+    def push(self, losses: dict[str, Tensor]) -> dict[str, float] | None:
+        keys = list(losses)
+        dev = torch.stack([losses[k].detach().float().reshape(()) for k in keys])
+        if len(self._host) < 2 or self._host[0].numel() != len(keys):
+            self._host = [torch.empty(len(keys), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        prev = self._take()
+        host = self._host[self._i]
+        self._i ^= 1
+        host.copy_(dev, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending = (keys, host, ev)
+        return prev
+
+    def flush(self) -> dict[str, float] | None:
+        return self._take()
+
+
 def training_step(diffuser, optimizer: torch.optim.Optimizer, batch: dict[str, Any], p_classifier_free_guidance: float = 0.0,
                   reducer: GradReducer | None = None, scheduler: Any | None = None, per_batch_scheduler: bool = False,
                   ema: EMA | None = None) -> dict[str, Tensor]:

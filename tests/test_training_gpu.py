@@ -196,3 +196,25 @@ def test_fused_ema_matches_restatement(cuda_device, beta, after, every):
     assert ema.step == 25
     assert rel_l2(got, ref) < 1e-6
     assert rel_l2(got, history[-1]) > 1e-4  # it is an average, not a copy
+
+
+def test_device_prefetcher_and_loss_reader(cuda_device):
+    """host batches arrive on the device in order and intact while copies run on a side stream; losses are read back one step late"""
+    from diffulab_b200.training import DevicePrefetcher, LossReader
+
+    g = torch.Generator().manual_seed(5)
+    host = [{"model_inputs": {"x": torch.randn(4, 3, 8, 8, generator=g).pin_memory(), "y": torch.randint(0, 9, (4,), generator=g).pin_memory()},
+             "extra": {"dst_features": torch.randn(4, 16, 8, generator=g).pin_memory()}, "tag": i} for i in range(5)]
+    reader, seen, sums = LossReader(), [], []
+    for b in DevicePrefetcher(host, "cuda"):
+        i = b["tag"]
+        assert b["model_inputs"]["x"].is_cuda and torch.equal(b["model_inputs"]["x"].cpu(), host[i]["model_inputs"]["x"])
+        assert torch.equal(b["model_inputs"]["y"].cpu(), host[i]["model_inputs"]["y"]) and torch.equal(b["extra"]["dst_features"].cpu(), host[i]["extra"]["dst_features"])
+        seen.append(i)
+        prev = reader.push({"loss": b["model_inputs"]["x"].sum(), "aux": b["extra"]["dst_features"].mean()})
+        if prev is not None:
+            sums.append(prev)
+    sums.append(reader.flush())
+    assert seen == list(range(5)) and len(sums) == 5 and reader.flush() is None
+    for i, s in enumerate(sums):
+        assert abs(s["loss"] - float(host[i]["model_inputs"]["x"].sum())) < 1e-3 and abs(s["aux"] - float(host[i]["extra"]["dst_features"].mean())) < 1e-6
