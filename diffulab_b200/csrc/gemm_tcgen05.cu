@@ -114,8 +114,9 @@ __device__ __forceinline__ void epilogue_tile(const CUtensorMap& tmC, const CUte
       for (int j = 0; j < 8; ++j) {
         const int off = (j ^ (lane & 7)) << 4;
         const bf16x8 av = *reinterpret_cast<const bf16x8*>(rowa + off), gv = *reinterpret_cast<const bf16x8*>(rowg + off);
-        // ~10 issue slots per element instead of ~20 (packed fp32 pairs): with 2 epilogue warps per scheduler the epilogue of a
-        // 128 x 128 tile must fit under the 2304-cycle main loop of a K = 1152 tile
+        // packed fp32 pairs: ~10 issue slots per element instead of ~20. Neutral in the train step (same-box A/B 11.8 vs 12.0 ms):
+        // the epilogue is bound by the latency of the H-tile loads and of the stores they wait behind, not by issue. A variant that
+        // prefetched H into registers with plain loads (no load behind a store) measured 0.7 ms SLOWER (uncoalesced row loads).
         bf16x8 dav, dgv;
         const f32x2 half2 = make_f32x2(0.5f, 0.5f), one2 = make_f32x2(1.f, 1.f), mone2 = make_f32x2(-1.f, -1.f);
 #pragma unroll

@@ -992,7 +992,7 @@ DLB_EXPORT int dlb_ln_modulate_fwd(const void* x, const float* w, const float* b
   // lean warp-per-row kernel (rowwise_lean.cuh): per-sample modulation, exact per-lane unit split of the channels
   static const bool no_lean = getenv("DLB_NO_LEAN") != nullptr;  // tests: force the general kernels
   if (!no_lean && rows_per_mod % lean::WARPS == 0 && R < (1ll << 31) && ((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0) {
-    const int rpc = lean::rows_per_cta_for((int)R, dlb_num_sms() * 3);  // 3 CTAs / SM resident (80 registers)
+    const int rpc = lean::rows_per_cta_for((int)R, dlb_num_sms() * 2);  // 2 CTAs / SM resident, 3 rows in flight per warp
     const int grid_l = (int)((R + rpc - 1) / rpc);
     DLB_LEAN_SWITCH(d, {
       lean::ln_modulate_fwd_lean<U, UPL><<<grid_l, lean::WARPS * 32, 0, stream>>>((const bf16*)x, w, b, (const bf16*)scale, (const bf16*)shift, mod_ld,

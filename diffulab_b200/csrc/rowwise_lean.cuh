@@ -105,7 +105,7 @@ gate_residual_fwd_lean(const bf16* __restrict__ x, const bf16* __restrict__ a1, 
 // P = w (1 + scale), Q = b (1 + scale) + shift per sample in shared memory (rebuilt when the CTA's sample changes).
 // ---------------------------------------------------------------------------------------------------------
 template <int U, int UPL>
-__global__ void __launch_bounds__(WARPS * 32, 3)
+__global__ void __launch_bounds__(WARPS * 32, 2)
 ln_modulate_fwd_lean(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, const bf16* __restrict__ scale,
                      const bf16* __restrict__ shift, int64_t mod_ld, int rows_per_mod, bf16* __restrict__ y, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int R, float eps, int rows_per_cta) {
@@ -115,12 +115,10 @@ ln_modulate_fwd_lean(const bf16* __restrict__ x, const float* __restrict__ w, co
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row0 = blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);  // row0 % 8 == 0, rows_per_mod % 8 == 0
   int cur_sample = -1;
-  // TWO rows in flight per warp beyond the one being processed: at 16-24 resident warps per SM one row each (2.3 KB) is ~40-55 KB
-  // in flight per SM, which by Little's law caps the kernel near 0.55 of the HBM peak (measured); two rows lift that bound
-  Row<U, UPL> cur, nxt, nx2;
-  if (row0 + warp < row1) cur.load(x + (int64_t)(row0 + warp) * d, lane);
-  if (row0 + warp + WARPS < row1) nxt.load(x + (int64_t)(row0 + warp + WARPS) * d, lane);
-  for (int base = row0; base < row1; base += WARPS) {
+  // Three row buffers per warp used in rotation (the loop is unrolled by three, so no buffer is ever COPIED: a register move of
+  // a row whose load is still in flight would stall on it and cancel the prefetch). The row being processed was requested two
+  // iterations ago; two further rows are in flight per warp.
+  auto step = [&](Row<U, UPL>& buf, int base) {
     const int sample = base / rows_per_mod;  // uniform over the CTA: all 8 rows of this step belong to one sample
     if (sample != cur_sample) {
       __syncthreads();
@@ -135,15 +133,15 @@ ln_modulate_fwd_lean(const bf16* __restrict__ x, const float* __restrict__ w, co
       cur_sample = sample;
     }
     const int r = base + warp;
-    if (r + 2 * WARPS < row1) nx2.load(x + (int64_t)(r + 2 * WARPS) * d, lane);
     if (r < row1) {
-      // packed fp32 pairs (FADD2 / FFMA2): one issue slot per two channels; two-pass statistics as before
+      // packed fp32 pairs (FADD2 / FFMA2): one issue slot per two channels; two-pass statistics
       f32x2 f[UPL][U / 2];
       f32x2 s2 = make_f32x2(0.f, 0.f);
 #pragma unroll
       for (int u = 0; u < UPL; ++u)
 #pragma unroll
-        for (int j = 0; j < U / 2; ++j) { f[u][j] = unpack2(cur.w[u][j]); s2 = add2(s2, f[u][j]); }
+        for (int j = 0; j < U / 2; ++j) { f[u][j] = unpack2(buf.w[u][j]); s2 = add2(s2, f[u][j]); }
+      if (r + 3 * WARPS < row1) buf.load(x + (int64_t)(r + 3 * WARPS) * d, lane);  // refill this buffer: consumed above
       float s_lo, s_hi;
       split_f32x2(s2, s_lo, s_hi);
       const float mean = warp_sum(s_lo + s_hi) * (1.f / d);
@@ -170,8 +168,15 @@ ln_modulate_fwd_lean(const bf16* __restrict__ x, const float* __restrict__ w, co
       }
       o.store(y + (int64_t)r * d, lane);
     }
-    cur = nxt;
-    nxt = nx2;
+  };
+  Row<U, UPL> b0, b1, b2;
+  if (row0 + warp < row1) b0.load(x + (int64_t)(row0 + warp) * d, lane);
+  if (row0 + warp + WARPS < row1) b1.load(x + (int64_t)(row0 + warp + WARPS) * d, lane);
+  if (row0 + warp + 2 * WARPS < row1) b2.load(x + (int64_t)(row0 + warp + 2 * WARPS) * d, lane);
+  for (int base = row0; base < row1; base += 3 * WARPS) {  // (all warps run every step: the sample switch holds CTA barriers)
+    step(b0, base);
+    if (base + WARPS < row1) step(b1, base + WARPS);
+    if (base + 2 * WARPS < row1) step(b2, base + 2 * WARPS);
   }
 }
 
@@ -182,6 +187,8 @@ ln_modulate_fwd_lean(const bf16* __restrict__ x, const float* __restrict__ w, co
 // invariants in registers; cos / sin arrive as ONE vector load per unit (pairs of a unit are adjacent in the table).
 // fp32 arithmetic with a single final rounding (the reference rounds to bf16 after the normalisation, after the scale and
 // inside the rotation; tests bound the difference against the fp32 restatement at 1e-2, this version is closer to it).
+// (A packed-fp32 / three-buffer variant like ln_modulate_fwd_lean measured 5 % SLOWER here, same box: the register pairs cost
+// this kernel its third resident CTA's worth of latency hiding; the scalar form stays.)
 // ---------------------------------------------------------------------------------------------------------
 constexpr int QK_WARPS = 4;  // 2 q-warps + 2 k-warps per CTA (the per-lane scale registers make this kernel register-heavy)
 template <int U, int UPL>
@@ -193,48 +200,36 @@ qknorm_rope_fwd_lean(const bf16* __restrict__ qkv, int64_t ld_in, const float* _
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int which = warp & 1;  // 0: q half-rows, 1: k half-rows
   const int row0 = blockIdx.x * rows_per_cta, row1 = min(R, row0 + rows_per_cta);
-  // loop invariants of this lane: learnable scales (even / odd channels of every rotary pair, as packed fp32 pairs over two
-  // adjacent pairs) and the rotary pair index of every unit (-1: the unit does not rotate)
-  f32x2 sce[UPL][U / 4], sco[UPL][U / 4];
+  // loop invariants of this lane: learnable scales and the rotary pair index of every unit (-1: the unit does not rotate)
+  float sc[UPL][U];
   int pj[UPL];
 #pragma unroll
   for (int u = 0; u < UPL; ++u) {
     const int c = (lane + 32 * u) * U;
-    float sc[U];
-    ldf<U>((which ? sk : sq) + c, sc);
-#pragma unroll
-    for (int j = 0; j < U / 4; ++j) { sce[u][j] = make_f32x2(sc[4 * j], sc[4 * j + 2]); sco[u][j] = make_f32x2(sc[4 * j + 1], sc[4 * j + 3]); }
+    ldf<U>((which ? sk : sq) + c, sc[u]);
     const int cl = c % hd;  // hd % 8 == 0 keeps a unit inside one head
     pj[u] = (cl >> 1) < rot_half ? (cl >> 1) : -1;
   }
   const int col0 = which * d;
   constexpr int STEP = QK_WARPS / 2;  // token rows advanced per iteration by the warps of each half
-  Row<U, UPL> cur, nxt, nx2;  // two half-rows in flight per warp beyond the current one (see ln_modulate_fwd_lean)
+  Row<U, UPL> cur, nxt;
   int r = row0 + (warp >> 1);
   if (r < row1) cur.load(qkv + (int64_t)r * ld_in + col0, lane);
-  if (r + STEP < row1) nxt.load(qkv + (int64_t)(r + STEP) * ld_in + col0, lane);
   for (; r < row1; r += STEP) {
-    if (r + 2 * STEP < row1) nx2.load(qkv + (int64_t)(r + 2 * STEP) * ld_in + col0, lane);
+    if (r + STEP < row1) nxt.load(qkv + (int64_t)(r + STEP) * ld_in + col0, lane);
     const uint32_t* csr = cs_t + (int64_t)(pos_idx ? pos_idx[r] : pos_offset + r % tokens_per_sample) * rot_half;
-    // word j of a unit = channels (2j, 2j+1) = one rotary pair (even, odd). Two adjacent words are processed together as packed
-    // fp32 pairs E = (even_j, even_j+1), O = (odd_j, odd_j+1): FMUL2 / FFMA2 do two pairs per issue slot.
-    f32x2 E[UPL][U / 4], O[UPL][U / 4];
-    f32x2 ss2 = make_f32x2(0.f, 0.f);
+    float f[UPL][U];
+    cur.unpack(f);
+    float ss = 0.f;
 #pragma unroll
-    for (int u = 0; u < UPL; ++u)
+    for (int u = 0; u < UPL; ++u) {
+      float t = 0.f;
 #pragma unroll
-      for (int j = 0; j < U / 4; ++j) {
-        const uint32_t w0 = cur.w[u][2 * j], w1 = cur.w[u][2 * j + 1];
-        E[u][j] = make_f32x2(blo(w0), blo(w1));
-        O[u][j] = make_f32x2(bhi(w0), bhi(w1));
-        ss2 = fma2(E[u][j], E[u][j], ss2);
-        ss2 = fma2(O[u][j], O[u][j], ss2);
-      }
-    float ss_lo, ss_hi;
-    split_f32x2(ss2, ss_lo, ss_hi);
-    const float rrms = rsqrtf(warp_sum(ss_lo + ss_hi) * (1.f / d) + eps);
+      for (int j = 0; j < U; ++j) t = fmaf(f[u][j], f[u][j], t);
+      ss += t;
+    }
+    const float rrms = rsqrtf(warp_sum(ss) * (1.f / d) + eps);
     if (lane == 0 && rrms_out) rrms_out[(int64_t)r * 2 + which] = rrms;
-    const f32x2 rr2 = make_f32x2(rrms, rrms);
     Row<U, UPL> o;
 #pragma unroll
     for (int u = 0; u < UPL; ++u) {
@@ -244,26 +239,19 @@ qknorm_rope_fwd_lean(const bf16* __restrict__ qkv, int64_t ld_in, const float* _
         else { const uint2 v = __ldg(reinterpret_cast<const uint2*>(csr + pj[u])); cs[0] = v.x; cs[1] = v.y; }
       }
 #pragma unroll
-      for (int j = 0; j < U / 4; ++j) {
-        f32x2 e2 = mul2(mul2(E[u][j], rr2), sce[u][j]), o2 = mul2(mul2(O[u][j], rr2), sco[u][j]);
+      for (int j = 0; j < U / 2; ++j) {
+        float e = f[u][2 * j] * rrms * sc[u][2 * j], od = f[u][2 * j + 1] * rrms * sc[u][2 * j + 1];
         if (pj[u] >= 0) {  // (cos, sin) packed as bf16x2: the reference casts the tables to the activation dtype
-          const uint32_t c0 = cs[2 * j], c1 = cs[2 * j + 1];
-          const f32x2 C = make_f32x2(blo(c0), blo(c1)), S = make_f32x2(bhi(c0), bhi(c1));
-          const f32x2 nS = make_f32x2(__uint_as_float((c0 & 0xffff0000u) ^ 0x80000000u), __uint_as_float((c1 & 0xffff0000u) ^ 0x80000000u));
-          const f32x2 re = fma2(o2, nS, mul2(e2, C)), ro = fma2(e2, S, mul2(o2, C));  // e c - o s,  e s + o c
-          e2 = re;
-          o2 = ro;
+          const float c = blo(cs[j]), s = bhi(cs[j]);
+          const float re = e * c - od * s, ro = fmaf(e, s, od * c);
+          e = re;
+          od = ro;
         }
-        float e_a, e_b, o_a, o_b;
-        split_f32x2(e2, e_a, e_b);
-        split_f32x2(o2, o_a, o_b);
-        o.w[u][2 * j] = pack_bf16x2(e_a, o_a);
-        o.w[u][2 * j + 1] = pack_bf16x2(e_b, o_b);
+        o.w[u][j] = pack_bf16x2(e, od);
       }
     }
     o.store(out + (int64_t)r * ld_out + col0, lane);
     cur = nxt;
-    nxt = nx2;
   }
 }
 

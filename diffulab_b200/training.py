@@ -523,11 +523,16 @@ class DevicePrefetcher:
     dicts of tensors are moved, everything else passes through). The compute stream waits for the copy's event, so a batch is
     never read before it has landed; the caching allocator is told about the cross-stream use (record_stream)."""
 
+    _streams: dict = {}
+
     def __init__(self, batches: Iterable[Any], device: torch.device, move: Any = None):
         self.it = iter(batches)
         self.device = torch.device(device)
         self.move = move or self._move
-        self.stream = torch.cuda.Stream(device=self.device)
+        key = (self.device.type, self.device.index if self.device.index is not None else torch.cuda.current_device())
+        if key not in DevicePrefetcher._streams:  # ONE copy stream per device for the life of the process: its allocator pool stays warm
+            DevicePrefetcher._streams[key] = torch.cuda.Stream(device=self.device)
+        self.stream = DevicePrefetcher._streams[key]
         self._next: tuple[Any, torch.cuda.Event] | None = None
         self._fill()
 
