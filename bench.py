@@ -330,7 +330,7 @@ def run_gpu_arm(args) -> None:
         def make_reducer(mode: str):
             return GradReducer(stores=opt.stores, bucket_mb=args.bucket_mb or GradReducer.DEFAULT_BUCKET_MB, tail_bucket_mb=args.tail_bucket_mb or None,
                                process_group=make_reduce_group(args.comm_ctas) if mode == "nccl" and args.comm_ctas > 0 else None,
-                               reserve_sms=args.reserve_sms, mode=mode, comm_ctas=max(1, args.comm_ctas))
+                               reserve_sms=args.reserve_sms, mode=mode, comm_ctas=max(1, args.comm_ctas), use_graphs=not args.no_dp_graphs)
 
         mode, why = args.dp_mode, None
         if mode != "nccl":  # symmetric (peer-mapped) memory must come up on EVERY rank, else all ranks use NCCL
@@ -429,7 +429,7 @@ def run_gpu_arm(args) -> None:
         tl = reducer.read_timeline()
         reducer.timeline = None
         dp = {"mode": reducer.mode, "replicas_identical_after_steps": identical, "buckets": len(reducer.buckets), "bucket_mb": args.bucket_mb or GradReducer.DEFAULT_BUCKET_MB,
-              "tail_bucket_mb": args.tail_bucket_mb or None, "comm_ctas": args.comm_ctas, "reserve_sms": args.reserve_sms,
+              "tail_bucket_mb": args.tail_bucket_mb or None, "comm_ctas": args.comm_ctas, "reserve_sms": args.reserve_sms, "bucket_graphs": len(getattr(reducer, "_graphs", {})),
               "grad_bytes_per_step": int(sum(b.numel() for b in reducer.buckets) * 4), "backward_after_first_bucket_ms": tl["end_backward_ms"],
               "exposed_tail_ms": tl["exposed_tail_ms"]}
         if rank == 0:
@@ -606,6 +606,7 @@ def main() -> None:
     ap.add_argument("--tail-bucket-mb", type=float, default=32.0, help="size cap of the buckets backward produces last (0 = same as --bucket-mb)")
     ap.add_argument("--dp-mode", default="ce", choices=["nccl", "ce", "nvls"], help="gradient reduction: NCCL all-reduce | copy-engine pulls over peer "
                     "memory + reduce kernel | in-switch multimem reduction kernel")
+    ap.add_argument("--no-dp-graphs", action="store_true", help="launch the per-bucket peer-memory reduction eagerly instead of replaying one CUDA graph per bucket")
     ap.add_argument("--comm-ctas", type=int, default=0, help="CTAs per gradient reduction (nccl: dedicated communicator, 0 = NCCL's default; nvls: kernel grid)")
     ap.add_argument("--reserve-sms", type=int, default=0, help="SMs the persistent kernels leave to the collective while buckets are in flight")
     ap.add_argument("--sample-batch", type=int, default=64)

@@ -24,8 +24,8 @@ reduce_pieces_kernel(float* __restrict__ own, const float* __restrict__ staged, 
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int q = 0; q < world; ++q) {
-      const float4* src = q == rank ? reinterpret_cast<const float4*>(own)
-                                    : reinterpret_cast<const float4*>(staged + (int64_t)((q - rank - 1 + world) % world) * stage_stride);
+      const int slot = q > rank ? q - rank - 1 : q - rank - 1 + world;  // (q - rank - 1) mod world
+      const float4* src = q == rank ? reinterpret_cast<const float4*>(own) : reinterpret_cast<const float4*>(staged + (int64_t)slot * stage_stride);
       const float4 v = src[i];
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }

@@ -306,7 +306,7 @@ class GradReducer:
 
     def __init__(self, stores: list[FlatParams] | None = None, params: list[nn.Parameter] | None = None,
                  bucket_mb: float = DEFAULT_BUCKET_MB, process_group: Any = None, tail_bucket_mb: float | None = None,
-                 reserve_sms: int = 0, mode: str = "nccl", comm_ctas: int = 4):
+                 reserve_sms: int = 0, mode: str = "nccl", comm_ctas: int = 4, use_graphs: bool = True):
         assert mode in ("nccl", "ce", "nvls"), mode
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -329,6 +329,10 @@ class GradReducer:
                 assert all(int(h.multicast_ptr) != 0 for h in self._sym), "no NVLink multicast (NVLS) mapping on this system: use mode='ce'"
             self.comm = torch.cuda.Stream(priority=-1)
             self._stage: Tensor | None = None
+            self._plans: dict[int, dict[str, Any]] = {}
+            self._graphs: dict[int, Any] = {}
+            self._uses: dict[int, int] = {}
+            self.use_graphs = use_graphs
         self.buckets: list[Tensor] = []
         self.bucket_of: dict[int, int] = {}
         self.pending_init: list[int] = []
@@ -363,6 +367,9 @@ class GradReducer:
         self.launched = [False] * len(self.buckets)
         self.works: list[Any] = []
         self.active = False
+        if self.mode == "ce":  # staging for the world - 1 peer copies of the largest piece (shared by all buckets: one stream)
+            piece_max = max(self._pieces(e - s_)[0] for _, s_, e in self.bucket_span)
+            self._stage = torch.empty((self.world - 1) * piece_max, device=self.buckets[0].device, dtype=torch.float32)
 
     def _add_bucket(self, tensor: Tensor, members: list[nn.Parameter]) -> None:
         bi = len(self.buckets)
@@ -409,35 +416,71 @@ class GradReducer:
         piece = ((n + self.world - 1) // self.world + _ALIGN - 1) // _ALIGN * _ALIGN
         return piece, [max(0, min(piece, n - q * piece)) for q in range(self.world)]
 
-    def _peer_reduce(self, bi: int) -> Any:
-        """Reduce bucket bi over NVLink peer memory on the communication stream; returns an event the compute stream waits for."""
+    def _plan(self, bi: int) -> dict[str, Any]:
+        """Views for bucket bi, built once: my piece, (staging slot <- peer's copy of my piece) pulls, (my copy of a peer's piece <-
+        the peer's reduced piece) pulls. Peer views come from the symmetric-memory handle and never change."""
+        if bi in self._plans:
+            return self._plans[bi]
         si, start, end = self.bucket_span[bi]
         hdl, t = self._sym[si], self.buckets[bi]
         W, r = self.world, self.rank
         piece, lens = self._pieces(end - start)
+        plan: dict[str, Any] = {"hdl": hdl, "piece": piece, "len": lens[r], "own": t[r * piece : r * piece + lens[r]], "pull": [], "gather": [],
+                                "mc": (int(hdl.multicast_ptr) + 4 * (start + r * piece)) if self.mode == "nvls" else 0}
+        for s_ in range(W - 1):
+            peer = (r + 1 + s_) % W
+            if lens[r] > 0 and self.mode == "ce":
+                plan["pull"].append((self._stage[s_ * piece : s_ * piece + lens[r]], hdl.get_buffer(peer, (lens[r],), torch.float32, start + r * piece)))
+            if lens[peer] > 0 and self.mode == "ce":
+                plan["gather"].append((t[peer * piece : peer * piece + lens[peer]], hdl.get_buffer(peer, (lens[peer],), torch.float32, start + peer * piece)))
+        self._plans[bi] = plan
+        return plan
+
+    def _enqueue(self, bi: int) -> None:
+        """The reduction of bucket bi on the CURRENT stream (the communication stream, possibly under graph capture)."""
+        pl = self._plan(bi)
+        hdl, W = pl["hdl"], self.world
+        hdl.barrier(channel=0, timeout_ms=self._BARRIER_TIMEOUT_MS)  # every rank's gradients of this bucket are complete
+        if self.mode == "nvls":
+            if pl["len"] > 0:
+                ops.multimem_allreduce_(pl["mc"], pl["len"], 1.0 / W, self.comm_ctas)
+            return
+        for dst, src in pl["pull"]:  # my piece of every peer's bucket (copy engines over NVLink)
+            dst.copy_(src, non_blocking=True)
+        if pl["len"] > 0:
+            ops.reduce_pieces_(pl["own"], self._stage, pl["piece"], W, self.rank, 1.0 / W)
+        hdl.barrier(channel=0, timeout_ms=self._BARRIER_TIMEOUT_MS)  # every rank's piece is reduced
+        for dst, src in pl["gather"]:  # the reduced pieces of the peers (copy engines again)
+            dst.copy_(src, non_blocking=True)
+
+    def _peer_reduce(self, bi: int) -> Any:
+        """Reduce bucket bi over NVLink peer memory on the communication stream; returns an event the compute stream waits for.
+        The per-bucket sequence (2 barriers, 2 (W - 1) copies, 1 kernel: 17 launches at W = 8) is recorded ONCE as a CUDA graph
+        (second use; the first runs eagerly) and replayed with one launch afterwards — at W = 8 the eager launches cost the
+        backward thread ~5 ms per step, which starved the compute stream."""
         ready = torch.cuda.Event()
         ready.record()
         with torch.cuda.stream(self.comm):
             self.comm.wait_event(ready)
-            hdl.barrier(channel=0, timeout_ms=self._BARRIER_TIMEOUT_MS)  # every rank's gradients of this bucket are complete
-            if self.mode == "nvls":
-                if lens[r] > 0:
-                    ops.multimem_allreduce_(int(hdl.multicast_ptr) + 4 * (start + r * piece), lens[r], 1.0 / W, self.comm_ctas)
+            graph = self._graphs.get(bi)
+            if graph is not None:
+                graph.replay()
+            elif self.use_graphs and self._uses.get(bi, 0) >= 1:
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self.comm, capture_error_mode="thread_local"):
+                        self._enqueue(bi)
+                    self._graphs[bi] = g
+                    g.replay()
+                except Exception as e:  # noqa: BLE001 - capture is an optimisation: fall back to eager launches, loudly
+                    import warnings
+
+                    warnings.warn(f"GradReducer: CUDA-graph capture of the bucket reduction failed ({e!r}); launching eagerly", stacklevel=2)
+                    self.use_graphs = False
+                    self._enqueue(bi)
             else:
-                if lens[r] > 0:
-                    if self._stage is None or self._stage.numel() < (W - 1) * piece:
-                        self._stage = torch.empty((W - 1) * piece, device=t.device, dtype=torch.float32)
-                    for s_ in range(W - 1):  # pull my piece of every peer's bucket (copy engines)
-                        peer = (r + 1 + s_) % W
-                        src = hdl.get_buffer(peer, (lens[r],), torch.float32, start + r * piece)
-                        self._stage[s_ * piece : s_ * piece + lens[r]].copy_(src, non_blocking=True)
-                    ops.reduce_pieces_(t[r * piece : r * piece + lens[r]], self._stage, piece, W, r, 1.0 / W)
-                hdl.barrier(channel=0, timeout_ms=self._BARRIER_TIMEOUT_MS)  # every rank's piece is reduced
-                for s_ in range(W - 1):  # pull the reduced pieces of the peers (copy engines)
-                    peer = (r + 1 + s_) % W
-                    if lens[peer] > 0:
-                        src = hdl.get_buffer(peer, (lens[peer],), torch.float32, start + peer * piece)
-                        t[peer * piece : peer * piece + lens[peer]].copy_(src, non_blocking=True)
+                self._enqueue(bi)
+            self._uses[bi] = self._uses.get(bi, 0) + 1
             done = torch.cuda.Event()
             done.record()
         return done
