@@ -35,6 +35,7 @@ for l in open('gpurun_out/elementwise_microbench_r2.jsonl'):
 import json
 for l in open('gpurun_out/elementwise_microbench_r2_general_kernels.jsonl'):
     d=json.loads(l); print('| general:', d['ms'], d['frac_of_measured_hbm_peak'])")
+timeout 300 python scripts/bench_gemm_pair.py > gpurun_out/gemm_pair_microbench_r2.jsonl 2>/dev/null; cut -c1-600 gpurun_out/gemm_pair_microbench_r2.jsonl
 timeout 300 python scripts/bench_attn.py > gpurun_out/attn_microbench_r2.jsonl 2>/dev/null; cut -c1-400 gpurun_out/attn_microbench_r2.jsonl | head -5
 echo "== ncu launch list, one full-depth step"
 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/ncu_launches_r2.csv \
@@ -66,4 +67,16 @@ echo "rc=$? $(ls -la gpurun_out/ncu_hot_r2.ncu-rep 2>/dev/null)"
 python scripts/ncu_summary.py gpurun_out/ncu_hot_r2.ncu-rep > gpurun_out/ncu_hot_kernels_r2.txt 2>/dev/null
 python scripts/ncu_sass_stalls.py gpurun_out/ncu_hot_r2.ncu-rep attn_fwd_ws > gpurun_out/ncu_attention_stalls_r2.txt 2>/dev/null
 rm -f gpurun_out/ncu_hot_r2.ncu-rep
+du -sh gpurun_out
+echo "== reference-GPU arm with torch.compile (oracle port under bf16 autocast, compiled blocks)"
+timeout 1200 python bench.py --steps 4 --warmup 3 --no-sample --ref-gpu compile > gpurun_out/bench_r2_refgpu_compile.json 2> gpurun_out/bench_r2_refgpu_compile.err
+echo "rc=$?"; tail -n 2 gpurun_out/bench_r2_refgpu_compile.err
+python - <<'PY'
+import json
+try:
+    d=json.loads(open('gpurun_out/bench_r2_refgpu_compile.json').read().strip().splitlines()[-1])
+    print({k:v for k,v in d['cpu_baseline'].items() if k.startswith('ref_gpu') and k!='ref_gpu_what'})
+except Exception as e:
+    print('compile arm failed', e)
+PY
 du -sh gpurun_out
