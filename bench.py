@@ -364,8 +364,8 @@ def run_gpu_arm(args) -> None:
         batch i + 1 runs on a side stream while step i computes) and every step's losses are read back to the host (asynchronously:
         the value of step i is collected while step i + 1 runs, the last one after the loop)."""
         reader, total = LossReader(), 0.0
-        move = lambda b, dev_, non_blocking=True: Workload.to_step(b, dev_, non_blocking=non_blocking)  # noqa: E731
-        for batch in DevicePrefetcher((host[i % pool] for i in range(n)), device, move=move):
+        restructure = lambda b: Workload.to_step(b, "cpu")  # noqa: E731  (dict reshuffle only: the tensors are already on the host)
+        for batch in DevicePrefetcher((host[i % pool] for i in range(n)), device, restructure=restructure):
             got = reader.push(training_step(diffuser, opt, batch, wl.p_cfg, reducer, ema=ema))
             total += sum(got.values()) if got else 0.0
         total += sum(reader.flush().values())

@@ -562,47 +562,56 @@ class GradReducer:
 class DevicePrefetcher:
     """Iterates host batches (pinned memory) as device batches, copying batch i + 1 on a side stream while step i computes —
     the place of `accelerator.prepare(train_dataloader)` in the reference's loop (base_trainer.py:277-307: the prepared DataLoader
-    moves every batch to the device). `move(batch, device, non_blocking=True)` builds the device batch (default: tensors / nested
-    dicts of tensors are moved, everything else passes through). The compute stream waits for the copy's event, so a batch is
-    never read before it has landed; the caching allocator is told about the cross-stream use (record_stream)."""
+    moves every batch to the device). `restructure(host_batch)` (optional) reshapes the host batch into the structure the step
+    takes WITHOUT copying (nested dicts of tensors; anything else passes through). The leaves are copied into TWO persistent sets
+    of device buffers used alternately (no allocation in the loop: freeing cross-stream blocks every step makes the caching
+    allocator fall back to cudaMalloc, which serialises host and device). Ordering: the compute stream waits for the copy's event;
+    the copy into a buffer set waits until the step that last used it has been fully enqueued and executed. A batch must not be
+    used after the NEXT batch has been requested twice (it is overwritten)."""
 
     _streams: dict = {}
+    N_BUF = 2
 
-    def __init__(self, batches: Iterable[Any], device: torch.device, move: Any = None):
+    def __init__(self, batches: Iterable[Any], device: torch.device, restructure: Any = None):
         self.it = iter(batches)
         self.device = torch.device(device)
-        self.move = move or self._move
+        self.restructure = restructure or (lambda b: b)
         key = (self.device.type, self.device.index if self.device.index is not None else torch.cuda.current_device())
-        if key not in DevicePrefetcher._streams:  # ONE copy stream per device for the life of the process: its allocator pool stays warm
+        if key not in DevicePrefetcher._streams:
             DevicePrefetcher._streams[key] = torch.cuda.Stream(device=self.device)
         self.stream = DevicePrefetcher._streams[key]
+        self._bufs: list[Any] = [None] * self.N_BUF        # persistent device leaves, same nesting as the host batch
+        self._reusable: list[Any] = [None] * self.N_BUF    # compute-stream event after which the set may be overwritten
+        self._n = 0                                        # batches issued so far
         self._next: tuple[Any, torch.cuda.Event] | None = None
         self._fill()
 
-    @staticmethod
-    def _move(b: Any, device: torch.device, non_blocking: bool = True) -> Any:
-        if isinstance(b, Tensor):
-            return b.to(device, non_blocking=non_blocking)
-        if isinstance(b, dict):
-            return {k: DevicePrefetcher._move(v, device, non_blocking) for k, v in b.items()}
-        return b
-
-    @staticmethod
-    def _tensors(b: Any):
-        if isinstance(b, Tensor):
-            yield b
-        elif isinstance(b, dict):
-            for v in b.values():
-                yield from DevicePrefetcher._tensors(v)
+    def _copy(self, dst: Any, src: Any) -> tuple[Any, Any]:
+        """-> (persistent structure, view handed to the consumer); tensors are copied on the current (side) stream"""
+        if isinstance(src, Tensor):
+            if not isinstance(dst, Tensor) or dst.shape != src.shape or dst.dtype != src.dtype:
+                dst = torch.empty(src.shape, dtype=src.dtype, device=self.device)
+            dst.copy_(src, non_blocking=True)
+            return dst, dst
+        if isinstance(src, dict):
+            keep, out = {}, {}
+            for k, v in src.items():
+                keep[k], out[k] = self._copy(dst.get(k) if isinstance(dst, dict) else None, v)
+            return keep, out
+        return src, src
 
     def _fill(self) -> None:
         try:
-            host = next(self.it)
+            host = self.restructure(next(self.it))
         except StopIteration:
             self._next = None
             return
+        k = self._n % self.N_BUF
+        self._n += 1
         with torch.cuda.stream(self.stream):
-            dev = self.move(host, self.device, non_blocking=True)
+            if self._reusable[k] is not None:
+                self.stream.wait_event(self._reusable[k])
+            self._bufs[k], dev = self._copy(self._bufs[k], host)
             ev = torch.cuda.Event()
             ev.record()
         self._next = (dev, ev)
@@ -615,9 +624,13 @@ class DevicePrefetcher:
             raise StopIteration
         dev, ev = self._next
         cur = torch.cuda.current_stream(self.device)
+        # everything enqueued so far belongs to steps that used EARLIER batches: the set holding the previous batch may be refilled
+        # once the compute stream has passed this point
+        if self._n >= 2:
+            done = torch.cuda.Event()
+            done.record(cur)
+            self._reusable[(self._n - 2) % self.N_BUF] = done
         cur.wait_event(ev)
-        for t in self._tensors(dev):
-            t.record_stream(cur)
         self._fill()  # the next batch's copy overlaps the step the caller is about to run
         return dev
 
