@@ -19,6 +19,7 @@ from torch import Tensor, nn
 from . import blocks as K
 from . import ops
 
+_SYNC_ZERO = bool(__import__("os").environ.get("DLB_SYNC_ZERO"))  # A/B switch: gradient memset on the compute stream
 _ALIGN = 64  # elements; keeps every parameter slice 256-byte (fp32) / 128-byte (bf16) aligned for TMA
 
 
@@ -100,6 +101,8 @@ class FusedAdamW(torch.optim.Optimizer):
         self._mask_key: list[frozenset | None] = []
         self._mask: list[Tensor | None] = []
         self.ema: "EMA | None" = None
+        self._zero_stream: Any = None
+        self._zero_done: Any = None
         for group in self.param_groups:
             st = FlatParams(group["params"])
             self.stores.append(st)
@@ -140,9 +143,32 @@ class FusedAdamW(torch.optim.Optimizer):
         self._point_state()
 
     def zero_grad(self, set_to_none: bool = True) -> None:  # noqa: ARG002 - gradients live in the flat buffer
+        self.wait_zero()
         for st in self.stores:
             st.zero_grad()
         K.clear_touched()
+
+    def zero_grad_async(self) -> None:
+        """zero_grad() on a side stream: the 3.3 GB memset of the flat gradient buffer (0.5 ms of HBM time for DiT-XL/2) overlaps
+        the forward pass, which never touches gradients. The caller must call `wait_zero()` before the first gradient is written
+        (`training_step` does, right before `backward()`)."""
+        cur = torch.cuda.current_stream()
+        if self._zero_stream is None:
+            self._zero_stream = torch.cuda.Stream()
+        start = torch.cuda.Event()
+        start.record(cur)  # everything that read the gradients (optimizer step, peers' pulls) is ordered before this point
+        with torch.cuda.stream(self._zero_stream):
+            self._zero_stream.wait_event(start)
+            for st in self.stores:
+                st.zero_grad()
+            self._zero_done = torch.cuda.Event()
+            self._zero_done.record()
+        K.clear_touched()
+
+    def wait_zero(self) -> None:
+        if self._zero_done is not None:
+            torch.cuda.current_stream().wait_event(self._zero_done)
+            self._zero_done = None
 
     def _active_mask(self, gi: int) -> Tensor | None:
         """uint8 per 64-element chunk: 0 for parameters that received no gradient this step (torch: .grad is None).
@@ -172,6 +198,7 @@ class FusedAdamW(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        self.wait_zero()
         ema_plan = self.ema.plan() if self.ema is not None else None  # ("skip" | "copy" | "lerp", decay)
         for gi, (group, st) in enumerate(zip(self.param_groups, self.stores)):
             st.check_versions()
@@ -679,13 +706,18 @@ def training_step(diffuser, optimizer: torch.optim.Optimizer, batch: dict[str, A
     EMA update. An `EMA` attached to a `FusedAdamW` is advanced inside `optimizer.step()` (same kernel pass); any other
     combination calls `ema.update()` here. Returns the loss dict as DEVICE tensors: the reference's per-step
     `loss.item()` host sync is left to the caller."""
-    optimizer.zero_grad()
+    if hasattr(optimizer, "zero_grad_async") and not _SYNC_ZERO:
+        optimizer.zero_grad_async()  # the gradient memset runs beside the forward pass
+    else:
+        optimizer.zero_grad()
     model_inputs = batch["model_inputs"]
     device = next(diffuser.denoiser.parameters()).device
     timesteps = diffuser.draw_timesteps(model_inputs["x"].shape[0]).to(device)
     model_inputs.update({"p": p_classifier_free_guidance})
     losses = diffuser.compute_loss(model_inputs=model_inputs, timesteps=timesteps, extra_args=batch.get("extra", {}))
     loss = sum(losses.values())
+    if hasattr(optimizer, "wait_zero"):
+        optimizer.wait_zero()
     if reducer is not None:
         reducer.begin()
     loss.backward()
