@@ -322,11 +322,12 @@ class GradReducer:
 
     `mode`:
       "nccl"  ncclAllReduce(AVG) per bucket on the communicator's stream (16-32 CTAs that time-slice with the persistent GEMMs:
-              measured +5 ms of kernel time per 143 ms step at N = 2, profiles/dp_overlap_r2.md).
+              measured +5 ms of kernel time per 143 ms step at N = 2, profiles/dp_r2/README.md).
       "ce"    the flat gradient buffer lives in symmetric (peer-mapped) memory; per bucket, rank p pulls piece p of every peer with
               device-to-device copies (copy engines over NVLink, no SMs), averages them (dlb_reduce_pieces), and all ranks pull
               the reduced pieces back. Stream-ordered symmetric-memory barriers order the phases across ranks.
-      "nvls"  one dlb_multimem_allreduce kernel per bucket (sum inside the NVSwitch, `comm_ctas` CTAs) between two barriers.
+      "nvls"  one dlb_multimem_allreduce kernel per bucket (sum inside the NVSwitch, `comm_ctas` CTAs) after a barrier; the closing
+              barrier of `finish()` orders the peers' multicast stores before this rank reads its buffer.
     Modes "ce" / "nvls" need a FlatParams store and an NCCL (CUDA) job; the mean is exact in fp32 as with NCCL."""
 
     DEFAULT_BUCKET_MB = 128.0
