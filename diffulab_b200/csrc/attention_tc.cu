@@ -608,6 +608,329 @@ __global__ void __launch_bounds__(NT, 1) attn_fwd_ws_tc_kernel(const Params p, c
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// forward, whole-row version for sequences of at most 256 keys (DiT-XL/2: N = 256; cifar DiT: 64; head dims <= 80).
+// The per-tile online softmax of the kernel above pays its fixed latencies (TMEM round trips, pair barrier, fences, mbarrier
+// hand-offs: ~2000 cycles for ~160 cycles of tensor work and a 512-cycle MUFU floor) once per 64 keys. Here the WHOLE score row
+// S = Q K^T (up to 256 fp32 columns of TMEM) is computed before the softmax starts, the softmax is a plain two-pass one over the
+// thread's 128 scores held in registers (row maximum; exponentials, row sum, P -> shared memory), and O = P V is ONE accumulating
+// MMA chain into TMEM — no rescaling, no per-tile register accumulation. O is double-buffered in TMEM and the epilogue of item k
+// runs after the softmax of item k + 1, so the compute warps never wait for the P V products. K and V tiles travel
+// through separate 4-stage rings so that the K tiles of item i+1 load during the softmax of item i (they are released as soon as
+// S(i) is computed) and its V tiles during the epilogue of item i. Hand-offs per item: bar_s, ps_full, bar_o.
+// TMEM: S at columns [0, 256), O buffers at [256, 256 + 2 HDP). Same warp roles, layouts and tensor maps as the kernels around it.
+// ---------------------------------------------------------------------------------------------------------
+template <int HDP, bool TMA, int FLAGS>
+__global__ void __launch_bounds__(NT, 1) attn_fwd_row_tc_kernel(const Params p, const __grid_constant__ BwdMaps maps) {
+  constexpr int TQ = 128 * HDP * 2, TK = KT * HDP * 2, NS = 4, PT = 128 * KT * 2;
+  constexpr int HH = HDP / 2;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sQ = smem;                                       // 2 x Q tile, layout L1(128)
+  uint8_t* sK = sQ + 2 * TQ;                                // NS K tiles, layout L1(64)
+  uint8_t* sV = sK + NS * TK;                               // NS V tiles
+  uint8_t* sP = sV + NS * TK;                               // 4 x [128 q][64 keys] bf16, layout L1(128)
+  bf16* sStage = reinterpret_cast<bf16*>(sP + 4 * PT);      // [128][HDP] output staging
+  float* sX = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sStage) + TQ);  // [2][2][128] pair exchange (max, sum)
+  __shared__ uint64_t fullK[NS], emptyK[NS], fullV[NS], emptyV[NS], bar_s, ps_full, bar_o[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const int T = (p.S + KT - 1) / KT, nxq = (p.S + 127) / 128;  // T <= 4, nxq <= 2
+  // FLAGS (compile time): 1 = the query tiles of a head share one copy of K / V, 2 = deferred epilogue, 4 = TMA store of the output
+  // tile, 8 = two-pass softmax that re-reads the scores from TMEM (fewer registers) instead of keeping 128 scores per thread
+  constexpr bool share = (FLAGS & 1) != 0, defer = (FLAGS & 2) != 0, tma_out = TMA && (FLAGS & 4) != 0, reread = (FLAGS & 8) != 0;
+  const int nx = share ? nxq : 1;  // query tiles per work unit
+  // work unit = one (sample, head): its nx query tiles are processed back to back against ONE copy of its K / V tiles in shared
+  // memory (the head-slice gather, ~14 B/clk/SM with 16-byte boxes, is what bounds this kernel otherwise: 92 KB per query tile)
+  const int nunits = p.H * p.B * (share ? 1 : nxq);
+  const int n_my = (nunits - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int NI = n_my * nx;  // items (query tiles) of this CTA: item i = (unit i / nx, tile i % nx)
+  auto item_of = [&](int i) {
+    const int w = (int)blockIdx.x + (i / nx) * (int)gridDim.x;
+    if (!share) return decode_item(p, w, nxq);
+    return Item{i % nx, w % p.H, w / p.H};
+  };
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) {
+      ptx::mbar_init(&fullK[i], TMA ? 1 : NPW * 32); ptx::mbar_init(&emptyK[i], 1);
+      ptx::mbar_init(&fullV[i], TMA ? 1 : NPW * 32); ptx::mbar_init(&emptyV[i], 1);
+    }
+    ptx::mbar_init(&bar_s, 1); ptx::mbar_init(&ps_full, NC); ptx::mbar_init(&bar_o[0], 1); ptx::mbar_init(&bar_o[1], 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp_u == 8) ptx::tmem_alloc<512>(&tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  constexpr uint32_t idesc_s = ptx::make_idesc_bf16(128, KT, false, false);
+  constexpr uint32_t idesc_o = ptx::make_idesc_bf16(128, HDP, false, true);
+
+#define ROW_TRACE_C(i, slot) do { if (p.trace != nullptr && tid == 0 && blockIdx.x == gridDim.x / 2 && ((i) == 2 || (i) == 3)) p.trace[((i) - 2) * 10 + (slot)] = clock64(); } while (0)
+#define ROW_TRACE_M(i, slot) do { if (p.trace != nullptr && lane == 0 && blockIdx.x == gridDim.x / 2 && ((i) == 2 || (i) == 3)) p.trace[32 + ((i) - 2) * 10 + (slot)] = clock64(); } while (0)
+  if (warp_u > 8) {
+    // ---------------- producer warps: per item Q + K tiles, then V tiles ----------------
+    const int pw = warp_u - 9;
+    for (int k = 0; k < n_my; ++k) {
+      const Item it = item_of(k * nx);
+      for (int j = 0; j < T; ++j) {
+        const int u = k * T + j;
+        if (u >= NS) ptx::mbar_wait(&emptyK[u % NS], ((u / NS) - 1) & 1);
+        uint8_t* st = sK + (u % NS) * TK;
+        // the unit's query tiles travel with its LAST key tile: that stage is only released once every score product of the
+        // previous unit (which read the query buffers) has completed
+        const bool with_q = j == T - 1;
+        if constexpr (TMA) {
+          if (pw == 0 && ptx::elect_one()) {
+            uint64_t* bar = &fullK[u % NS];
+            ptx::mbar_expect_tx(bar, TK + (with_q ? nx * TQ : 0));
+            if (with_q)
+              for (int x = 0; x < nx; ++x) tma_tile(sQ + ((share ? x : k) & 1) * TQ, maps, M_Q128, p, it.b, it.h, (share ? x : it.x) * 128, bar);
+            tma_tile(st, maps, M_K64, p, it.b, it.h, j * KT, bar);
+          }
+          __syncwarp();
+        } else {
+          if (with_q)
+            for (int x = 0; x < nx; ++x) load_tile<HDP, T_Q, 128, NPW>(sQ + ((share ? x : k) & 1) * TQ, p, it.b, it.h, (share ? x : it.x) * 128, pw, lane);
+          load_tile<HDP, T_K, KT, NPW>(st, p, it.b, it.h, j * KT, pw, lane);
+          cp_async_arrive_noinc(&fullK[u % NS]);
+        }
+      }
+      for (int j = 0; j < T; ++j) {
+        const int u = k * T + j;
+        if (u >= NS) ptx::mbar_wait(&emptyV[u % NS], ((u / NS) - 1) & 1);
+        uint8_t* st = sV + (u % NS) * TK;
+        if constexpr (TMA) {
+          if (pw == 0 && ptx::elect_one()) {
+            uint64_t* bar = &fullV[u % NS];
+            ptx::mbar_expect_tx(bar, TK);
+            tma_tile(st, maps, M_V64, p, it.b, it.h, j * KT, bar);
+          }
+          __syncwarp();
+        } else {
+          load_tile<HDP, T_V, KT, NPW>(st, p, it.b, it.h, j * KT, pw, lane);
+          cp_async_arrive_noinc(&fullV[u % NS]);
+        }
+      }
+    }
+    if constexpr (!TMA) cp_async_wait<0>();
+  } else if (warp_u == 8) {
+    // ---------------- MMA-issue warp: S(0); then per item: P V (after the softmax), S(next) ----------------
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot, 0);
+    const uint32_t qa = ptx::smem_u32(sQ), ka = ptx::smem_u32(sK), va = ptx::smem_u32(sV), pa = ptx::smem_u32(sP);
+    auto issue_s = [&](int i) {  // S(i) = Q(i) K^T into TMEM columns [0, T * 64)
+      const int k = i / nx, x = i % nx;
+      const uint64_t dq0 = desc_k128(qa + ((share ? x : k) & 1) * TQ);
+      if (x == 0) {  // the unit's query tiles arrive with its last key tile
+        const int ul = k * T + T - 1;
+        ptx::mbar_wait(&fullK[ul % NS], (ul / NS) & 1);
+      }
+      for (int j = 0; j < T; ++j) {
+        const int u = k * T + j;
+        if (x == 0) ptx::mbar_wait(&fullK[u % NS], (u / NS) & 1);
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_after();
+        const uint64_t dk = desc_k64(ka + (u % NS) * TK);
+#pragma unroll
+        for (int ks = 0; ks < HDP / 16; ++ks) ptx::umma_bf16_elect(tmem + j * KT, dq0 + ks * KSTEP_K128, dk + ks * KSTEP_K64, idesc_s, ks > 0);
+        if (x == nx - 1) ptx::umma_commit_elect(&emptyK[u % NS]);  // refill as soon as the unit's last scores exist
+      }
+      ptx::umma_commit_elect(&bar_s);
+      ROW_TRACE_M(i, 1);  // S(i) issued
+    };
+    if (NI > 0) issue_s(0);
+    for (int i = 0; i < NI; ++i) {
+      const int k = i / nx, x = i % nx;
+      ptx::mbar_wait(&ps_full, i & 1);  // P(i) written, S(i) drained
+      ptx::tc_fence_after();
+      ROW_TRACE_M(i, 2);  // ps_full(i) seen
+      for (int j = 0; j < T; ++j) {
+        const int u = k * T + j;
+        if (x == 0) ptx::mbar_wait(&fullV[u % NS], (u / NS) & 1);
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_after();
+        const uint64_t dp0 = desc_k128(pa + j * PT);
+        const uint64_t dv = desc_mn64(va + (u % NS) * TK);
+#pragma unroll
+        for (int ks = 0; ks < KT / 16; ++ks)
+          ptx::umma_bf16_elect(tmem + 256 + (i & 1) * HDP, dp0 + ks * KSTEP_K128, dv + ks * KSTEP_MN64, idesc_o, (j > 0 || ks > 0));
+        if (x == nx - 1) ptx::umma_commit_elect(&emptyV[u % NS]);
+      }
+      ptx::umma_commit_elect(&bar_o[i & 1]);
+      ROW_TRACE_M(i, 3);  // P V(i) issued
+      if (i + 1 < NI) issue_s(i + 1);
+    }
+  } else {
+    // ---------------- compute warps: two threads per row, each owns 32 of the 64 columns of every key tile ----------------
+    const int r = tid & 127, half = tid >> 7;
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + lane_off + half * 32, tO = tmem + 256 + lane_off;
+    // epilogue of item k (O(k) / l -> staging -> global). It runs one iteration LATE, after the softmax of item k + 1, so that the
+    // compute warps never wait for the P V products (O is double-buffered in TMEM for that).
+    auto epilogue = [&](int k, const Item& it, float inv) {
+      ptx::mbar_wait(&bar_o[k & 1], (k >> 1) & 1);
+      ptx::tc_fence_after();
+      ROW_TRACE_C(k + 1, 6);  // O(k) ready
+      if constexpr (tma_out) {
+        // staging tile in layout L1(128) (16-byte chunk c of row r at c * 2048 + r * 16: conflict-free writes), sent by ONE TMA
+        // store through the same kind of 4-D head-slice map the loads use; the padded chunk of a 72-wide head is clipped
+        if (tid == 0) ptx::tma_wait_group_read<0>();  // the previous store has finished reading the staging tile
+        compute_barrier();
+        uint32_t v[HH];
+        const uint32_t a = tO + (k & 1) * HDP + half * HH;
+        ptx::tmem_ld32(a, v);
+        if constexpr (HH == 40) ptx::tmem_ld8(a + 32, v + 32);
+        ptx::tmem_ld_wait();
+        uint8_t* st = reinterpret_cast<uint8_t*>(sStage);
+        (void)maps;
+#pragma unroll
+        for (int c = 0; c < HH / 8; ++c) {
+          float t8[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t8[j] = __uint_as_float(v[c * 8 + j]) * inv;
+          *reinterpret_cast<bf16x8*>(st + (half * (HH / 8) + c) * 2048 + r * 16) = pack8(t8);
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::tc_fence_before();
+        compute_barrier();
+        ROW_TRACE_C(k + 1, 7);  // staged
+        if (tid == 0) {
+          const int s0 = it.x * 128, sg = s0 < p.seg[0].len ? 0 : 1;
+          const int grow = it.b * p.seg[sg].len + (sg ? s0 - p.seg[0].len : s0);
+          ptx::tma_store_4d(&maps.m[sg][M_O128], st, 0, grow, 0, it.h);
+          ptx::tma_commit_group();
+        }
+      } else {
+        compute_barrier();  // the previous item's store_tile has finished reading the staging tile
+        tmem_half_to_stage<HDP>(tO + (k & 1) * HDP, sStage, r, half, inv);
+        ptx::tc_fence_before();
+        compute_barrier();
+        ROW_TRACE_C(k + 1, 7);  // staged
+        store_tile<HDP, O_OUT>(sStage, p, it.b, it.h, it.x * 128, tid);
+      }
+      ROW_TRACE_C(k + 1, 8);  // stored
+    };
+    Item it_prev{0, 0, 0};
+    float inv_prev = 0.f;
+    for (int k = 0; k < NI; ++k) {
+      const Item it = item_of(k);
+      ROW_TRACE_C(k, 0);  // iteration start
+      ptx::mbar_wait(&bar_s, k & 1);
+      ptx::tc_fence_after();
+      ROW_TRACE_C(k, 1);  // S(k) ready
+      float mx = -INFINITY, l0 = 0.f, l1 = 0.f;
+      float* sx = sX + (k & 1) * 512;  // double-buffered by item parity
+      float m, ms;
+      if constexpr (reread) {
+        // pass 1: row maximum over my columns of every key tile
+        for (int j = 0; j < T; ++j) {
+          uint32_t v[32];
+          ptx::tmem_ld32(tS + j * KT, v);
+          ptx::tmem_ld_wait();
+          float m0 = -INFINITY, m1 = -INFINITY;
+          if (tile_may_be_masked(p, j * KT)) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              m0 = fmaxf(m0, __uint_as_float(v[i]) + key_bias(p, it.b, j * KT + half * 32 + i));
+              m1 = fmaxf(m1, __uint_as_float(v[i + 1]) + key_bias(p, it.b, j * KT + half * 32 + i + 1));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) { m0 = fmaxf(m0, __uint_as_float(v[i])); m1 = fmaxf(m1, __uint_as_float(v[i + 1])); }
+          }
+          mx = fmaxf(mx, fmaxf(m0, m1));
+        }
+        ROW_TRACE_C(k, 2);
+        sx[half * 128 + r] = mx;
+        pair_barrier(1 + (warp & 3));
+        m = fmaxf(sx[r], sx[128 + r]);
+        ms = (m == -INFINITY) ? 0.f : m * p.scale_log2;
+        ROW_TRACE_C(k, 3);  // row maximum exchanged
+        // pass 2: exponentials, row sum, P -> shared memory (scores re-read from TMEM)
+        for (int j = 0; j < T; ++j) {
+          uint32_t v[32];
+          float e[32];
+          ptx::tmem_ld32(tS + j * KT, v);
+          ptx::tmem_ld_wait();
+          if (tile_may_be_masked(p, j * KT)) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) e[i] = ex2((__uint_as_float(v[i]) + key_bias(p, it.b, j * KT + half * 32 + i)) * p.scale_log2 - ms);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) e[i] = ex2(__uint_as_float(v[i]) * p.scale_log2 - ms);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            l0 += (e[i] + e[i + 1]) + (e[i + 2] + e[i + 3]);
+            l1 += (e[i + 4] + e[i + 5]) + (e[i + 6] + e[i + 7]);
+          }
+          store_bf16x32(sP + j * PT + r * 16, half * 32, e);
+        }
+      } else {
+      // the thread's 32 columns of every key tile, read from TMEM once (all loads in flight before the single wait)
+      float sv[4][32];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < T) ptx::tmem_ld32(tS + j * KT, reinterpret_cast<uint32_t*>(sv[j]));
+      ptx::tmem_ld_wait();
+      ROW_TRACE_C(k, 2);  // scores in registers
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < T) {
+          if (tile_may_be_masked(p, j * KT)) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sv[j][i] += key_bias(p, it.b, j * KT + half * 32 + i);
+          }
+          float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) { m0 = fmaxf(m0, sv[j][i]); m1 = fmaxf(m1, sv[j][i + 1]); }
+          mx = fmaxf(mx, fmaxf(m0, m1));
+        }
+      }
+      sx[half * 128 + r] = mx;
+      pair_barrier(1 + (warp & 3));
+      m = fmaxf(sx[r], sx[128 + r]);
+      ms = (m == -INFINITY) ? 0.f : m * p.scale_log2;
+      ROW_TRACE_C(k, 3);  // row maximum exchanged
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < T) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) sv[j][i] = ex2(sv[j][i] * p.scale_log2 - ms);
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            l0 += (sv[j][i] + sv[j][i + 1]) + (sv[j][i + 2] + sv[j][i + 3]);
+            l1 += (sv[j][i + 4] + sv[j][i + 5]) + (sv[j][i + 6] + sv[j][i + 7]);
+          }
+          store_bf16x32(sP + j * PT + r * 16, half * 32, sv[j]);
+        }
+      }
+      }
+      sx[256 + half * 128 + r] = l0 + l1;
+      ptx::fence_proxy_async_smem();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&ps_full);
+      ROW_TRACE_C(k, 4);  // P written, arrived
+      pair_barrier(1 + (warp & 3));
+      const float lt = sx[256 + r] + sx[256 + 128 + r];
+      const float inv = lt > 0.f ? 1.f / lt : 0.f;
+      const int row = it.x * 128 + r;
+      if (half == 0 && p.lse && row < p.S) p.lse[((int64_t)it.b * p.H + it.h) * p.S + row] = m * p.scale + logf(lt);
+      ROW_TRACE_C(k, 5);  // before the epilogue
+      if (!defer) epilogue(k, it, inv);
+      else if (k > 0) epilogue(k - 1, it_prev, inv_prev);
+      ROW_TRACE_C(k, 9);  // after the epilogue
+      it_prev = it;
+      inv_prev = inv;
+    }
+    if (defer && NI > 0) epilogue(NI - 1, it_prev, inv_prev);
+    if constexpr (tma_out) { if (tid == 0) ptx::tma_wait_group<0>(); }  // the last store has landed before the CTA exits
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp_u == 8) ptx::tmem_dealloc<512>(__shfl_sync(0xffffffffu, tmem_slot, 0));
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // backward: dQ (and D = rowsum(dO o O))
 // ---------------------------------------------------------------------------------------------------------
 template <int HDP, int RES, int NST, bool TMA>
@@ -1109,6 +1432,21 @@ static int fill_tc_params(attn_tc::Params& p, const char* who, const dlb_attn_se
     default: { constexpr int HDPV = 128; __VA_ARGS__; break; }          \
   }
 
+// launch one compile-time variant of the whole-row forward kernel (uses the locals of dlb_attn_fwd_tc)
+#define DLB_ROW_LAUNCH(FL)                                                                                                      \
+  case FL: {                                                                                                                    \
+    if (use_tma) {                                                                                                              \
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd_row_tc_kernel<HDPV, true, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      DLB_REQUIRE(e == cudaSuccess, (int)e, "attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                    \
+      attn_fwd_row_tc_kernel<HDPV, true, FL><<<grid_r, NT, smem, stream>>>(p, maps_r);                                          \
+    } else {                                                                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(attn_fwd_row_tc_kernel<HDPV, false, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      DLB_REQUIRE(e == cudaSuccess, (int)e, "attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                    \
+      attn_fwd_row_tc_kernel<HDPV, false, FL><<<grid_r, NT, smem, stream>>>(p, maps_r);                                         \
+    }                                                                                                                           \
+    break;                                                                                                                      \
+  }
+
 // Same contract as dlb_attn_fwd (attention.cu); tcgen05 implementation.
 DLB_EXPORT int dlb_attn_fwd_tc(const dlb_attn_seg* segs, int nseg, float* lse, const uint8_t* kmask, int mask_len, int B,
                                int H, int hd, float scale, cudaStream_t stream) {
@@ -1123,6 +1461,38 @@ DLB_EXPORT int dlb_attn_fwd_tc(const dlb_attn_seg* segs, int nseg, float* lse, c
     bool use_tma = true;
     for (int i = 0; i < nseg; ++i) use_tma = use_tma && segs[i].len > 0 && segs[i].len % 128 == 0;
     if (getenv("DLB_ATTN_NO_TMA") != nullptr) use_tma = false;  // tests: force the cp.async producers on TMA-eligible shapes
+    static const bool no_row = getenv("DLB_ATTN_NO_ROW") != nullptr;  // tests / A-B: force the per-tile online-softmax kernel
+    const int hdp = (hd + 15) / 16 * 16;
+    if (!no_row && T <= 4 && hdp <= 80) {  // whole-row softmax kernel: at most 256 keys, head dim <= 80
+      HDP_SWITCH_TC(hd, {
+        if constexpr (HDPV <= 80) {
+          const size_t smem = (size_t)2 * 128 * HDPV * 2 + (size_t)8 * 64 * HDPV * 2 + 4 * 16384 + (size_t)128 * HDPV * 2 + 1024 * 4;
+          static const int row_flags = getenv("DLB_ATTN_ROW_FLAGS") ? atoi(getenv("DLB_ATTN_ROW_FLAGS")) : 10;
+          const int nunits = (row_flags & 1) ? H * B : nitems;  // bit 0: one (sample, head) per work unit, its query tiles share K / V
+          const int grid_r = (T == 4 && nunits > sms) ? sms : nunits;  // persistent only when a unit fills both rings exactly
+          static BwdMaps maps_r;
+          if (use_tma) {
+            for (int i = 0; i < nseg; ++i) {
+              const dlb_attn_seg& g = segs[i];
+              const int64_t rows = (int64_t)B * g.len;
+              rc = head_map(&maps_r.m[i][M_Q128], g.q, rows, g.ldq, H, hd, 128, HDPV / 8);
+              if (!rc) rc = head_map(&maps_r.m[i][M_K64], g.k, rows, g.ldk, H, hd, 64, HDPV / 8);
+              if (!rc) rc = head_map(&maps_r.m[i][M_V64], g.v, rows, g.ldv, H, hd, 64, HDPV / 8);
+              if (!rc) rc = head_map(&maps_r.m[i][M_O128], g.o, rows, g.ldo, H, hd, 128, HDPV / 8);  // output tile (TMA store)
+              if (rc) return rc;
+            }
+          }
+          switch (row_flags) {
+            // same-box sweep of all variants (profiles/attn_r2/row_kernel_variants.md): 0.129-0.149 ms at the DiT-XL/2 geometry against
+            // 0.149 ms for the per-tile kernel; 10 (two-pass re-read + deferred epilogue, 79 registers) was the fastest
+            DLB_ROW_LAUNCH(8) DLB_ROW_LAUNCH(10) DLB_ROW_LAUNCH(14) DLB_ROW_LAUNCH(15)
+            default: DLB_REQUIRE(false, DLB_ERR_UNSUPPORTED, "attn_fwd_tc: row-kernel variant %d is not instantiated", row_flags);
+          }
+        }
+      });
+      dlb_count_launch();
+      return dlb_check_launch("attn_fwd_row_tc");
+    }
     HDP_SWITCH_TC(hd, {
       constexpr int RES_F = HDPV <= 80 ? 2 : 1, NST_F = HDPV <= 96 ? 4 : 3;
       const size_t smem = (size_t)RES_F * 128 * HDPV * 2 + (size_t)NST_F * 2 * 64 * HDPV * 2 + 16384 + (size_t)128 * HDPV * 2 + 1024 * 4;
