@@ -100,3 +100,48 @@ def test_tail_buckets_are_small():
     assert sizes[0] == 4096 and sizes[-1] == 512 and sizes[-2] == 512 and max(sizes) == 4096
     same = GradReducer(stores=[st], bucket_mb=mb(4096))
     assert [b.numel() for b in same.buckets] == [4096] * 4
+
+
+def test_piece_partition_of_a_bucket():
+    """peer-memory reducers: a bucket of n floats is cut into world pieces of one 64-aligned length (the last ones short or empty)
+    that tile it exactly — the offsets every rank derives must agree without communication"""
+    from diffulab_b200.training import _ALIGN, GradReducer
+
+    for world in (2, 3, 4, 8):
+        red = GradReducer.__new__(GradReducer)
+        red.world = world
+        for n in (64, 128, 64 * 7, 64 * 1000, 64 * 1001, 33_554_432, 37_748_736 + 64):
+            piece, lens = red._pieces(n)
+            assert piece % _ALIGN == 0 and len(lens) == world and sum(lens) == n
+            assert all(0 <= v <= piece for v in lens) and all(v % 4 == 0 for v in lens)
+            seen_short = False
+            for v in lens:  # full pieces first, then at most one short piece, then empty ones
+                if seen_short:
+                    assert v == 0
+                elif v < piece:
+                    seen_short = True
+
+
+def test_ema_schedule_host_logic():
+    """EMA.plan(): copy on the first update, nothing between multiples of update_every, copy up to update_after_step, then the
+    warm-up decay 1 - (1 + e / inv_gamma) ** -power clamped to [min_value, beta] (the rule restated in the class docstring)"""
+    from diffulab_b200.training import EMA
+
+    ema = EMA.__new__(EMA)
+    ema.beta, ema.update_after_step, ema.update_every = 0.999, 20, 10
+    ema.inv_gamma, ema.power, ema.min_value = 1.0, 2.0 / 3.0, 0.0
+    ema.step, ema.initted = 0, False
+    kinds = []
+    for _ in range(61):
+        kinds.append(ema.plan())
+        ema.advance()
+    assert kinds[0] == ("copy", 0.0)
+    assert all(k == ("skip", 0.0) for i, k in enumerate(kinds) if i % 10 != 0)
+    assert kinds[10] == ("copy", 0.0) and kinds[20] == ("copy", 0.0)
+    for step in (30, 40, 50, 60):
+        kind, decay = kinds[step]
+        e = step + 1 - 20 - 1
+        assert kind == "lerp" and abs(decay - min(1.0 - (1.0 + e) ** (-2.0 / 3.0), 0.999)) < 1e-12
+    assert kinds[30][1] < kinds[40][1] < kinds[50][1] < kinds[60][1] <= 0.999
+    ema.beta = 0.5
+    assert ema.get_current_decay(10_000) == 0.5 and ema.get_current_decay(21) == 0.0
